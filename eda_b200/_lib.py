@@ -1,0 +1,58 @@
+"""ctypes binding of libeda_b200.so (C ABI: include/eda_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the reference raises RuntimeError through TORCH_CHECK, pointnet2/_ext_src/include/utils.h:10-30,
+and exit(-1)s on launch errors, cuda_utils.h:35-44 — here launch errors also become RuntimeError).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "lib", "libeda_b200.so")
+
+_c_int, _c_float, _vp, _sz = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every prototype of include/eda_b200.h (tests check this)
+PROTOTYPES = {
+    "eda_version": (_c_int, []),
+    "eda_error_string": (ctypes.c_char_p, [_c_int]),
+    "eda_last_cuda_error": (ctypes.c_char_p, []),
+    "eda_fps_scratch_bytes": (_sz, [_c_int, _c_int, _c_int]),
+    "eda_furthest_point_sampling": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "eda_ball_query": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp]),
+    "eda_group_points": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_group_points_grad": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_gather_points": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_gather_points_grad": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_three_nn": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "eda_three_interpolate": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_three_interpolate_grad": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the library once.  Raises RuntimeError (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            f"eda_b200: {SO_PATH} not found — build it with `python -m eda_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU/PyTorch fallback for this path")
+    lib = ctypes.CDLL(SO_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        lib = load()
+        msg = lib.eda_error_string(rc).decode()
+        cuda = lib.eda_last_cuda_error().decode()
+        raise RuntimeError(f"eda_b200.{what} failed: {msg}" + (f" [{cuda}]" if cuda else ""))

@@ -1,0 +1,30 @@
+// Version / error-string entry points of the C ABI (include/eda_b200.h).
+#include <string.h>
+#include <stdio.h>
+#include "common.cuh"
+
+namespace eda {
+static thread_local char g_last_err[256] = "";
+void set_last_cuda_error(cudaError_t e, const char *where) {
+  snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace eda
+
+extern "C" {
+
+int eda_version(void) { return 100; }
+
+const char *eda_error_string(int code) {
+  switch (code) {
+    case EDA_OK: return "ok";
+    case EDA_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case EDA_ERR_CUDA_LAUNCH: return "CUDA launch/runtime error (see eda_last_cuda_error)";
+    case EDA_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    case EDA_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error code";
+  }
+}
+
+const char *eda_last_cuda_error(void) { return eda::g_last_err; }
+
+}  // extern "C"

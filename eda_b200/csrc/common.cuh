@@ -1,0 +1,123 @@
+// Shared helpers for the eda_b200 sm_100a kernels: error plumbing, PTX wrappers for
+// clusters / DSMEM / mbarrier / bulk (TMA) copies.  No torch types anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/eda_b200.h"
+
+namespace eda {
+
+void set_last_cuda_error(cudaError_t e, const char *where);
+
+// Call after every launch: records the error text and maps it to an ABI code (never exits,
+// unlike the reference's CUDA_CHECK_ERRORS(), pointnet2/_ext_src/include/cuda_utils.h:35-44).
+inline int check_launch(const char *where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, where);
+    return EDA_ERR_CUDA_LAUNCH;
+  }
+  return EDA_OK;
+}
+
+#define EDA_CUDA_TRY(expr, where)                       \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) {                            \
+      ::eda::set_last_cuda_error(_e, where);            \
+      return EDA_ERR_CUDA_LAUNCH;                       \
+    }                                                   \
+  } while (0)
+
+// The reference computes a*a + b*b + c*c as FMUL(b,b); FFMA(a,a,.); FFMA(c,c,.) (SASS of its
+// sm_100a build).  Intrinsics pin that order so nvcc cannot re-associate.
+__device__ __forceinline__ float sq3(float a, float b, float c) {
+  return __fmaf_rn(c, c, __fmaf_rn(a, a, __fmul_rn(b, b)));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Map a local shared-memory address to the same offset in CTA `rank` of the cluster.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init_cluster() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// Same wait, but with acquire at cluster scope: the data was written by a peer CTA (st.async).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// One-sided 16-byte / 4-byte stores into a peer CTA's shared memory that complete_tx on the
+// peer's mbarrier (DSMEM; no cluster-wide barrier needed on the critical path).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   remote_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t remote_addr, uint32_t a, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(a), "r"(remote_bar)
+               : "memory");
+}
+
+// 1-D bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP); completes on `bar`.
+// Requires 16-byte aligned src/dst and a byte count that is a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace eda

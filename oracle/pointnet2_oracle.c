@@ -1,0 +1,234 @@
+/*
+ * CPU ORACLE for the 9 pointnet2 `_ext` ops — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C restatement of the reference CUDA kernels under
+ * /root/reference/pointnet2/_ext_src/src (file:line cited per function).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product path (eda_b200/) never calls into this file.
+ *
+ * Parity status: the reference ships NO golden vectors for these ops (its only test is a
+ * gradcheck, pointnet2/pointnet2_test.py:18-30).  This oracle is pinned instead against
+ * outputs of the reference's own compiled `_ext` (oracle/_ref, built by oracle/build_ref.py)
+ * run on the B200 box: see tests/golden/ (fixtures + generating script) and
+ * tests/test_gpu_parity.py::test_oracle_matches_reference_ext.
+ *
+ * Float-op order is taken from the SASS of the reference build for sm_100a
+ * (nvcc 12.9 -O2, default -fmad=true):
+ *     a*a + b*b + c*c   ->   FMUL(b,b); FFMA(a,a,.); FFMA(c,c,.)
+ * i.e. fmaf(c,c, fmaf(a,a, b*b)).  Compile this file with -ffp-contract=off so that only
+ * the explicit fmaf() calls fuse.
+ *
+ * FPS is emulated literally: BS "lanes", lane t scanning k = t, t+BS, ... and the same
+ * shared-memory tree (sampling_gpu.cu:64-70,116-173), so the tie-break is the reference's
+ * by construction rather than by a derived ordering rule.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* include/cuda_utils.h:18-22 — same expression, same libm, so the same rounding quirks. */
+static int opt_n_threads(int work_size) {
+  const int pow_2 = (int)(log((double)work_size) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
+
+int oracle_opt_n_threads(int work_size) { return opt_n_threads(work_size); }
+
+static inline float sq3(float a, float b, float c) {
+  /* a*a + b*b + c*c as compiled: FMUL(b,b), FFMA(a,a,.), FFMA(c,c,.) */
+  return fmaf(c, c, fmaf(a, a, b * b));
+}
+
+/* sampling_gpu.cu:74-178 (kernel), :180-234 (block-size dispatch), sampling.cpp:70-91
+ * (idx zero-init, temp = 1e10).  dataset (b,n,3) -> idxs (b,m). */
+void oracle_furthest_point_sampling(int b, int n, int m, const float *dataset, int *idxs) {
+  if (m <= 0) return;
+  const int BS = opt_n_threads(n);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int bi = 0; bi < b; ++bi) {
+    const float *pts = dataset + (size_t)bi * n * 3;
+    int *out = idxs + (size_t)bi * m;
+    float *temp = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    float *dists = (float *)malloc(sizeof(float) * BS);
+    int *dists_i = (int *)malloc(sizeof(int) * BS);
+    for (int k = 0; k < n; ++k) temp[k] = (float)1e10;
+    memset(out, 0, sizeof(int) * (size_t)m);
+    int old = 0;
+    out[0] = old;
+    for (int j = 1; j < m; ++j) {
+      for (int t = 0; t < BS; ++t) { dists[t] = -1.0f; dists_i[t] = 0; }
+      const float x1 = pts[old * 3 + 0], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
+      for (int k = 0; k < n; ++k) { /* ascending k visits every lane's points in lane order */
+        const int t = k % BS;
+        const float x2 = pts[k * 3 + 0], y2 = pts[k * 3 + 1], z2 = pts[k * 3 + 2];
+        const float mag = sq3(x2, y2, z2);
+        if ((double)mag <= 1e-3) continue; /* double compare, NaN is processed */
+        const float d = sq3(x2 - x1, y2 - y1, z2 - z1);
+        const float d2 = fminf(d, temp[k]);
+        temp[k] = d2;
+        if (d2 > dists[t]) { dists_i[t] = k; dists[t] = d2; }
+      }
+      for (int s = BS / 2; s >= 1; s >>= 1) {
+        for (int t = 0; t < s; ++t) {
+          const float v1 = dists[t], v2 = dists[t + s];
+          const int i1 = dists_i[t], i2 = dists_i[t + s];
+          dists[t] = v1 > v2 ? v1 : (v2 > v1 ? v2 : v1); /* max(v1,v2) */
+          dists_i[t] = v2 > v1 ? i2 : i1;
+        }
+      }
+      old = dists_i[0];
+      out[j] = old;
+    }
+    free(temp); free(dists); free(dists_i);
+  }
+}
+
+/* ball_query_gpu.cu:14-49, ball_query.cpp:24-26 (idx zero-init).
+ * new_xyz (b,m,3), xyz (b,n,3) -> idx (b,m,nsample) */
+void oracle_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                       const float *xyz, int *idx) {
+  const float radius2 = radius * radius;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int bi = 0; bi < b; ++bi) {
+    const float *P = xyz + (size_t)bi * n * 3;
+    const float *Q = new_xyz + (size_t)bi * m * 3;
+    int *I = idx + (size_t)bi * m * nsample;
+    memset(I, 0, sizeof(int) * (size_t)m * nsample);
+    for (int j = 0; j < m; ++j) {
+      const float nx = Q[j * 3 + 0], ny = Q[j * 3 + 1], nz = Q[j * 3 + 2];
+      for (int k = 0, cnt = 0; k < n && cnt < nsample; ++k) {
+        const float d2 = sq3(nx - P[k * 3 + 0], ny - P[k * 3 + 1], nz - P[k * 3 + 2]);
+        if (d2 < radius2) {
+          if (cnt == 0)
+            for (int l = 0; l < nsample; ++l) I[j * nsample + l] = k;
+          I[j * nsample + cnt] = k;
+          ++cnt;
+        }
+      }
+    }
+  }
+}
+
+/* group_points_gpu.cu:13-33.  points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample) */
+void oracle_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                         const int *idx, float *out) {
+#pragma omp parallel for schedule(static)
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < npoints; ++j)
+        for (int k = 0; k < nsample; ++k) {
+          const int ii = idx[((size_t)bi * npoints + j) * nsample + k];
+          out[(((size_t)bi * c + l) * npoints + j) * nsample + k] = points[((size_t)bi * c + l) * n + ii];
+        }
+}
+
+/* group_points_gpu.cu:48-69 (atomicAdd scatter; summation order is unspecified in the
+ * reference — here it is (j,k) ascending), group_points.cpp:52-54 (zero-init). */
+void oracle_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                              const int *idx, float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * n);
+#pragma omp parallel for schedule(static)
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < npoints; ++j)
+        for (int k = 0; k < nsample; ++k) {
+          const int ii = idx[((size_t)bi * npoints + j) * nsample + k];
+          grad_points[((size_t)bi * c + l) * n + ii] +=
+              grad_out[(((size_t)bi * c + l) * npoints + j) * nsample + k];
+        }
+}
+
+/* sampling_gpu.cu:13-25.  points (b,c,n), idx (b,m) -> out (b,c,m) */
+void oracle_gather_points(int b, int c, int n, int m, const float *points, const int *idx, float *out) {
+#pragma omp parallel for schedule(static)
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < m; ++j)
+        out[((size_t)bi * c + l) * m + j] = points[((size_t)bi * c + l) * n + idx[(size_t)bi * m + j]];
+}
+
+/* sampling_gpu.cu:39-52 (atomicAdd scatter), sampling.cpp:52-54 (zero-init). */
+void oracle_gather_points_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * n);
+#pragma omp parallel for schedule(static)
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < m; ++j)
+        grad_points[((size_t)bi * c + l) * n + idx[(size_t)bi * m + j]] += grad_out[((size_t)bi * c + l) * m + j];
+}
+
+/* interpolate_gpu.cu:14-64.  unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3), idx (b,n,3).
+ * bests are doubles initialised to 1e40; the stored value is the (float) conversion. */
+void oracle_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx) {
+#pragma omp parallel for schedule(static)
+  for (int bi = 0; bi < b; ++bi) {
+    const float *U = unknown + (size_t)bi * n * 3;
+    const float *K = known + (size_t)bi * m * 3;
+    for (int j = 0; j < n; ++j) {
+      const float ux = U[j * 3 + 0], uy = U[j * 3 + 1], uz = U[j * 3 + 2];
+      double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+      int besti1 = 0, besti2 = 0, besti3 = 0;
+      for (int k = 0; k < m; ++k) {
+        const float d = sq3(ux - K[k * 3 + 0], uy - K[k * 3 + 1], uz - K[k * 3 + 2]);
+        if (d < best1) {
+          best3 = best2; besti3 = besti2; best2 = best1; besti2 = besti1; best1 = d; besti1 = k;
+        } else if (d < best2) {
+          best3 = best2; besti3 = besti2; best2 = d; besti2 = k;
+        } else if (d < best3) {
+          best3 = d; besti3 = k;
+        }
+      }
+      float *D = dist2 + ((size_t)bi * n + j) * 3;
+      int *I = idx + ((size_t)bi * n + j) * 3;
+      D[0] = best1 > FLT_MAX ? INFINITY : (float)best1;
+      D[1] = best2 > FLT_MAX ? INFINITY : (float)best2;
+      D[2] = best3 > FLT_MAX ? INFINITY : (float)best3;
+      I[0] = besti1; I[1] = besti2; I[2] = besti3;
+    }
+  }
+}
+
+/* interpolate_gpu.cu:77-106.  points (b,c,m), idx (b,n,3), weight (b,n,3) -> out (b,c,n).
+ * p1*w1 + p2*w2 + p3*w3 compiles to FMUL(p2,w2); FFMA(p1,w1,.); FFMA(p3,w3,.). */
+void oracle_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                              const float *weight, float *out) {
+#pragma omp parallel for schedule(static)
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l) {
+      const float *P = points + ((size_t)bi * c + l) * m;
+      for (int j = 0; j < n; ++j) {
+        const float *W = weight + ((size_t)bi * n + j) * 3;
+        const int *I = idx + ((size_t)bi * n + j) * 3;
+        out[((size_t)bi * c + l) * n + j] = fmaf(P[I[2]], W[2], fmaf(P[I[0]], W[0], P[I[1]] * W[1]));
+      }
+    }
+}
+
+/* interpolate_gpu.cu:121-148 (3 atomicAdds per element; order unspecified in the reference),
+ * interpolate.cpp:90-92 (zero-init).  grad_out (b,c,n) -> grad_points (b,c,m) */
+void oracle_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                   const float *weight, float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * m);
+#pragma omp parallel for schedule(static)
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l) {
+      float *G = grad_points + ((size_t)bi * c + l) * m;
+      for (int j = 0; j < n; ++j) {
+        const float *W = weight + ((size_t)bi * n + j) * 3;
+        const int *I = idx + ((size_t)bi * n + j) * 3;
+        const float g = grad_out[((size_t)bi * c + l) * n + j];
+        G[I[0]] += g * W[0];
+        G[I[1]] += g * W[1];
+        G[I[2]] += g * W[2];
+      }
+    }
+}
