@@ -27,6 +27,14 @@ PROTOTYPES = {
     "eda_three_nn": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "eda_three_interpolate": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_three_interpolate_grad": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_sa_mlp_packed_floats": (_sz, [_c_int, _c_int, _c_int, _c_int]),
+    "eda_sa_mlp_pack": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_sa_mlp_forward": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int,
+                                    _c_int, _c_int, _c_int, _c_int, _c_float, _c_int, _c_int, _vp, _vp, _vp]),
+    "eda_bn_finalize": (_c_int, [_vp, ctypes.c_double, _vp, _vp, _c_float, _c_float, _vp, _vp, _c_int, _c_int, _vp,
+                                 _vp, _vp, _vp, _vp]),
+    "eda_transpose_last2": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_selftest_umma": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
 }
 
 _lib = None

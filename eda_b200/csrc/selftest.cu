@@ -1,0 +1,92 @@
+// Hardware self-test of the tcgen05 building blocks in umma.cuh (descriptor encodings, the
+// chunk-major K-major shared-memory layout, TMEM lane/column addressing, A-from-TMEM).  One CTA
+// computes D[128 x N] = A[128 x K] * W[N x K]^T with kind::tf32.  Exposed through the C ABI so that
+// tests/test_gpu_umma.py can check it against a CPU tf32-rounded reference before any fused
+// kernel relies on these conventions.
+#include "umma.cuh"
+
+namespace eda {
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, int N, int K, int mode,
+                     float *__restrict__ D) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *sA = reinterpret_cast<float4 *>(smem_raw);  // [K/4][128]
+  float4 *sW = sA + (K / 4) * 128;                    // [K/4][N]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init_cluster();
+  }
+  for (int i = tid; i < (K / 4) * N; i += 128) {
+    const int c = i / N, n = i % N;
+    sW[i] = *reinterpret_cast<const float4 *>(W + (size_t)n * K + c * 4);
+  }
+  if (mode == 0) {
+    for (int c = 0; c < K / 4; ++c) sA[c * 128 + tid] = *reinterpret_cast<const float4 *>(A + (size_t)tid * K + c * 4);
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tbase = tmem_base_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32);
+  constexpr uint32_t kAcol = 256;  // A operand lives at columns [256, 256+K) in mode 1
+  if (mode == 1) {
+    for (int c0 = 0; c0 < K; c0 += 16) {
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(A[(size_t)tid * K + c0 + j]);
+      umma::tmem_st16(umma::tmem_addr(tbase, lane_base, kAcol + c0), v);
+    }
+    umma::tmem_st_wait();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+  }
+  if (tid == 0) {
+    const uint32_t idesc = umma::idesc_tf32(128, N);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint64_t bdesc = umma::smem_desc_kmajor_noswizzle(smem_u32(sW + ks * 2 * N), (uint32_t)N * 16u, 128u);
+      if (mode == 0) {
+        const uint64_t adesc = umma::smem_desc_kmajor_noswizzle(smem_u32(sA + ks * 2 * 128), 128u * 16u, 128u);
+        umma::mma_tf32_ss(tbase, adesc, bdesc, idesc, ks > 0);
+      } else {
+        umma::mma_tf32_ts(tbase, tbase + kAcol + ks * 8, bdesc, idesc, ks > 0);
+      }
+    }
+    umma::mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  umma::fence_after_thread_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    umma::tmem_ld16(umma::tmem_addr(tbase, lane_base, c0), v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[(size_t)tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
+}  // namespace
+}  // namespace eda
+
+extern "C" int eda_selftest_umma(const float *A, const float *W, int N, int K, int mode, float *D, void *stream) {
+  using namespace eda;
+  if (!A || !W || !D) return EDA_ERR_INVALID_ARGUMENT;
+  if (N < 16 || N > 256 || N % 16 || K < 16 || K > 128 || K % 16 || (mode != 0 && mode != 1))
+    return EDA_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(K / 4) * (128 + N) * sizeof(float4);
+  EDA_CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "selftest smem attr");
+  umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(A, W, N, K, mode, D);
+  return check_launch("umma_selftest_kernel");
+}

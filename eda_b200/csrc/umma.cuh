@@ -1,0 +1,124 @@
+// tcgen05 (5th-gen tensor core) / TMEM primitives for sm_100a, written as inline PTX.
+//
+// Conventions used by every kernel in this directory:
+//   * kind::tf32 operands: fp32 words in shared memory (or TMEM for A), fp32 accumulate in TMEM.
+//   * Shared-memory operands use the K-major, SWIZZLE_NONE canonical layout in "chunk-major" form:
+//         element (row r, k) lives at   base + (k/4) * LBO + (r/8) * 128 + (r%8) * 16 + (k%4) * 4
+//     i.e. an array  float4 tile[K/4][rows]  (LBO = rows*16 bytes, SBO = 128 bytes).  A core
+//     matrix is 8 rows x 16 bytes, stored contiguously; one MMA consumes K = 8 (two 16-byte
+//     chunks, LBO apart).  Row-contiguous float4 stores by 32 consecutive threads are
+//     bank-conflict free in this layout.
+//   * Accumulator / TMEM-A layout for M = 128, cta_group::1: TMEM lane = row, column = n (or k).
+#pragma once
+#include <stdint.h>
+#include "common.cuh"
+
+namespace eda {
+namespace umma {
+
+// ---- descriptors --------------------------------------------------------------------------
+// 64-bit shared-memory matrix descriptor (sm_100 format: version field = 1).
+__device__ __forceinline__ uint64_t smem_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                               uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);         // [0,14)  start address >> 4
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;   // [16,30) leading (K) byte offset >> 4
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;   // [32,46) stride (M/N, per 8 rows) byte offset >> 4
+  d |= (uint64_t)1 << 46;                              // [46,48) descriptor version = 1 (Blackwell)
+  // base_offset [49,52) = 0, lbo_mode [52] = 0, layout_type [61,64) = 0 (SWIZZLE_NONE)
+  return d;
+}
+
+// 32-bit instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4)                    // c_format = F32
+         | (2u << 7)                  // a_format = TF32
+         | (2u << 10)                 // b_format = TF32
+         | (0u << 15) | (0u << 16)    // a_major = K, b_major = K
+         | ((uint32_t)(N >> 3) << 17) // n_dim
+         | ((uint32_t)(M >> 4) << 24);// m_dim
+}
+
+// ---- TMEM allocation ------------------------------------------------------------------------
+// One full warp calls alloc; the base address lands in *smem_slot.  ncols: power of two >= 32.
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void fence_before_thread_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_thread_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- MMA issue (one thread) -------------------------------------------------------------------
+// D[tmem] (+)= A[smem] * B[smem]^T          A: 128 x 8 (K-major), B: N x 8 (K-major)
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T          A: 128 lanes x 8 columns of fp32
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// All MMAs issued so far by this thread arrive (once) on `bar` when they complete.  Implies
+// tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- TMEM <-> registers (warp-wide; warp w touches lanes [32*(w%4), 32*(w%4)+32)) -------------
+// 32 lanes x 16 consecutive columns: thread t gets lane base+t, columns c..c+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+          taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TMEM address = (lane << 16) | column
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, uint32_t lane, uint32_t col) {
+  return base + (lane << 16) + col;
+}
+
+}  // namespace umma
+}  // namespace eda

@@ -1,0 +1,196 @@
+"""Host side of the fused set-abstraction kernel (eda_sa_mlp_forward): parameter folding, the
+train-mode BatchNorm statistics passes, layout bookkeeping and the autograd boundary.
+
+Forward is entirely hand-written CUDA (pack -> [stats pass -> finalize] x3 in train mode -> fused
+gather+MLP+max-pool).  Backward (round 1): the grouped tensor is rebuilt with the unfused CUDA ops
+and differentiated by autograd — identical maths to the reference's backward
+(group_points_grad scatter, cuDNN/cuBLAS conv + BatchNorm backward); a fused backward is the next step.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+from . import _ext
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def transpose_last2(x):
+    """(B,R,C) contiguous -> (B,C,R) contiguous, on the current stream."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    B, R, C = x.shape
+    out = torch.empty((B, C, R), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().eda_transpose_last2(_p(x), B, R, C, _p(out), _stream(x.device))
+    _lib.check(rc, "transpose_last2")
+    return out
+
+
+def point_major(features):
+    """(B,C,N) -> a (B,N,C)-shaped tensor whose rows are contiguous, reusing the copy a previous fused
+    layer left behind when there is one."""
+    cached = getattr(features, "_eda_point_major", None)
+    if cached is not None and cached.shape == (features.size(0), features.size(2), features.size(1)) \
+            and cached.device == features.device:
+        return cached
+    t = features.transpose(1, 2)
+    if t.is_contiguous():
+        return t
+    return transpose_last2(features.contiguous())
+
+
+def fusable(C, widths, nsample):
+    if len(widths) != 3 or nsample is None:
+        return False
+    if nsample < 16 or (nsample & (nsample - 1)) != 0:
+        return False
+    return _lib.load().eda_sa_mlp_packed_floats(int(C), *[int(w) for w in widths]) > 0
+
+
+def _bn_scale_shift(lib, dev, stats, count, bn, conv_bias, C, training_update):
+    """scale/shift of one layer.  bn None: scale = None (1), shift = conv bias (or None)."""
+    if bn is None:
+        return None, (conv_bias.detach().contiguous() if conv_bias is not None else None)
+    scale = torch.empty(C, dtype=torch.float32, device=dev)
+    shift = torch.empty(C, dtype=torch.float32, device=dev)
+    momentum = bn.momentum
+    if training_update:
+        bn.num_batches_tracked += 1
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked.item())
+    rc = lib.eda_bn_finalize(_p(stats), float(count), _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps),
+                             float(momentum if momentum is not None else 0.0), _p(bn.running_mean),
+                             _p(bn.running_var), 1 if training_update else 0, C, _p(scale), _p(shift), None, None,
+                             _stream(dev))
+    _lib.check(rc, "bn_finalize")
+    return scale, shift
+
+
+def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, training):
+    """Runs the fused kernels.  layers = [(conv, bn_or_None)] * 3.  Returns out (B,M,C3) point-major."""
+    lib = _lib.load()
+    dev = xyz.device
+    B, N, _ = xyz.shape
+    M, S = idx.size(1), idx.size(2)
+    C = 0 if feat_pm is None else feat_pm.size(2)
+    widths = [conv.out_channels for conv, _ in layers]
+    nfl = lib.eda_sa_mlp_packed_floats(C, *widths)
+    assert nfl > 0
+    Ws = [conv.weight.detach().reshape(conv.out_channels, -1).contiguous() for conv, _ in layers]
+    assert Ws[0].size(1) == C + 3 and Ws[1].size(1) == widths[0] and Ws[2].size(1) == widths[1]
+    packed = torch.empty(nfl, dtype=torch.float32, device=dev)
+    feat_stride = 0
+    if feat_pm is not None:
+        assert feat_pm.stride(2) == 1 and feat_pm.stride(0) == N * feat_pm.stride(1)
+        feat_stride = feat_pm.stride(1)
+    stream = _stream(dev)
+    scales, shifts = [None] * 3, [None] * 3
+    count = float(B) * M * S
+
+    def pack(nlayers):
+        rc = lib.eda_sa_mlp_pack(_p(Ws[0]), _p(Ws[1]), _p(Ws[2]), _p(scales[0]), _p(scales[1]), _p(scales[2]), C,
+                                 *widths, nlayers, _p(packed), stream)
+        _lib.check(rc, "sa_mlp_pack")
+
+    def run(stats_layer, out, stats):
+        rc = lib.eda_sa_mlp_forward(_p(xyz), _p(new_xyz), _p(feat_pm), feat_stride, _p(idx), _p(packed),
+                                    _p(shifts[0]), _p(shifts[1]), _p(shifts[2]), B, N, M, S, C, *widths,
+                                    float(radius), 1 if normalize_xyz else 0, stats_layer, _p(out), _p(stats), stream)
+        _lib.check(rc, "sa_mlp_forward")
+
+    with torch.cuda.device(dev):
+        for l, (conv, bn) in enumerate(layers):
+            batch_stats = training and bn is not None
+            if batch_stats:
+                # train-mode BatchNorm: batch statistics of layer l's conv output, layers < l already final
+                stats = torch.empty(2 * widths[l], dtype=torch.float32, device=dev)
+                pack(l + 1)
+                run(l + 1, None, stats)
+                scales[l], shifts[l] = _bn_scale_shift(lib, dev, stats, count, bn, conv.bias, widths[l], True)
+            else:
+                scales[l], shifts[l] = _bn_scale_shift(lib, dev, None, 0.0, bn, conv.bias, widths[l], False)
+        out = torch.empty((B, M, widths[2]), dtype=torch.float32, device=dev)
+        pack(3)
+        run(0, out, None)
+    return out
+
+
+def _composed(xyz, new_xyz, features, idx, params, has_bn, radius, normalize_xyz, use_batch_stats, running, eps):
+    """Unfused, differentiable restatement (used for the backward pass only)."""
+    from . import pointnet2_utils as pu
+
+    grouped_xyz = pu.grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
+    grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+    if normalize_xyz:
+        grouped_xyz = grouped_xyz / radius
+    x = grouped_xyz if features is None else torch.cat([grouped_xyz, pu.grouping_operation(features, idx)], dim=1)
+    it = iter(params)
+    for l in range(3):
+        w = next(it)
+        bias = next(it)
+        x = F.conv2d(x, w, bias)
+        if has_bn[l]:
+            g, b = next(it), next(it)
+            if use_batch_stats:
+                x = F.batch_norm(x, None, None, g, b, True, 0.0, eps[l])
+            else:
+                x = F.batch_norm(x, running[l][0], running[l][1], g, b, False, 0.0, eps[l])
+        x = F.relu(x)
+    return F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+
+
+class FusedSAFunction(torch.autograd.Function):
+    """new_features (B,C3,M) = maxpool(MLP(group(xyz, features, idx)))."""
+
+    @staticmethod
+    def forward(ctx, module, xyz, new_xyz, features, idx, *params):
+        layers = module.mlp_module.fusable_layers()
+        feat_pm = None if features is None else point_major(features)
+        training = module.training
+        has_bn = [bn is not None for _, bn in layers]
+        # BN buffers as they are BEFORE this forward (eval-mode backward needs the ones that were used)
+        ctx.running = [(bn.running_mean.clone(), bn.running_var.clone()) if (bn is not None and not training) else None
+                       for _, bn in layers]
+        out_pm = sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, module.radius, module.normalize_xyz, training)
+        out = transpose_last2(out_pm)
+        ctx.save_for_backward(xyz, new_xyz, features, idx, *params)
+        ctx.meta = (has_bn, float(module.radius), bool(module.normalize_xyz), training,
+                    [bn.eps if bn is not None else 0.0 for _, bn in layers])
+        ctx.mark_non_differentiable(out_pm)
+        return out, out_pm
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_pm=None):
+        xyz, new_xyz, features, idx, *params = ctx.saved_tensors
+        has_bn, radius, normalize_xyz, training, eps = ctx.meta
+        with torch.enable_grad():
+            f = None if features is None else features.detach().requires_grad_(ctx.needs_input_grad[3])
+            ps = [None if p is None else p.detach().requires_grad_(True) for p in params]
+            out = _composed(xyz, new_xyz, f, idx, ps, has_bn, radius, normalize_xyz, training, ctx.running, eps)
+            wanted = [t for t in ([f] + ps) if t is not None and t.requires_grad]
+            grads = torch.autograd.grad(out, wanted, grad_out, allow_unused=True)
+        gmap = {id(t): g for t, g in zip(wanted, grads)}
+        gf = gmap.get(id(f)) if f is not None else None
+        gps = [gmap.get(id(p)) if p is not None else None for p in ps]
+        return (None, None, None, gf, None, *gps)
+
+
+def sa_params(layers):
+    """Flat parameter list in the order _composed consumes it: per layer conv.weight, conv.bias (or None),
+    then bn.weight, bn.bias when the layer has a BatchNorm."""
+    out = []
+    for conv, bn in layers:
+        out.append(conv.weight)
+        out.append(conv.bias)
+        if bn is not None:
+            out.append(bn.weight)
+            out.append(bn.bias)
+    return out

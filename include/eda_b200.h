@@ -98,6 +98,53 @@ EDA_API int eda_three_interpolate(const float *points, const int *idx, const flo
 EDA_API int eda_three_interpolate_grad(const float *grad_out, const int *idx, const float *weight, int B,
                                int C, int n, int m, float *grad_points, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused set-abstraction grouped MLP: neighbour gather + centre/normalise + concat + 3 x [1x1 conv ->
+ * BatchNorm -> ReLU] + max over nsample, one kernel, tcgen05 kind::tf32 with fp32 accumulation.
+ * Replaces the composition QueryAndGroup.forward (minus the ball query itself)
+ *   pointnet2/pointnet2_utils.py:344-359  ->  SharedMLP  pointnet2/pytorch_utils.py:11-36,67-120
+ *   ->  F.max_pool2d  pointnet2/pointnet2_modules.py:251-267.
+ *
+ * Shapes: xyz (B,N,3), new_xyz (B,M,3), idx (B,M,S) from eda_ball_query, features POINT-major: row
+ * (b,i) = feat + (b*N+i)*feat_stride, C floats (C may be 0, feat NULL); conv weights W1 (C1,3+C) with
+ * the reference's column order [xyz | features], W2 (C2,C1), W3 (C3,C2), no bias (pytorch_utils.py:87).
+ * Supported: C1,C2 <= 128, C3 <= 256, all multiples of 16; S a power of two >= 16.  Anything else
+ * returns EDA_ERR_UNSUPPORTED and the host composes the unfused ops.
+ *
+ * eda_sa_mlp_pack: folds per-output-channel `scale_l` (NULL = 1) into W_l, rounds to tf32 and lays the
+ *   first `nlayers` layers out in the streaming order of the kernel; `packed` holds
+ *   eda_sa_mlp_packed_floats(C,C1,C2,C3) floats (0 = unsupported dims).
+ * eda_sa_mlp_forward, stats_layer == 0: out (B,M,C3) POINT-major = max_s relu(conv3'(relu(conv2'(relu(
+ *   conv1'(x) + shift1)) + shift2)) + shift3)   (zero-filled by the callee).
+ *   stats_layer == l in 1..3: layers < l as above, layer l's conv output is only reduced to
+ *   stats[0:C_l] = sum, stats[C_l:2C_l] = sum of squares over all B*M*S rows (zero-filled by the
+ *   callee) — the batch statistics train-mode BatchNorm2d needs.
+ * eda_bn_finalize: (sum, sumsq, count) + gamma/beta/eps -> scale = gamma/sqrt(var+eps),
+ *   shift = beta - mean*scale; optionally updates running_mean/var with `momentum` (unbiased variance),
+ *   as nn.BatchNorm2d does in training.  count <= 0: use running_mean/var instead (eval mode).
+ *   save_mean / save_invstd may be NULL.
+ * eda_transpose_last2: (B,R,C) -> (B,C,R). */
+EDA_API size_t eda_sa_mlp_packed_floats(int C, int C1, int C2, int C3);
+EDA_API int eda_sa_mlp_pack(const float *W1, const float *W2, const float *W3, const float *scale1,
+                            const float *scale2, const float *scale3, int C, int C1, int C2, int C3, int nlayers,
+                            float *packed, void *stream);
+EDA_API int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const float *feat, int feat_stride,
+                               const int *idx, const float *packed, const float *shift1, const float *shift2,
+                               const float *shift3, int B, int N, int M, int S, int C, int C1, int C2, int C3,
+                               float radius, int normalize_xyz, int stats_layer, float *out, float *stats,
+                               void *stream);
+EDA_API int eda_bn_finalize(const float *stats, double count, const float *gamma, const float *beta, float eps,
+                            float momentum, float *running_mean, float *running_var, int update_running, int C,
+                            float *scale, float *shift, float *save_mean, float *save_invstd, void *stream);
+EDA_API int eda_transpose_last2(const float *in, int B, int R, int C, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Hardware self-test of the tcgen05/TMEM building blocks the fused kernels rely on (no reference
+ * counterpart).  D[128,N] = A[128,K] * W[N,K]^T with kind::tf32, fp32 accumulate, one CTA.
+ * mode 0: A from shared memory; mode 1: A from tensor memory.  N % 16 == 0, 16 <= N <= 256;
+ * K % 16 == 0, 16 <= K <= 128. */
+EDA_API int eda_selftest_umma(const float *A, const float *W, int N, int K, int mode, float *D, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
