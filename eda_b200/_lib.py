@@ -17,6 +17,7 @@ PROTOTYPES = {
     "eda_version": (_c_int, []),
     "eda_error_string": (ctypes.c_char_p, [_c_int]),
     "eda_last_cuda_error": (ctypes.c_char_p, []),
+    "eda_launch_count": (ctypes.c_ulonglong, []),
     "eda_fps_scratch_bytes": (_sz, [_c_int, _c_int, _c_int]),
     "eda_furthest_point_sampling": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "eda_ball_query": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp]),

@@ -8,9 +8,13 @@ static thread_local char g_last_err[256] = "";
 void set_last_cuda_error(cudaError_t e, const char *where) {
   snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 }  // namespace eda
 
 extern "C" {
+
+unsigned long long eda_launch_count(void) { return __atomic_load_n(&eda::g_launches, __ATOMIC_RELAXED); }
 
 int eda_version(void) { return 100; }
 

@@ -6,19 +6,22 @@
 // first hit, all zeros for an empty ball.
 //
 // The reference gives each centre to ONE thread of ONE block per scene and walks xyz in
-// global memory.  Here a CTA owns kWarps centres and streams the scene's xyz through shared
+// global memory.  Here a CTA owns kBqWarps * kQ centres and streams the scene's xyz through shared
 // memory in tiles fetched by the TMA engine (1-D cp.async.bulk, double buffered, mbarrier
-// completion).  One warp per centre tests 128 points per step (4 per lane); hits are rare, so
-// the common step is branch-free, and the ordered compaction (ballot + prefix popcount)
-// keeps "first nsample in index order" exact.  The row is staged in smem and written once,
-// coalesced, including the padding — idx needs no zero-fill by the caller.
+// completion).  The kernel is bound by instruction issue, so the inner loop is register-tiled: a
+// lane loads a point once and tests it against the warp's kQ = 4 centres with packed fp32x2 math
+// (two centres per FADD2 / FMUL2 / FFMA2), 64 points per warp step.  Hits are rare, so the common
+// step is branch-free; the ordered compaction (ballot + prefix popcount) keeps "first nsample in
+// index order" exact.  Rows are staged in smem and written once, coalesced, including the padding —
+// idx needs no zero-fill by the caller.
 #include "common.cuh"
 
 namespace eda {
 namespace {
 
-constexpr int kBqWarps = 16;
+constexpr int kBqWarps = 8;
 constexpr int kBqThreads = kBqWarps * 32;
+constexpr int kQ = 4;        // centres per warp
 constexpr int kTile = 2048;  // points per smem tile: 24 KB, x2 buffers
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -28,20 +31,29 @@ ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *tile0 = reinterpret_cast<float *>(smem_raw);
   float *tile1 = tile0 + kTile * 3;
-  int *hits = reinterpret_cast<int *>(tile1 + kTile * 3);  // [kBqWarps][nsample]
+  int *hits = reinterpret_cast<int *>(tile1 + kTile * 3);  // [kBqWarps][kQ][nsample]
   __shared__ __align__(8) uint64_t full[2];
 
   const int b = blockIdx.y;
   const float *__restrict__ xyz = xyz_all + (size_t)b * N * 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int centre = blockIdx.x * kBqWarps + warp;
-  const bool active = centre < M;
-  int *myhits = hits + warp * nsample;
+  const int centre0 = (blockIdx.x * kBqWarps + warp) * kQ;
+  int *myhits = hits + warp * kQ * nsample;
 
-  float cx = 0.f, cy = 0.f, cz = 0.f;
-  if (active) {
-    const float *c = new_xyz_all + ((size_t)b * M + centre) * 3;
-    cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
+  // centre coordinates as pairs: (c0,c1) and (c2,c3); centres past M start "already full", their hits are ignored
+  float2 cx[2], cy[2], cz[2];
+  int cnt[kQ];
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) {
+    const int c = centre0 + q;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (c < M) {
+      const float *p = new_xyz_all + ((size_t)b * M + c) * 3;
+      x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    }
+    if (q & 1) { cx[q >> 1].y = x; cy[q >> 1].y = y; cz[q >> 1].y = z; }
+    else       { cx[q >> 1].x = x; cy[q >> 1].x = y; cz[q >> 1].x = z; }
+    cnt[q] = (c < M) ? 0 : nsample;  // "already full": its hits are ignored
   }
   const int ntiles = (N + kTile - 1) / kTile;
   auto tile_pts = [&](int t) { return min(kTile, N - t * kTile); };
@@ -62,8 +74,13 @@ ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict
     }
   }
 
-  int cnt = 0;  // warp-uniform number of hits so far (may exceed nsample in the last step)
-  bool done = !active;
+  auto all_full = [&]() {
+    bool f = true;
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) f = f && (cnt[q] >= nsample);
+    return f;
+  };
+  bool done = all_full();
   for (int t = 0; t < ntiles; ++t) {
     const int buf = t & 1;
     float *tile = buf ? tile1 : tile0;
@@ -78,30 +95,46 @@ ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict
     }
     if (!done) {
       const int kbase = t * kTile;
-      for (int base = 0; base < npts && cnt < nsample; base += 128) {
-        bool hit[4];
+      for (int base = 0; base < npts && !done; base += 64) {
+        bool hit[2][kQ];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
           const int k = base + u * 32 + lane;
           const int kk = min(k, npts - 1);
           const float x = tile[kk * 3 + 0], y = tile[kk * 3 + 1], z = tile[kk * 3 + 2];
-          // (new_x - x)^2 + ... as the reference compiles it: FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.)
-          const float d2 = sq3(__fsub_rn(cx, x), __fsub_rn(cy, y), __fsub_rn(cz, z));
-          hit[u] = (k < npts) && (d2 < r2);
-        }
-        if (__any_sync(kFull, hit[0] | hit[1] | hit[2] | hit[3])) {
+          const float2 mx = make_float2(-x, -x), my = make_float2(-y, -y), mz = make_float2(-z, -z);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const unsigned mask = __ballot_sync(kFull, hit[u]);
-            if (hit[u]) {
-              const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-              if (pos < nsample) myhits[pos] = kbase + base + u * 32 + lane;
-            }
-            cnt += __popc(mask);
+          for (int h = 0; h < 2; ++h) {
+            // (new_x - x)^2 + ... as the reference compiles it: FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.)
+            const float2 dx = __fadd2_rn(cx[h], mx), dy = __fadd2_rn(cy[h], my), dz = __fadd2_rn(cz[h], mz);
+            const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+            hit[u][2 * h + 0] = (k < npts) && (d2.x < r2);
+            hit[u][2 * h + 1] = (k < npts) && (d2.y < r2);
           }
         }
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) any = any || hit[u][q];
+        if (__any_sync(kFull, any)) {
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const unsigned mask = __ballot_sync(kFull, hit[u][q]);
+              if (mask && cnt[q] < nsample) {
+                if (hit[u][q]) {
+                  const int pos = cnt[q] + __popc(mask & ((1u << lane) - 1u));
+                  if (pos < nsample) myhits[q * nsample + pos] = kbase + base + u * 32 + lane;
+                }
+                cnt[q] = min(nsample, cnt[q] + __popc(mask));
+              }
+            }
+          }
+          done = all_full();
+        }
       }
-      done = cnt >= nsample;
     }
     // every warp is past this tile -> its buffer can be refilled; stop early when all are done
     const int all_done = __syncthreads_and(done ? 1 : 0);
@@ -116,12 +149,16 @@ ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict
     }
   }
 
-  if (active) {
-    __syncwarp();
-    int *out = idx_all + ((size_t)b * M + centre) * nsample;
-    const int have = min(cnt, nsample);
-    const int first = have > 0 ? myhits[0] : 0;  // ball_query_gpu.cu:38-42 pads with the first hit
-    for (int s = lane; s < nsample; s += 32) out[s] = s < have ? myhits[s] : first;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) {
+    const int c = centre0 + q;
+    if (c < M) {
+      int *out = idx_all + ((size_t)b * M + c) * nsample;
+      const int have = cnt[q];
+      const int first = have > 0 ? myhits[q * nsample] : 0;  // ball_query_gpu.cu:38-42 pads with the first hit
+      for (int s = lane; s < nsample; s += 32) out[s] = s < have ? myhits[q * nsample + s] : first;
+    }
   }
 }
 
@@ -139,7 +176,7 @@ extern "C" int eda_ball_query(const float *new_xyz, const float *xyz, int B, int
     EDA_CUDA_TRY(cudaMemsetAsync(idx, 0, (size_t)B * M * nsample * sizeof(int), st), "ball_query memset");
     return EDA_OK;
   }
-  const size_t smem = (size_t)2 * kTile * 3 * sizeof(float) + (size_t)kBqWarps * nsample * sizeof(int);
+  const size_t smem = (size_t)2 * kTile * 3 * sizeof(float) + (size_t)kBqWarps * kQ * nsample * sizeof(int);
   if (smem > 200 * 1024) return EDA_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     EDA_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -147,7 +184,7 @@ extern "C" int eda_ball_query(const float *new_xyz, const float *xyz, int B, int
   // bulk copies need 16-byte aligned sources and sizes: every scene/tile starts at a multiple of 4 points
   const int use_tma = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(xyz) & 15u) == 0);
   const float r2 = radius * radius;  // f32 product, ball_query_gpu.cu:27
-  dim3 grid((unsigned)((M + kBqWarps - 1) / kBqWarps), (unsigned)B);
+  dim3 grid((unsigned)((M + kBqWarps * kQ - 1) / (kBqWarps * kQ)), (unsigned)B);
   ball_query_kernel<<<grid, kBqThreads, smem, st>>>(new_xyz, xyz, N, M, r2, nsample, use_tma, idx);
   return check_launch("ball_query_kernel");
 }

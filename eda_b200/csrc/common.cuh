@@ -8,10 +8,12 @@
 namespace eda {
 
 void set_last_cuda_error(cudaError_t e, const char *where);
+void count_launches(int n);  // bookkeeping for eda_launch_count() (bench.py's gpu_launches)
 
 // Call after every launch: records the error text and maps it to an ABI code (never exits,
 // unlike the reference's CUDA_CHECK_ERRORS(), pointnet2/_ext_src/include/cuda_utils.h:35-44).
-inline int check_launch(const char *where) {
+inline int check_launch(const char *where, int kernels = 1) {
+  count_launches(kernels);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_cuda_error(e, where);

@@ -6,30 +6,32 @@
 //
 // Here one thread-block CLUSTER owns a scene.  Every thread keeps its <= P points (xyz and
 // running minimum) in registers for the whole kernel; an iteration is
-//     P register updates -> warp arg-max (2x redux.sync) -> CTA arg-max (1 bar.sync)
+//     P register updates (packed fp32x2 math: FADD2 / FMUL2 / FFMA2, two points per instruction)
+//     -> warp arg-max (2x redux.sync) -> CTA arg-max (1 bar.sync, 8 warps)
 //     -> one-sided DSMEM exchange of the CTA winners (st.async + mbarrier complete_tx,
 //        no cluster barrier) -> every warp picks the cluster winner and its coordinates.
-// The winner's xyz travels with its key, so nothing touches L2/HBM inside the loop.
+// The winner's xyz travels with its key, so nothing touches L2/HBM inside the loop.  The loop is
+// bound by instruction issue and by the reduction latency chain, so CTAs are kept small (256
+// threads, many points per thread): the per-warp reduction overhead is paid by 8 warps, not 32.
 //
 // Bit-exactness.  The reference's result depends on its thread layout: lane t of BS lanes
 // scans k = t, t+BS, ... keeping the first strict maximum, then a shared-memory tree keeps
 // the LOWER slot on ties.  That is the total order
 //     (d2 desc, bitrev_{log2 BS}(k mod BS) asc, k div BS asc)            [BS = opt_n_threads(N)]
-// (verified against the literal emulation in oracle/pointnet2_oracle.c).
-// Any decomposition that reduces with this order gives the same index.  A thread here holds
-// points of ONE reference lane in ascending k, so its local strict-'>' scan is already in
-// order, and cross-thread reduction compares (d2 bits, ~code) with
-//     code = bitrev(k mod BS) << 23 | (k div BS).
-// Points the reference skips (|p|^2 <= 1e-3, compared in double) and padding get a running
-// minimum of -1: fminf keeps it at -1 forever and -1 never beats the initial best of -1.
+// (verified against the literal emulation in oracle/pointnet2_oracle.c and against the
+// reference's compiled kernel, tests/golden).  Any decomposition that reduces with this order gives
+// the same index.  A thread here visits its points in ascending order of
+//     code = bitrev(k mod BS) << 23 | (k div BS)
+// so its local strict-'>' scan already honours the order, and cross-thread reduction compares
+// (d2 bits, ~code).  Points the reference skips (|p|^2 <= 1e-3, compared in double) and padding get
+// a running minimum of -1: fminf keeps it at -1 forever and -1 never beats the initial best of -1.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace eda {
 namespace {
 
-constexpr int kThreads = 1024;
-constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct Key {
@@ -45,6 +47,13 @@ struct __align__(16) Cand {  // what one CTA tells its peers: 20 payload bytes
   int pad[3];
 };
 
+struct __align__(16) WarpCand {  // a warp's winner: key + where its coordinates sit in s_xyz
+  int hi;
+  unsigned lo;
+  int slot;
+  int pad;
+};
+
 __device__ __forceinline__ unsigned bitrev(unsigned v, int lb) { return lb ? (__brev(v) >> (32 - lb)) : 0u; }
 
 // Warp arg-max under the reference order.  Two redux.sync instead of a 5-step shuffle tree.
@@ -55,11 +64,36 @@ __device__ __forceinline__ Key warp_argmax(int hi, unsigned lo) {
   return k;
 }
 
-template <int P, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
-fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, int *__restrict__ idxs_all) {
-  extern __shared__ __align__(16) float s_xyz[];  // [P][kThreads][3] copy of this CTA's points
-  __shared__ Key s_warp[2][kWarps];
+// Where a thread's jj-th point lives.  G = threads per scene, BS = 1 << lb reference lanes,
+// rows = ceil(N / BS).
+//   G >= BS : thread g serves lane g mod BS, rows (g div BS) + jj * (G / BS)
+//   G <  BS : thread g serves lanes g + u*G (u < BS/G), all rows of one lane before the next, lanes
+//             taken in ascending bit-reversed order (u = bitrev_q(jj div rows))
+// Either way the thread's codes ascend with jj.
+struct Layout {
+  int lb, lG, rows;  // log2 BS, log2 G
+  // returns false for a padding slot (no such point); L/row are then only a unique-ish placeholder
+  __device__ __forceinline__ bool locate(unsigned g, int jj, unsigned &L, unsigned &row) const {
+    if (lG >= lb) {
+      L = g & ((1u << lb) - 1u);
+      row = (g >> lb) + ((unsigned)jj << (lG - lb));
+      return row < (unsigned)rows;
+    }
+    const int q = lb - lG;
+    const unsigned up = (unsigned)jj / (unsigned)rows;
+    row = (unsigned)jj - up * (unsigned)rows;
+    L = g + (bitrev(up & ((1u << q) - 1u), q) << lG);
+    return up < (1u << q);
+  }
+};
+
+template <int P2, int CL, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, int *__restrict__ idxs_all) {
+  constexpr int P = 2 * P2;
+  constexpr int kWarps = T / 32;
+  extern __shared__ __align__(16) float s_xyz[];  // [P][T][3] copy of this CTA's points
+  __shared__ WarpCand s_warp[2][kWarps];
   __shared__ Cand s_cta[2][CL];
   __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -69,28 +103,35 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, int 
   int *__restrict__ idxs = idxs_all + (size_t)scene * m;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned g = rank * kThreads + tid;              // thread id within the cluster
-  const unsigned L = g & ((1u << lb) - 1u);              // reference lane this thread serves
-  const unsigned rg = g >> lb;                           // row group
-  const int lrg = 10 + (CL == 1 ? 0 : CL == 2 ? 1 : CL == 4 ? 2 : CL == 8 ? 3 : 4) - lb;  // log2(RG)
-  const unsigned codeL = bitrev(L, lb) << 23;
+  const unsigned g = rank * T + tid;  // thread id within the scene
+  const int lb = lay.lb;
 
-  float px[P], py[P], pz[P], t[P];
+  float2 px[P2], py[P2], pz[P2], t[P2];
 #pragma unroll
-  for (int j = 0; j < P; ++j) {
-    const unsigned row = rg + ((unsigned)j << lrg);
-    const long long k = (long long)L + ((long long)row << lb);
-    float x = 0.f, y = 0.f, z = 0.f, tt = -1.0f;
-    if (k < N) {
-      x = __ldg(xyz + k * 3 + 0);
-      y = __ldg(xyz + k * 3 + 1);
-      z = __ldg(xyz + k * 3 + 2);
-      const float mag = sq3(x, y, z);
-      tt = ((double)mag <= 1e-3) ? -1.0f : (float)1e10;  // sampling_gpu.cu:105-106, sampling.cpp:78-80
+  for (int i = 0; i < P2; ++i) {
+    float cx[2], cy[2], cz[2], ct[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int jj = 2 * i + e;
+      unsigned L, row;
+      const bool slot_ok = lay.locate(g, jj, L, row);
+      const long long k = (long long)L + ((long long)row << lb);
+      float x = 0.f, y = 0.f, z = 0.f, tt = -1.0f;
+      if (slot_ok && k < N) {
+        x = __ldg(xyz + k * 3 + 0);
+        y = __ldg(xyz + k * 3 + 1);
+        z = __ldg(xyz + k * 3 + 2);
+        const float mag = sq3(x, y, z);
+        tt = ((double)mag <= 1e-3) ? -1.0f : (float)1e10;  // sampling_gpu.cu:105-106, sampling.cpp:78-80
+      }
+      cx[e] = x; cy[e] = y; cz[e] = z; ct[e] = tt;
+      float *s = s_xyz + ((size_t)jj * T + tid) * 3;
+      s[0] = x; s[1] = y; s[2] = z;
     }
-    px[j] = x; py[j] = y; pz[j] = z; t[j] = tt;
-    float *s = s_xyz + ((size_t)j * kThreads + tid) * 3;
-    s[0] = x; s[1] = y; s[2] = z;
+    px[i] = make_float2(cx[0], cx[1]);
+    py[i] = make_float2(cy[0], cy[1]);
+    pz[i] = make_float2(cz[0], cz[1]);
+    t[i] = make_float2(ct[0], ct[1]);
   }
   const float p0x = __ldg(xyz + 0), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
   float ox = p0x, oy = p0y, oz = p0z;
@@ -111,84 +152,100 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, int 
     const int buf = it & 1;
     if (CL > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], CL * 20);
 
-    // ---- distance update, thread-local arg-max (first strict maximum, ascending k) ----
+    // ---- distance update, thread-local arg-max (first strict maximum, ascending code) ----
+    // (p - o) as p + (-o): same rounding; two points per FADD2 / FMUL2 / FFMA2
+    const float2 nx = make_float2(-ox, -ox), ny = make_float2(-oy, -oy), nz = make_float2(-oz, -oz);
     float best = -1.0f;
     int bj = 0;
 #pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const float d = sq3(__fsub_rn(px[j], ox), __fsub_rn(py[j], oy), __fsub_rn(pz[j], oz));
-      const float d2 = fminf(d, t[j]);
-      t[j] = d2;
-      if (d2 > best) { best = d2; bj = j; }
+    for (int i = 0; i < P2; ++i) {
+      const float2 dx = __fadd2_rn(px[i], nx), dy = __fadd2_rn(py[i], ny), dz = __fadd2_rn(pz[i], nz);
+      const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));  // sq3 order, per component
+      const float a = fminf(d.x, t[i].x), b = fminf(d.y, t[i].y);
+      t[i] = make_float2(a, b);
+      if (a > best) { best = a; bj = 2 * i; }
+      if (b > best) { best = b; bj = 2 * i + 1; }
     }
-    const unsigned row = rg + ((unsigned)bj << lrg);
-    const Key wk = warp_argmax(__float_as_int(best), ~(codeL | row));
-    if (lane == 0) s_warp[buf][warp] = wk;
+    unsigned L, row;
+    lay.locate(g, bj, L, row);
+    const int hi = __float_as_int(best);
+    const unsigned lo = ~((bitrev(L, lb) << 23) | row);
+    const Key wk = warp_argmax(hi, lo);
+    if (hi == wk.hi && lo == wk.lo) {  // at most one lane (codes are unique); none if no candidate
+      WarpCand c;
+      c.hi = hi; c.lo = lo; c.slot = bj * T + tid; c.pad = 0;
+      s_warp[buf][warp] = c;
+    }
     __syncthreads();
 
-    Key fk;  // cluster-wide winner
+    Key fk;  // scene-wide winner
+    int hi2 = -0x7fffffff;
+    unsigned lo2 = 0;
+    int slot2 = 0;
+    if (lane < kWarps) {
+      const WarpCand c = s_warp[buf][lane];
+      hi2 = c.hi; lo2 = c.lo; slot2 = c.slot;
+    }
+    const Key ck = warp_argmax(hi2, lo2);  // this CTA's winner (every warp computes it)
     if (CL > 1) {
       if (warp == 0) {
-        const Key mine = s_warp[buf][lane];
-        const Key ck = warp_argmax(mine.hi, mine.lo);
+        // the lane holding the CTA winner fetches its coordinates and broadcasts them inside the warp
+        const unsigned owner = __ballot_sync(kFull, hi2 == ck.hi && lo2 == ck.lo && ck.hi >= 0);
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if (owner) {
+          const int src = __ffs(owner) - 1;
+          const int slot = __shfl_sync(kFull, slot2, src);
+          const float *s = s_xyz + (size_t)slot * 3;
+          cx = s[0]; cy = s[1]; cz = s[2];
+        }
         if (lane < CL) {
-          float cx = 0.f, cy = 0.f, cz = 0.f;
-          if (ck.hi >= 0) {  // decode the owner's slot in this CTA's smem copy
-            const unsigned code = ~ck.lo;
-            const unsigned crow = code & 0x7fffffu;
-            const unsigned cL = bitrev(code >> 23, lb);
-            const unsigned cg = cL | ((crow & ((1u << lrg) - 1u)) << lb);
-            const unsigned cj = crow >> lrg;
-            const float *s = s_xyz + ((size_t)cj * kThreads + (cg & (kThreads - 1))) * 3;
-            cx = s[0]; cy = s[1]; cz = s[2];
-          }
-          const uint32_t slot = mapa_u32(smem_u32(&s_cta[buf][rank]), lane);
+          const uint32_t dst = mapa_u32(smem_u32(&s_cta[buf][rank]), lane);
           const uint32_t rbar = mapa_u32(smem_u32(&s_bar[buf]), lane);
-          st_async_v4(slot, (uint32_t)ck.hi, ck.lo, __float_as_uint(cx), __float_as_uint(cy), rbar);
-          st_async_b32(slot + 16, __float_as_uint(cz), rbar);
+          st_async_v4(dst, (uint32_t)ck.hi, ck.lo, __float_as_uint(cx), __float_as_uint(cy), rbar);
+          st_async_b32(dst + 16, __float_as_uint(cz), rbar);
         }
       }
       mbar_wait_cluster(&s_bar[buf], ((it - 1) >> 1) & 1);
-      int hi = -0x7fffffff;
-      unsigned lo = 0;
-      if (lane < CL) { hi = s_cta[buf][lane].hi; lo = s_cta[buf][lane].lo; }
-      fk = warp_argmax(hi, lo);
+      int hi3 = -0x7fffffff;
+      unsigned lo3 = 0;
+      if (lane < CL) { hi3 = s_cta[buf][lane].hi; lo3 = s_cta[buf][lane].lo; }
+      fk = warp_argmax(hi3, lo3);
       if (fk.hi >= 0) {
-        const int w = __ffs(__ballot_sync(kFull, hi == fk.hi && lo == fk.lo)) - 1;
+        const int w = __ffs(__ballot_sync(kFull, hi3 == fk.hi && lo3 == fk.lo)) - 1;
         ox = s_cta[buf][w].x; oy = s_cta[buf][w].y; oz = s_cta[buf][w].z;
       }
     } else {
-      const Key mine = s_warp[buf][lane];
-      fk = warp_argmax(mine.hi, mine.lo);
+      fk = ck;
       if (fk.hi >= 0) {
-        const unsigned code = ~fk.lo;
-        const unsigned crow = code & 0x7fffffu;
-        const unsigned cL = bitrev(code >> 23, lb);
-        const unsigned cg = cL | ((crow & ((1u << lrg) - 1u)) << lb);
-        const unsigned cj = crow >> lrg;
-        const float *s = s_xyz + ((size_t)cj * kThreads + cg) * 3;
+        const unsigned owner = __ballot_sync(kFull, hi2 == ck.hi && lo2 == ck.lo);
+        const int slot = __shfl_sync(kFull, slot2, __ffs(owner) - 1);
+        const float *s = s_xyz + (size_t)slot * 3;
         ox = s[0]; oy = s[1]; oz = s[2];
       }
     }
-    int old = 0;
-    if (fk.hi >= 0) {
-      const unsigned code = ~fk.lo;
-      old = (int)(bitrev(code >> 23, lb) + ((code & 0x7fffffu) << lb));
-    } else {  // every point skipped: the reference leaves besti = 0 (sampling_gpu.cu:95)
+    if (fk.hi < 0) {  // every point skipped: the reference leaves besti = 0 (sampling_gpu.cu:95)
       ox = p0x; oy = p0y; oz = p0z;
     }
-    if (rank == 0 && tid == 0) idxs[it] = old;
+    if (rank == 0 && tid == 0) {
+      int old = 0;
+      if (fk.hi >= 0) {
+        const unsigned code = ~fk.lo;
+        old = (int)(bitrev(code >> 23, lb) + ((code & 0x7fffffu) << lb));
+      }
+      idxs[it] = old;
+    }
   }
   if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still address its smem
 }
 
 // Generic fallback: any N, running minima in global scratch (the reference's layout), one
 // 1024-thread CTA per scene, same ordering rule.  Used only when the register variant does
-// not cover the shape (N > 16*1024*P_max) or a cluster launch is not possible.
-__global__ void __launch_bounds__(kThreads, 1)
+// not cover the shape or a cluster launch is not possible.
+constexpr int kGThreads = 1024;
+__global__ void __launch_bounds__(kGThreads, 1)
 fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float *__restrict__ temp_all,
                   int *__restrict__ idxs_all) {
-  __shared__ Key s_warp[2][kWarps];
+  __shared__ Key s_warp[2][kGThreads / 32];
   const int scene = blockIdx.x;
   const float *__restrict__ xyz = xyz_all + (size_t)scene * N * 3;
   float *__restrict__ temp = temp_all + (size_t)scene * N;
@@ -196,7 +253,7 @@ fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned L = tid & ((1u << lb) - 1u);
   const unsigned rg = tid >> lb;
-  const unsigned RG = kThreads >> lb;
+  const unsigned RG = kGThreads >> lb;
   const unsigned codeL = bitrev(L, lb) << 23;
   const long long rows = ((long long)N + (1ll << lb) - 1) >> lb;
 
@@ -249,57 +306,80 @@ int ref_log2_block(int n) {
 
 struct FpsPlan {
   int cl;  // cluster size, 0 = global fallback
-  int p;   // points per thread (template instance)
+  int t;   // threads per CTA
+  int p2;  // point PAIRS per thread (template instance)
+  Layout lay;
 };
 
-constexpr int kPs[] = {1, 2, 4, 7, 10, 13};
+constexpr int kP2s[] = {1, 2, 4, 6, 8, 10, 13};
+constexpr int kMaxP2 = 13;
 
-int round_p(int need) {
-  for (int p : kPs)
-    if (need <= p) return p;
+int round_p2(int need_points) {
+  for (int p2 : kP2s)
+    if (need_points <= 2 * p2) return p2;
   return 0;
 }
 
-int need_p(int N, int lb, int cl) {
-  const long long rows = ((long long)N + (1ll << lb) - 1) >> lb;
-  const long long RG = ((long long)cl * kThreads) >> lb;
-  return (int)((rows + RG - 1) / RG);
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+
+// points per thread when G threads share one scene
+int need_points(int N, int lb, int G) {
+  const int BS = 1 << lb;
+  const long long rows = ((long long)N + BS - 1) / BS;
+  if (G >= BS) return (int)((rows + (G / BS) - 1) / (G / BS));
+  return (int)(rows * (BS / G));
+}
+
+bool try_plan(int N, int lb, int cl, int t, FpsPlan *out) {
+  const int G = cl * t;
+  const int need = need_points(N, lb, G);
+  const int p2 = round_p2(need);
+  if (!p2) return false;
+  if (t > 256 && p2 > 10) return false;  // 512 threads: <= 128 registers per thread
+  out->cl = cl; out->t = t; out->p2 = p2;
+  out->lay.lb = lb; out->lay.lG = ilog2(G);
+  out->lay.rows = (int)(((long long)N + (1 << lb) - 1) >> lb);
+  return true;
 }
 
 FpsPlan plan_fps(int B, int N, int lb) {
   (void)B;
-  // Smallest cluster that keeps <= 4 points per thread; the serial chain is latency bound,
-  // so past that extra CTAs only help by shrinking the register sweep.
-  const int force = [] {
-    const char *e = getenv("EDA_FPS_CLUSTER");
-    return e ? atoi(e) : 0;
-  }();
+  FpsPlan pl = {};
+  // EDA_FPS_CLUSTER / EDA_FPS_THREADS force a decomposition (tests sweep them: the result may not change)
+  const char *e = getenv("EDA_FPS_CLUSTER");
+  const char *et = getenv("EDA_FPS_THREADS");
+  const int force = e ? atoi(e) : 0;
+  const int force_t = et ? atoi(et) : 0;
   if (force == 1 || force == 2 || force == 4 || force == 8 || force == 16) {
-    const int p = round_p(need_p(N, lb, force));
-    if (p) return {force, p};
+    for (int t : {256, 512})
+      if ((force_t == 0 || force_t == t) && try_plan(N, lb, force, t, &pl)) return pl;
   }
-  if (need_p(N, lb, 1) <= 4) return {1, round_p(need_p(N, lb, 1))};
-  for (int cl : {2, 4, 8}) {
-    const int need = need_p(N, lb, cl);
-    if (need <= (cl == 8 ? 7 : 4)) return {cl, round_p(need)};
-  }
-  {
-    const int p = round_p(need_p(N, lb, 16));
-    if (p) return {16, p};
-  }
-  return {0, 0};
+  // Smallest cluster whose threads can hold the scene in registers: the serial chain is latency/issue
+  // bound, extra CTAs only help by shrinking the per-thread sweep.  16-CTA clusters fit one per GPC, so
+  // 8 scenes would run in two waves: last resort.
+  for (int cl : {1, 2, 4, 8})
+    if (try_plan(N, lb, cl, 256, &pl)) return pl;
+  for (int cl : {8, 16})
+    for (int t : {256, 512})
+      if (try_plan(N, lb, cl, t, &pl)) return pl;
+  pl.cl = 0;
+  return pl;
 }
 
-template <int P, int CL>
-int launch_cluster(const float *xyz, int B, int N, int m, int lb, int *idxs, cudaStream_t st) {
-  auto kern = fps_cluster_kernel<P, CL>;
-  const size_t smem = (size_t)P * kThreads * 3 * sizeof(float);
+template <int P2, int CL, int T>
+int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int *idxs, cudaStream_t st) {
+  auto kern = fps_cluster_kernel<P2, CL, T>;
+  const size_t smem = (size_t)2 * P2 * T * 3 * sizeof(float);
   EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps smem attr");
   if (CL > 8)
     EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "fps cluster attr");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * CL));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(T);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -309,20 +389,30 @@ int launch_cluster(const float *xyz, int B, int N, int m, int lb, int *idxs, cud
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, lb, idxs), "fps_cluster_kernel launch");
+  EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, lay, idxs), "fps_cluster_kernel launch");
   return check_launch("fps_cluster_kernel");
 }
 
-template <int CL>
-int dispatch_p(int p, const float *xyz, int B, int N, int m, int lb, int *idxs, cudaStream_t st) {
-  switch (p) {
-    case 1: return launch_cluster<1, CL>(xyz, B, N, m, lb, idxs, st);
-    case 2: return launch_cluster<2, CL>(xyz, B, N, m, lb, idxs, st);
-    case 4: return launch_cluster<4, CL>(xyz, B, N, m, lb, idxs, st);
-    case 7: return launch_cluster<7, CL>(xyz, B, N, m, lb, idxs, st);
-    case 10: return launch_cluster<10, CL>(xyz, B, N, m, lb, idxs, st);
-    case 13: return launch_cluster<13, CL>(xyz, B, N, m, lb, idxs, st);
+template <int CL, int T>
+int dispatch_p(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, cudaStream_t st) {
+  switch (pl.p2) {
+    case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    case 6: return launch_cluster<6, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    case 8: return launch_cluster<8, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    case 10: return launch_cluster<10, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    case 13:
+      if constexpr (T == 256) return launch_cluster<13, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+      break;
   }
+  return EDA_ERR_UNSUPPORTED;
+}
+
+template <int CL>
+int dispatch_t(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, cudaStream_t st) {
+  if (pl.t == 256) return dispatch_p<CL, 256>(pl, xyz, B, N, m, idxs, st);
+  if (pl.t == 512) return dispatch_p<CL, 512>(pl, xyz, B, N, m, idxs, st);
   return EDA_ERR_UNSUPPORTED;
 }
 
@@ -348,15 +438,15 @@ int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, void *scr
   const int lb = ref_log2_block(N);
   const FpsPlan pl = plan_fps(B, N, lb);
   switch (pl.cl) {
-    case 1: return dispatch_p<1>(pl.p, xyz, B, N, m, lb, idxs, st);
-    case 2: return dispatch_p<2>(pl.p, xyz, B, N, m, lb, idxs, st);
-    case 4: return dispatch_p<4>(pl.p, xyz, B, N, m, lb, idxs, st);
-    case 8: return dispatch_p<8>(pl.p, xyz, B, N, m, lb, idxs, st);
-    case 16: return dispatch_p<16>(pl.p, xyz, B, N, m, lb, idxs, st);
+    case 1: return dispatch_t<1>(pl, xyz, B, N, m, idxs, st);
+    case 2: return dispatch_t<2>(pl, xyz, B, N, m, idxs, st);
+    case 4: return dispatch_t<4>(pl, xyz, B, N, m, idxs, st);
+    case 8: return dispatch_t<8>(pl, xyz, B, N, m, idxs, st);
+    case 16: return dispatch_t<16>(pl, xyz, B, N, m, idxs, st);
     default: break;
   }
   if (!scratch) return EDA_ERR_INVALID_ARGUMENT;
-  fps_global_kernel<<<B, kThreads, 0, st>>>(xyz, N, m, lb, (float *)scratch, idxs);
+  fps_global_kernel<<<B, kGThreads, 0, st>>>(xyz, N, m, lb, (float *)scratch, idxs);
   return check_launch("fps_global_kernel");
 }
 

@@ -526,7 +526,7 @@ int eda_sa_mlp_pack(const float *W1, const float *W2, const float *W3, const flo
   if (nlayers >= 2) pack_layer_kernel<<<(C2 * C1 + 255) / 256, 256, 0, st>>>(W2, scale2, C2, C1, C1, -1, dst);
   dst += (size_t)C2 * C1;
   if (nlayers >= 3) pack_layer_kernel<<<(C3 * C2 + 255) / 256, 256, 0, st>>>(W3, scale3, C3, C2, C2, -1, dst);
-  return check_launch("pack_layer_kernel");
+  return check_launch("pack_layer_kernel", nlayers);
 }
 
 int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const float *feat, int feat_stride, const int *idx,

@@ -45,6 +45,8 @@ EDA_API int eda_version(void);
 EDA_API const char *eda_error_string(int code);
 /* Text of the last CUDA error seen by this thread inside the library ("" if none). */
 EDA_API const char *eda_last_cuda_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (bookkeeping only). */
+EDA_API unsigned long long eda_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * Furthest point sampling.

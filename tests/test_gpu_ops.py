@@ -36,11 +36,13 @@ def test_fps_bit_exact_vs_oracle(ext, oracle, family, B, N, m):
     assert torch.equal(got, want), f"first mismatch at {torch.nonzero(got != want)[0].tolist()}"
 
 
+@pytest.mark.parametrize("threads", [256, 512])
 @pytest.mark.parametrize("cl", [1, 2, 4, 8, 16])
-def test_fps_every_cluster_size_bit_exact(ext, oracle, cl, monkeypatch):
-    # EDA_FPS_CLUSTER forces the decomposition: the result may not depend on it
+def test_fps_every_cluster_size_bit_exact(ext, oracle, cl, threads, monkeypatch):
+    # EDA_FPS_CLUSTER / EDA_FPS_THREADS force the decomposition: the result may not depend on it
     monkeypatch.setenv("EDA_FPS_CLUSTER", str(cl))
-    for family, N, m in [("lattice", 8192, 300), ("dup", 5000, 300)]:
+    monkeypatch.setenv("EDA_FPS_THREADS", str(threads))
+    for family, N, m in [("lattice", 8192, 300), ("dup", 5000, 300), ("lattice", 1000, 200), ("dup", 300, 100)]:
         xyz = synthetic.point_clouds(2, N, family, seed=cl, channels=0)
         want = oracle.furthest_point_sampling(xyz, m)
         got = ext.furthest_point_sampling(_cuda(xyz), m).cpu()
