@@ -43,17 +43,16 @@ def main():
     for N, m, r, ns in stages:
         key = f"N{N}_m{m}"
         res[f"fps_{key}"] = timeit(lambda: _ext.furthest_point_sampling(xyz, m))
-        if N == 50000:
-            for cl in (4, 8, 16):
-                for thr in (256, 512):
-                    os.environ["EDA_FPS_CLUSTER"] = str(cl)
-                    os.environ["EDA_FPS_THREADS"] = str(thr)
-                    try:
-                        res[f"fps_{key}_cl{cl}_t{thr}"] = timeit(lambda: _ext.furthest_point_sampling(xyz, m))
-                    except RuntimeError as e:
-                        res[f"fps_{key}_cl{cl}_t{thr}"] = repr(e)
-            os.environ.pop("EDA_FPS_CLUSTER")
-            os.environ.pop("EDA_FPS_THREADS")
+        combos = [(8, 256), (8, 512), (16, 256)] if N == 50000 else [(1, 256), (1, 512), (1, 1024), (2, 256)]
+        for cl, thr in combos:
+            os.environ["EDA_FPS_CLUSTER"] = str(cl)
+            os.environ["EDA_FPS_THREADS"] = str(thr)
+            try:
+                res[f"fps_{key}_cl{cl}_t{thr}"] = timeit(lambda: _ext.furthest_point_sampling(xyz, m))
+            except RuntimeError as e:
+                res[f"fps_{key}_cl{cl}_t{thr}"] = repr(e)
+        os.environ.pop("EDA_FPS_CLUSTER")
+        os.environ.pop("EDA_FPS_THREADS")
         inds = _ext.furthest_point_sampling(xyz, m)
         new_xyz = torch.gather(xyz, 1, inds.long()[..., None].expand(-1, -1, 3)).contiguous()
         res[f"bq_{key}_ns{ns}"] = timeit(lambda: _ext.ball_query(new_xyz, xyz, r, ns))

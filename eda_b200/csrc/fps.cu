@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, int *__restrict__ idxs_all) {
   constexpr int P = 2 * P2;
   constexpr int kWarps = T / 32;
-  extern __shared__ __align__(16) float s_xyz[];  // [P][T][3] copy of this CTA's points
+  extern __shared__ __align__(16) float s_xyz[];  // [P][T][3] copy of this CTA's points, then [P][T] ~codes
+  unsigned *s_code = reinterpret_cast<unsigned *>(s_xyz + (size_t)P * T * 3);
   __shared__ WarpCand s_warp[2][kWarps];
   __shared__ Cand s_cta[2][CL];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -127,6 +128,7 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
       cx[e] = x; cy[e] = y; cz[e] = z; ct[e] = tt;
       float *s = s_xyz + ((size_t)jj * T + tid) * 3;
       s[0] = x; s[1] = y; s[2] = z;
+      s_code[jj * T + tid] = ~((bitrev(L, lb) << 23) | row);
     }
     px[i] = make_float2(cx[0], cx[1]);
     py[i] = make_float2(cy[0], cy[1]);
@@ -155,21 +157,34 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
     // ---- distance update, thread-local arg-max (first strict maximum, ascending code) ----
     // (p - o) as p + (-o): same rounding; two points per FADD2 / FMUL2 / FFMA2
     const float2 nx = make_float2(-ox, -ox), ny = make_float2(-oy, -oy), nz = make_float2(-oz, -oz);
-    float best = -1.0f;
-    int bj = 0;
+    float val[P];
 #pragma unroll
     for (int i = 0; i < P2; ++i) {
       const float2 dx = __fadd2_rn(px[i], nx), dy = __fadd2_rn(py[i], ny), dz = __fadd2_rn(pz[i], nz);
       const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));  // sq3 order, per component
       const float a = fminf(d.x, t[i].x), b = fminf(d.y, t[i].y);
       t[i] = make_float2(a, b);
-      if (a > best) { best = a; bj = 2 * i; }
-      if (b > best) { best = b; bj = 2 * i + 1; }
+      val[2 * i] = a;
+      val[2 * i + 1] = b;
     }
-    unsigned L, row;
-    lay.locate(g, bj, L, row);
+    // first strict maximum in slot order as a tournament (depth log2 P instead of a P-long dependency
+    // chain): the later slot wins only if strictly greater, so ties keep the earlier slot at every level
+    int sel[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) sel[j] = j;
+#pragma unroll
+    for (int stride = 1; stride < P; stride *= 2) {
+#pragma unroll
+      for (int j = 0; j + stride < P; j += 2 * stride) {
+        const bool later = val[j + stride] > val[j];
+        sel[j] = later ? sel[j + stride] : sel[j];
+        val[j] = fmaxf(val[j], val[j + stride]);
+      }
+    }
+    const float best = val[0];
+    const int bj = sel[0];
     const int hi = __float_as_int(best);
-    const unsigned lo = ~((bitrev(L, lb) << 23) | row);
+    const unsigned lo = s_code[bj * T + tid];
     const Key wk = warp_argmax(hi, lo);
     if (hi == wk.hi && lo == wk.lo) {  // at most one lane (codes are unique); none if no candidate
       WarpCand c;
@@ -339,7 +354,7 @@ bool try_plan(int N, int lb, int cl, int t, FpsPlan *out) {
   const int need = need_points(N, lb, G);
   const int p2 = round_p2(need);
   if (!p2) return false;
-  if (t > 256 && p2 > 10) return false;  // 512 threads: <= 128 registers per thread
+  if (t > 512 && p2 > 4) return false;  // 1024 threads: <= 64 registers per thread
   out->cl = cl; out->t = t; out->p2 = p2;
   out->lay.lb = lb; out->lay.lG = ilog2(G);
   out->lay.rows = (int)(((long long)N + (1 << lb) - 1) >> lb);
@@ -355,7 +370,7 @@ FpsPlan plan_fps(int B, int N, int lb) {
   const int force = e ? atoi(e) : 0;
   const int force_t = et ? atoi(et) : 0;
   if (force == 1 || force == 2 || force == 4 || force == 8 || force == 16) {
-    for (int t : {256, 512})
+    for (int t : {256, 512, 1024})
       if ((force_t == 0 || force_t == t) && try_plan(N, lb, force, t, &pl)) return pl;
   }
   // Smallest cluster whose threads can hold the scene in registers: the serial chain is latency/issue
@@ -373,7 +388,7 @@ FpsPlan plan_fps(int B, int N, int lb) {
 template <int P2, int CL, int T>
 int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int *idxs, cudaStream_t st) {
   auto kern = fps_cluster_kernel<P2, CL, T>;
-  const size_t smem = (size_t)2 * P2 * T * 3 * sizeof(float);
+  const size_t smem = (size_t)2 * P2 * T * 4 * sizeof(float);
   EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps smem attr");
   if (CL > 8)
     EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "fps cluster attr");
@@ -395,6 +410,14 @@ int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int
 
 template <int CL, int T>
 int dispatch_p(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, cudaStream_t st) {
+  if constexpr (T == 1024) {
+    switch (pl.p2) {
+      case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+      case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+      case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    }
+    return EDA_ERR_UNSUPPORTED;
+  }
   switch (pl.p2) {
     case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
     case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
@@ -402,9 +425,7 @@ int dispatch_p(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *id
     case 6: return launch_cluster<6, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
     case 8: return launch_cluster<8, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
     case 10: return launch_cluster<10, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-    case 13:
-      if constexpr (T == 256) return launch_cluster<13, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-      break;
+    case 13: return launch_cluster<13, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
   }
   return EDA_ERR_UNSUPPORTED;
 }
@@ -413,6 +434,7 @@ template <int CL>
 int dispatch_t(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, cudaStream_t st) {
   if (pl.t == 256) return dispatch_p<CL, 256>(pl, xyz, B, N, m, idxs, st);
   if (pl.t == 512) return dispatch_p<CL, 512>(pl, xyz, B, N, m, idxs, st);
+  if (pl.t == 1024) return dispatch_p<CL, 1024>(pl, xyz, B, N, m, idxs, st);
   return EDA_ERR_UNSUPPORTED;
 }
 
