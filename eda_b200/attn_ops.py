@@ -1,0 +1,285 @@
+"""Host side of the attention-layer kernels (eda_linear_forward, eda_attention_forward): weight
+packing cache, launch wrappers, and the autograd boundary of the three fused blocks the layers in
+encoder_decoder_layers.py are made of:
+
+    mha_block  : LayerNorm(residual + MHA(q_in [+ q_pos], k_in [+ k_pos], v_in, key_padding_mask))
+    ffn_block  : LayerNorm(x + W2 relu(W1 x + b1) + b2)
+    linear     : act(x W^T + b)
+
+Forward = hand-written CUDA only (3 launches per mha_block, 2 per ffn_block).  Backward (round 1) =
+recompute of the same maths with differentiable torch ops on the GPU, as for the fused SA kernel.
+There is no CPU path: CPU tensors raise RuntimeError like the rest of the package.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _require_cuda(t, name="input"):
+    if not t.is_cuda:
+        raise RuntimeError(f"eda_b200: {name} must be a CUDA tensor (CPU not supported)")
+
+
+# ---------------------------------------------------------------------------------------------------
+# packed weights
+# ---------------------------------------------------------------------------------------------------
+def _cache_of(owner):
+    """The packed-weight cache lives ON the owning module, so it dies with it (a process-wide dict keyed by
+    id() / data_ptr() could hand a new module the packed weights of a dead one whose memory it reuses)."""
+    d = owner.__dict__.get("_eda_pack_cache")
+    if d is None:
+        d = {}
+        owner.__dict__["_eda_pack_cache"] = d
+    return d
+
+
+def pack_weight(W, scale=None, cache_key=None):
+    """W (N,K) f32 CUDA (any row-contiguous view) -> packed tensor for eda_linear_forward.  With
+    `cache_key` = (owner module, name) the result is reused until the weight is modified in place
+    (optimizer step, load_state_dict) or reallocated (.to())."""
+    lib = _lib.load()
+    N, K = W.shape
+    cache = None
+    if cache_key is not None and scale is None:
+        cache = _cache_of(cache_key[0])
+        tag = (W.data_ptr(), W._version, N, K, W.device)
+        hit = cache.get(cache_key[1])
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+    Wc = W.detach()
+    if not Wc.is_contiguous():
+        Wc = Wc.contiguous()
+    n = lib.eda_linear_packed_floats(N, K)
+    if n == 0:
+        raise RuntimeError(f"eda_b200.linear: unsupported weight shape ({N},{K})")
+    packed = torch.empty(n, dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+        rc = lib.eda_linear_pack(_p(Wc), _p(scale), N, K, _p(packed), _stream(W.device))
+    _lib.check(rc, "linear_pack")
+    if cache is not None:
+        cache[cache_key[1]] = (tag, packed)
+    return packed
+
+
+def linear_raw(problems, K, N, relu=False, ln=None):
+    """problems: list (<= 3) of dicts x (R,K), w_packed, optional pos, bias, residual.  Returns [y (R,N)]."""
+    lib = _lib.load()
+    dev = problems[0]["x"].device
+    arr = (_lib.LinearProblem * len(problems))()
+    outs, keep = [], []
+    for i, pr in enumerate(problems):
+        x = pr["x"]
+        _require_cuda(x)
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.size(-1) == K
+        R = x.numel() // K
+        y = torch.empty((R, N), dtype=torch.float32, device=dev)
+        pos, res, bias = pr.get("pos"), pr.get("residual"), pr.get("bias")
+        if pos is not None:
+            assert pos.is_contiguous() and pos.numel() == x.numel()
+        if res is not None:
+            assert res.is_contiguous() and res.numel() == R * N
+        if bias is not None:
+            bias = bias.detach().contiguous()
+        keep.append((x, pos, res, bias, pr["w_packed"]))
+        arr[i].x, arr[i].pos, arr[i].w_packed = x.data_ptr(), (pos.data_ptr() if pos is not None else None), \
+            pr["w_packed"].data_ptr()
+        arr[i].bias = bias.data_ptr() if bias is not None else None
+        arr[i].residual = res.data_ptr() if res is not None else None
+        arr[i].y, arr[i].rows = y.data_ptr(), R
+        outs.append(y)
+    g = b = None
+    eps = 0.0
+    if ln is not None:
+        g, b, eps = ln
+        g = g.detach().contiguous() if g is not None else None
+        b = b.detach().contiguous() if b is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.eda_linear_forward(ctypes.cast(arr, ctypes.c_void_p), len(problems), K, N, 1 if relu else 0, _p(g),
+                                    _p(b), float(eps), 1 if ln is not None else 0, _stream(dev))
+    _lib.check(rc, "linear_forward")
+    return outs
+
+
+def attention_raw(q, k, v, key_padding_mask, B, Nq, Nk, H):
+    """q (B*Nq,E), k, v (B*Nk,E) projected; mask (B,Nk) bool or None -> ctx (B*Nq,E)."""
+    lib = _lib.load()
+    E = q.size(-1)
+    D = E // H
+    ctx = torch.empty((B * Nq, E), dtype=torch.float32, device=q.device)
+    m = None
+    if key_padding_mask is not None:
+        m = key_padding_mask
+        if m.dtype != torch.bool:
+            m = m != 0
+        m = m.contiguous().view(torch.uint8)
+        assert m.shape == (B, Nk)
+    with torch.cuda.device(q.device):
+        rc = lib.eda_attention_forward(_p(q), _p(k), _p(v), _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), _p(ctx),
+                                       _stream(q.device))
+    _lib.check(rc, "attention_forward")
+    return ctx
+
+
+# ---------------------------------------------------------------------------------------------------
+# differentiable restatements (backward only)
+# ---------------------------------------------------------------------------------------------------
+def _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H):
+    E = q_in.size(-1)
+    D = E // H
+    B, Nq, _ = q_in.shape
+    Nk = k_in.size(1)
+    q = F.linear(q_in if q_pos is None else q_in + q_pos, in_w[:E], in_b[:E])
+    k = F.linear(k_in if k_pos is None else k_in + k_pos, in_w[E:2 * E], in_b[E:2 * E])
+    v = F.linear(v_in, in_w[2 * E:], in_b[2 * E:])
+    q = q.view(B, Nq, H, D).transpose(1, 2) * (1.0 / math.sqrt(D))
+    k = k.view(B, Nk, H, D).transpose(1, 2)
+    v = v.view(B, Nk, H, D).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if mask is not None:
+        s = s.masked_fill(mask.view(B, 1, 1, Nk), float("-inf"))
+    ctx = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, Nq, E)
+    return F.linear(ctx, out_w, out_b)
+
+
+class _MHABlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, eps, key, mask, q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b):
+        E = q_in.size(-1)
+        B, Nq, _ = q_in.shape
+        Nk = k_in.size(1)
+        for t in (q_in, k_in, v_in):
+            _require_cuda(t)
+        q_in, k_in, v_in = q_in.contiguous(), k_in.contiguous(), v_in.contiguous()
+        qp = q_pos.contiguous() if q_pos is not None else None
+        kp = k_pos.contiguous() if k_pos is not None else None
+        wq = pack_weight(in_w[:E], cache_key=(key, "q"))
+        wk = pack_weight(in_w[E:2 * E], cache_key=(key, "k"))
+        wv = pack_weight(in_w[2 * E:], cache_key=(key, "v"))
+        wo = pack_weight(out_w, cache_key=(key, "o"))
+        ib = in_b.detach()
+        q, k, v = linear_raw([
+            dict(x=q_in, pos=qp, w_packed=wq, bias=ib[:E]),
+            dict(x=k_in, pos=kp, w_packed=wk, bias=ib[E:2 * E]),
+            dict(x=v_in, w_packed=wv, bias=ib[2 * E:]),
+        ], E, E)
+        c = attention_raw(q, k, v, mask, B, Nq, Nk, H)
+        res = residual.contiguous() if residual is not None else None
+        ln = (ln_w, ln_b, eps) if ln_w is not None else None
+        (y,) = linear_raw([dict(x=c, w_packed=wo, bias=out_b, residual=res)], E, E, ln=ln)
+        if ln is None and res is not None:
+            y = y + res.view(-1, E)
+        ctx.save_for_backward(q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b)
+        ctx.meta = (H, eps, mask)
+        return y.view(B, Nq, E)
+
+    @staticmethod
+    def backward(ctx, grad):
+        H, eps, mask = ctx.meta
+        saved = ctx.saved_tensors
+        with torch.enable_grad():
+            ts = [None if t is None else t.detach().requires_grad_(ctx.needs_input_grad[4 + i])
+                  for i, t in enumerate(saved)]
+            q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b = ts
+            y = _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H)
+            if residual is not None:
+                y = residual + y
+            if ln_w is not None:
+                y = F.layer_norm(y, (y.size(-1),), ln_w, ln_b, eps)
+            wanted = [t for t in ts if t is not None and t.requires_grad]
+            grads = torch.autograd.grad(y, wanted, grad, allow_unused=True) if wanted else []
+        gmap = {id(t): g for t, g in zip(wanted, grads)}
+        return (None, None, None, None, *[gmap.get(id(t)) if t is not None else None for t in ts])
+
+
+def mha_block(mha, q_in, k_in, v_in, q_pos=None, k_pos=None, key_padding_mask=None, residual=None, norm=None):
+    """LayerNorm(residual + MHA(q_in + q_pos, k_in + k_pos, v_in)) with `mha` an nn.MultiheadAttention
+    (parameters only) and `norm` an nn.LayerNorm (or None: no residual LayerNorm, plain attention output
+    [+ residual]).  All activations batch-first (B, S, E)."""
+    if mha.training and mha.dropout > 0.0:
+        raise RuntimeError("eda_b200: train-mode attention dropout > 0 is not fused yet; set dropout=0 "
+                           "(parity configuration, SURVEY.md 8c) or call .eval()")
+    return _MHABlockFn.apply(mha.num_heads, norm.eps if norm is not None else 0.0, mha, key_padding_mask, q_in,
+                             q_pos, k_in, k_pos, v_in, residual, mha.in_proj_weight, mha.in_proj_bias,
+                             mha.out_proj.weight, mha.out_proj.bias, norm.weight if norm is not None else None,
+                             norm.bias if norm is not None else None)
+
+
+class _FFNBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eps, key, x, w1, b1, w2, b2, ln_w, ln_b):
+        _require_cuda(x)
+        shape = x.shape
+        E, Fh = w1.size(1), w1.size(0)
+        x2 = x.contiguous().view(-1, E)
+        p1 = pack_weight(w1, cache_key=(key, "w1"))
+        p2 = pack_weight(w2, cache_key=(key, "w2"))
+        (hdn,) = linear_raw([dict(x=x2, w_packed=p1, bias=b1)], E, Fh, relu=True)
+        (y,) = linear_raw([dict(x=hdn, w_packed=p2, bias=b2, residual=x2)], Fh, E, ln=(ln_w, ln_b, eps))
+        ctx.save_for_backward(x, w1, b1, w2, b2, ln_w, ln_b)
+        ctx.eps = eps
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        with torch.enable_grad():
+            ts = [t.detach().requires_grad_(ctx.needs_input_grad[2 + i]) for i, t in enumerate(ctx.saved_tensors)]
+            x, w1, b1, w2, b2, ln_w, ln_b = ts
+            y = F.layer_norm(x + F.linear(F.relu(F.linear(x, w1, b1)), w2, b2), (x.size(-1),), ln_w, ln_b, ctx.eps)
+            wanted = [t for t in ts if t.requires_grad]
+            grads = torch.autograd.grad(y, wanted, grad, allow_unused=True) if wanted else []
+        gmap = {id(t): g for t, g in zip(wanted, grads)}
+        return (None, None, *[gmap.get(id(t)) for t in ts])
+
+
+def ffn_block(ffn, x, norm):
+    """norm(x + ffn(x)) for ffn = Sequential(Linear, ReLU, Dropout, Linear, Dropout) (indices 0 and 3)."""
+    for mod in ffn:
+        if isinstance(mod, torch.nn.Dropout) and mod.training and mod.p > 0.0:
+            raise RuntimeError("eda_b200: train-mode FFN dropout > 0 is not fused yet; set dropout=0 or call .eval()")
+    l1, l2 = ffn[0], ffn[3]
+    return _FFNBlockFn.apply(norm.eps, ffn, x, l1.weight, l1.bias, l2.weight, l2.bias, norm.weight, norm.bias)
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, relu, key, x, w, b, scale):
+        _require_cuda(x)
+        N, K = w.shape
+        x2 = x.contiguous().view(-1, K)
+        packed = pack_weight(w, scale=scale, cache_key=key)
+        (y,) = linear_raw([dict(x=x2, w_packed=packed, bias=b)], K, N, relu=relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu = relu
+        ctx.has_scale = scale is not None
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, grad):
+        if ctx.has_scale:
+            raise RuntimeError("eda_b200.linear: the scale-folded variant is inference-only")
+        x, w, y = ctx.saved_tensors
+        K = w.size(1)
+        g = grad.reshape(-1, w.size(0))
+        if ctx.relu:
+            g = g * (y > 0)
+        gx = (g @ w).view(x.shape) if ctx.needs_input_grad[2] else None
+        gw = g.t() @ x.reshape(-1, K) if ctx.needs_input_grad[3] else None
+        gb = g.sum(0) if ctx.needs_input_grad[4] else None
+        return None, None, gx, gw, gb, None
+
+
+def linear(x, weight, bias=None, relu=False, scale=None, cache_key=None):
+    """act(x W^T * scale + bias) on the tcgen05 linear kernel; x (..., K), weight (N, K)."""
+    return _LinearFn.apply(relu, cache_key, x, weight, bias, scale)

@@ -1,0 +1,112 @@
+"""Pointnet2Backbone with the constructor / forward signature, submodule names and `end_points`
+keys of the reference's models/backbone_module.py:26-144, on the sm_100a kernels.
+
+What is different underneath: furthest-point sampling depends on xyz only, so the four FPS stages
+(50 000 -> 2048 -> 1024 -> 512 -> 256; 3836 strictly serial iterations, the latency floor of the
+whole forward) run as one chain on a side CUDA stream while the main stream does ball query +
+fused group/MLP/max-pool of the previous stage.  Each SA module then receives its `inds` through
+the `inds=` argument the reference API already has (pointnet2_modules.py:210-236).
+Results are identical to running the stages back to back.
+"""
+import torch
+import torch.nn as nn
+
+from .pointnet2 import pointnet2_utils
+from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+
+
+class Pointnet2Backbone(nn.Module):
+    """Backbone network for point cloud feature learning (PointNet++ single-scale grouping)."""
+
+    def __init__(self, input_feature_dim=0, width=1, depth=2, output_dim=288):
+        super().__init__()
+        self.depth = depth
+        self.width = width
+        self.sa1 = PointnetSAModuleVotes(
+            npoint=2048, radius=0.2, nsample=64,
+            mlp=[input_feature_dim] + [64 * width for _ in range(depth)] + [128 * width],
+            use_xyz=True, normalize_xyz=True)
+        self.sa2 = PointnetSAModuleVotes(
+            npoint=1024, radius=0.4, nsample=32,
+            mlp=[128 * width] + [128 * width for _ in range(depth)] + [256 * width],
+            use_xyz=True, normalize_xyz=True)
+        self.sa3 = PointnetSAModuleVotes(
+            npoint=512, radius=0.8, nsample=16,
+            mlp=[256 * width] + [128 * width for _ in range(depth)] + [256 * width],
+            use_xyz=True, normalize_xyz=True)
+        self.sa4 = PointnetSAModuleVotes(
+            npoint=256, radius=1.2, nsample=16,
+            mlp=[256 * width] + [128 * width for _ in range(depth)] + [256 * width],
+            use_xyz=True, normalize_xyz=True)
+        self.fp1 = PointnetFPModule(mlp=[256 * width + 256 * width, 256 * width, 256 * width])
+        self.fp2 = PointnetFPModule(mlp=[256 * width + 256 * width, 256 * width, output_dim])
+        self.overlap_fps = True  # False: plain back-to-back stages (tests compare the two)
+        self._side = None
+
+    def _break_up_pc(self, pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def _fps_chain(self, xyz):
+        """All four FPS stages on a side stream.  Returns [(inds, event)] per stage."""
+        main = torch.cuda.current_stream(xyz.device)
+        if self._side is None or self._side.device != xyz.device:
+            self._side = torch.cuda.Stream(device=xyz.device)
+        side = self._side
+        side.wait_stream(main)
+        out = []
+        with torch.cuda.stream(side):
+            cur = xyz
+            for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+                inds = pointnet2_utils.furthest_point_sample(cur, sa.npoint)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                out.append((inds, ev))
+                if sa is not self.sa4:
+                    cur = torch.gather(cur, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+                    cur.record_stream(main)
+                inds.record_stream(main)
+        return out
+
+    def forward(self, pointcloud, end_points=None):
+        """pointcloud (B, N, 3 + input_feature_dim) -> end_points dict with sa{1..4}_{xyz,features},
+        sa{1,2}_inds, fp2_{features,xyz,inds}  (backbone_module.py:92-144)."""
+        if not end_points:
+            end_points = {}
+        xyz, features = self._break_up_pc(pointcloud)
+        chain = self._fps_chain(xyz) if (self.overlap_fps and xyz.is_cuda) else None
+
+        def run(sa, k, xyz, features):
+            if chain is None:
+                return sa(xyz, features)
+            inds, ev = chain[k]
+            torch.cuda.current_stream(xyz.device).wait_event(ev)
+            return sa(xyz, features, inds)
+
+        xyz, features, fps_inds = run(self.sa1, 0, xyz, features)
+        end_points['sa1_inds'] = fps_inds
+        end_points['sa1_xyz'] = xyz
+        end_points['sa1_features'] = features
+
+        xyz, features, fps_inds = run(self.sa2, 1, xyz, features)
+        end_points['sa2_inds'] = fps_inds
+        end_points['sa2_xyz'] = xyz
+        end_points['sa2_features'] = features
+
+        xyz, features, fps_inds = run(self.sa3, 2, xyz, features)
+        end_points['sa3_xyz'] = xyz
+        end_points['sa3_features'] = features
+
+        xyz, features, fps_inds = run(self.sa4, 3, xyz, features)
+        end_points['sa4_xyz'] = xyz
+        end_points['sa4_features'] = features
+
+        features = self.fp1(end_points['sa3_xyz'], end_points['sa4_xyz'], end_points['sa3_features'],
+                            end_points['sa4_features'])
+        features = self.fp2(end_points['sa2_xyz'], end_points['sa3_xyz'], end_points['sa2_features'], features)
+        end_points['fp2_features'] = features
+        end_points['fp2_xyz'] = end_points['sa2_xyz']
+        num_seed = end_points['fp2_xyz'].shape[1]
+        end_points['fp2_inds'] = end_points['sa1_inds'][:, 0:num_seed]
+        return end_points

@@ -141,6 +141,44 @@ EDA_API int eda_bn_finalize(const float *stats, double count, const float *gamma
 EDA_API int eda_transpose_last2(const float *in, int B, int R, int C, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Cross-modal attention layers (models/encoder_decoder_layers.py).  All activations are row-major
+ * "batch-first" matrices: row (b, s) of a (B, S, E) tensor is one contiguous E-float row.
+ *
+ * eda_linear_forward: Y[R x N] = act((X [+ P])[R x K] W[N x K]^T + bias), optionally followed by
+ *   LayerNorm(residual + Y) * gamma + beta over the N columns (layer_norm != 0; residual may be NULL).
+ *   Replaces F.linear inside nn.MultiheadAttention (in/out projections, torch/nn/functional.py
+ *   math path as called from encoder_decoder_layers.py:87-117,149-183,366-401), the residual +
+ *   nn.LayerNorm after each attention / FFN block (:94-96,106-107,118-122,371-405), the FFN linears
+ *   (:53-59,322-328) and the 1x1 Conv1d's of PositionEmbeddingLearned (:24-28).
+ *   Up to 3 problems with the same K, N and epilogue share one launch (q / k / v in-projections).
+ *   `w_packed` comes from eda_linear_pack (W (N,K) row-major, optional per-row scale folded in, tf32
+ *   rounding, kernel streaming order); eda_linear_packed_floats(N,K) floats, 0 = unsupported
+ *   (N % 16 == 0, 16 <= N <= 320).  x, pos: R x K contiguous; y, residual: R x N contiguous,
+ *   16-byte aligned.  tcgen05 kind::tf32, fp32 accumulate.
+ *
+ * eda_attention_forward: ctx (B,Nq,H*D) = softmax(q k^T * scale + mask) v per head, q (B,Nq,H*D),
+ *   k, v (B,Nk,H*D) already projected; key_padding_mask (B,Nk) bytes, nonzero = ignore (may be NULL).
+ *   Replaces the bmm/softmax/bmm of the same math path.  D % 4 == 0, D <= 64.  A fully masked row
+ *   yields NaN as in the reference. */
+typedef struct eda_linear_problem {
+  const float *x;        /* (rows, K) */
+  const float *pos;      /* (rows, K) added to x before the product, or NULL */
+  const float *w_packed; /* eda_linear_pack output for W (N, K) */
+  const float *bias;     /* (N) or NULL */
+  const float *residual; /* (rows, N) or NULL; only read when layer_norm != 0 */
+  float *y;              /* (rows, N) */
+  int rows;
+} eda_linear_problem;
+EDA_API size_t eda_linear_packed_floats(int N, int K);
+EDA_API int eda_linear_pack(const float *W, const float *scale, int N, int K, float *packed, void *stream);
+EDA_API int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu,
+                               const float *ln_gamma, const float *ln_beta, float ln_eps, int layer_norm,
+                               void *stream);
+EDA_API int eda_attention_forward(const float *q, const float *k, const float *v,
+                                  const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
+                                  float scale, float *ctx, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05/TMEM building blocks the fused kernels rely on (no reference
  * counterpart).  D[128,N] = A[128,K] * W[N,K]^T with kind::tf32, fp32 accumulate, one CTA.
  * mode 0: A from shared memory; mode 1: A from tensor memory.  N % 16 == 0, 16 <= N <= 256;

@@ -79,3 +79,26 @@ def layers_from_state_dict(sd, prefix, nlayers):
             L["bn"] = {k: sd[base + "bn.bn." + k] for k in ("weight", "bias", "running_mean", "running_var")}
         out.append(L)
     return out
+
+
+BACKBONE_SA = [  # models/backbone_module.py:44-78: (npoint, radius, nsample)
+    (2048, 0.2, 64), (1024, 0.4, 32), (512, 0.8, 16), (256, 1.2, 16)]
+
+
+def backbone_forward(sd, pointcloud, training=False):
+    """Pointnet2Backbone.forward (models/backbone_module.py:92-144) over a reference-named state dict
+    (`sa{1..4}.mlp_module.layer{i}.*`, `fp{1,2}.mlp.layer{i}.*`).  Returns the end_points dict."""
+    xyz = pointcloud[..., 0:3].contiguous()
+    features = pointcloud[..., 3:].transpose(1, 2).contiguous() if pointcloud.size(-1) > 3 else None
+    ep = {}
+    for i, (npoint, radius, nsample) in enumerate(BACKBONE_SA, start=1):
+        layers = layers_from_state_dict(sd, f"sa{i}.mlp_module.", 3)
+        xyz, features, inds, _ = sa_module_forward(xyz, features, npoint, radius, nsample, layers, True, training)
+        ep[f"sa{i}_xyz"], ep[f"sa{i}_features"], ep[f"sa{i}_inds"] = xyz, features, inds
+    f = fp_module_forward(ep["sa3_xyz"], ep["sa4_xyz"], ep["sa3_features"], ep["sa4_features"],
+                          layers_from_state_dict(sd, "fp1.mlp.", 2), training)
+    f = fp_module_forward(ep["sa2_xyz"], ep["sa3_xyz"], ep["sa2_features"], f,
+                          layers_from_state_dict(sd, "fp2.mlp.", 2), training)
+    ep["fp2_features"], ep["fp2_xyz"] = f, ep["sa2_xyz"]
+    ep["fp2_inds"] = ep["sa1_inds"][:, :ep["fp2_xyz"].shape[1]]
+    return ep

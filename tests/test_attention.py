@@ -1,0 +1,301 @@
+"""Cross-modal attention layers.
+
+CPU suite : the oracle (oracle/attention_oracle.py) against the golden outputs of the REFERENCE's own
+            models/encoder_decoder_layers.py (tests/golden/attn_*.npz, made by make_golden_attention.py),
+            state-dict key/shape identity of this repo's mirror classes, loud failure on CPU tensors.
+GPU suite : the CUDA layers (eda_b200/encoder_decoder_layers.py -> eda_linear_forward /
+            eda_attention_forward through the C ABI) against the same fixtures and against the oracle at the
+            BASELINE sizes (V=1024, L=80, D=132, K=256).
+
+Tolerance for the CUDA path (tf32 tensor-core operands, fp32 accumulation, fp32 softmax / LayerNorm;
+SURVEY.md 8c): one fused block (a GEMM, an attention core) rtol = atol = 2e-3; a whole layer = 6-7 chained
+blocks with LayerNorm in between, measured per-block max error 1.5e-3 / rms 2.5e-4 on O(1) outputs:
+max error <= 5e-3 and rms error <= 1e-3; the 3-layer encoder: 1e-2 / 2e-3.  Oracle vs reference
+fixture: 2e-5 (same fp32 maths, different association).
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import attn_cases as ac  # noqa: E402
+
+from eda_b200 import encoder_decoder_layers as edl  # noqa: E402
+from oracle import attention_oracle as ao  # noqa: E402
+
+TOL = dict(rtol=2e-3, atol=2e-3)
+
+
+def build(kind):
+    if kind == "bi_encoder_layer":
+        return edl.BiEncoderLayer(ac.E, dropout=0.1, activation="relu", n_heads=ac.HEADS, dim_feedforward=ac.FF,
+                                  self_attend_lang=True, self_attend_vis=True, use_butd_enc_attn=True)
+    if kind == "bi_encoder":
+        return edl.BiEncoder(build("bi_encoder_layer"), 3)
+    return edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.1, "relu", self_position_embedding="loc_learned", butd=True)
+
+
+def oracle_run(kind, sd, inp):
+    if kind == "bi_encoder_layer":
+        v, t = ao.bi_encoder_layer(sd, "", inp["vis"], inp["pos"], None, inp["text"], inp["text_mask"], inp["det"],
+                                   inp["det_mask"])
+        return dict(vis=v, text=t)
+    if kind == "bi_encoder":
+        v, t = ao.bi_encoder(sd, "", 3, inp["vis"], inp["pos"], None, inp["text"], inp["text_mask"], inp["det"],
+                             inp["det_mask"])
+        return dict(vis=v, text=t)
+    q = ao.bi_decoder_layer(sd, "", inp["query"], inp["vis"], inp["text"], inp["query_pos"], None, inp["text_mask"],
+                            inp["det"], inp["det_mask"])
+    return dict(query=q)
+
+
+def module_run(kind, m, inp):
+    if kind in ("bi_encoder_layer", "bi_encoder"):
+        v, t = m(inp["vis"], inp["pos"], None, inp["text"], inp["text_mask"], {}, detected_feats=inp["det"],
+                 detected_mask=inp["det_mask"])
+        return dict(vis=v, text=t)
+    q = m(inp["query"], inp["vis"], inp["text"], inp["query_pos"], None, inp["text_mask"], detected_feats=inp["det"],
+          detected_mask=inp["det_mask"])
+    return dict(query=q)
+
+
+def assert_layer_close(got, want, depth=1):
+    """max / rms error bounds for `depth` chained layers (see the module docstring)."""
+    err = (got.double() - want.double()).abs()
+    assert torch.isfinite(got).all()
+    lim_max, lim_rms = (5e-3, 1e-3) if depth == 1 else (1e-2, 2e-3)
+    rms = err.pow(2).mean().sqrt().item()
+    assert err.max().item() <= lim_max and rms <= lim_rms, f"max err {err.max().item():.3e}, rms err {rms:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU suite
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(ac.CASES))
+def test_oracle_matches_reference_fixture(name):
+    kind = ac.CASES[name][0]
+    fx = np.load(os.path.join(HERE, "golden", f"attn_{name}.npz"))
+    m = ac.fill_params(build(kind), seed=100 + len(name)).eval()
+    sd = m.state_dict()
+    # the mirror has exactly the reference's state-dict keys and shapes (checkpoints load)
+    assert sorted(sd.keys()) == list(fx["keys"])
+    assert [str(tuple(sd[k].shape)) for k in sorted(sd.keys())] == list(fx["shapes"])
+    with torch.no_grad():
+        out = oracle_run(kind, sd, ac.make_inputs(name))
+    for k, v in out.items():
+        torch.testing.assert_close(v, torch.from_numpy(fx[k]), rtol=2e-5, atol=2e-5)
+
+
+def test_layers_refuse_cpu_tensors():
+    m = build("bi_decoder_layer").eval()
+    inp = ac.make_inputs("dec_layer")
+    with pytest.raises(RuntimeError):
+        module_run("bi_decoder_layer", m, inp)
+
+
+def test_train_mode_dropout_is_loud():
+    m = build("bi_encoder_layer").train()
+    inp = ac.make_inputs("enc_layer")
+    with pytest.raises(RuntimeError):
+        module_run("bi_encoder_layer", m, inp)
+
+
+def test_oracle_masked_keys_have_no_influence():
+    m = ac.fill_params(build("bi_encoder_layer"), seed=3).eval()
+    sd = m.state_dict()
+    inp = ac.make_inputs("enc_layer")
+    with torch.no_grad():
+        a = oracle_run("bi_encoder_layer", sd, inp)
+        inp2 = dict(inp)
+        inp2["det"] = inp["det"].clone()
+        inp2["det"][inp["det_mask"]] = 1e3  # garbage in padded boxes
+        b = oracle_run("bi_encoder_layer", sd, inp2)
+    torch.testing.assert_close(a["vis"], b["vis"], rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU suite
+# ------------------------------------------------------------------------------------------------
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,K,N,relu,ln,pos", [
+    (300, 288, 288, False, False, True), (128, 288, 256, True, False, False), (1000, 256, 288, False, True, False),
+    (77, 6, 288, True, False, False), (513, 3, 288, False, False, False), (2048, 288, 288, False, True, True),
+    (5, 288, 64, False, False, False), (260, 40, 16, True, False, True),
+])
+def test_linear_kernel(R, K, N, relu, ln, pos):
+    from eda_b200 import attn_ops as ops
+
+    g = torch.Generator().manual_seed(R + K + N)
+    x = torch.randn(R, K, generator=g).cuda()
+    p = torch.randn(R, K, generator=g).cuda() if pos else None
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    res = torch.randn(R, N, generator=g).cuda() if ln else None
+    gam, bet = (1 + 0.1 * torch.randn(N, generator=g)).cuda(), (0.1 * torch.randn(N, generator=g)).cuda()
+    packed = ops.pack_weight(W)
+    (y,) = ops.linear_raw([dict(x=x, pos=p, w_packed=packed, bias=b, residual=res)], K, N, relu=relu,
+                          ln=(gam, bet, 1e-5) if ln else None)
+    xin = (x + p) if pos else x
+    ref = (xin.double() @ W.double().t() + b.double())
+    if relu:
+        ref = ref.clamp_min(0)
+    if ln:
+        ref = torch.nn.functional.layer_norm(ref + res.double(), (N,), gam.double(), bet.double(), 1e-5)
+        torch.testing.assert_close(y.double(), ref, **TOL)
+    else:
+        # tf32 operands: each product carries <= 2 * 2^-11 relative error -> bound on sum |x||w|
+        bound = xin.abs().double() @ W.abs().double().t()
+        assert ((y.double() - ref).abs() <= 1.1e-3 * bound + 1e-5).all()
+
+
+@pytest.mark.gpu
+def test_linear_kernel_three_problems_one_launch():
+    from eda_b200 import attn_ops as ops
+
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(r, 288, generator=g).cuda() for r in (130, 80, 1024)]
+    Ws = [(torch.randn(288, 288, generator=g) / 17).cuda() for _ in range(3)]
+    bs = [torch.randn(288, generator=g).cuda() for _ in range(3)]
+    ys = ops.linear_raw([dict(x=x, w_packed=ops.pack_weight(W), bias=b) for x, W, b in zip(xs, Ws, bs)], 288, 288)
+    for x, W, b, y in zip(xs, Ws, bs, ys):
+        torch.testing.assert_close(y.double(), x.double() @ W.double().t() + b.double(), **TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Nq,Nk,masked", [(2, 80, 80, True), (2, 256, 132, True), (2, 200, 1024, False),
+                                            (1, 1024, 1024, False), (3, 7, 5, True), (2, 129, 257, True)])
+def test_attention_kernel(B, Nq, Nk, masked):
+    from eda_b200 import attn_ops as ops
+
+    H, D = 8, 36
+    g = torch.Generator().manual_seed(B * 1000 + Nq + Nk)
+    q, k, v = (torch.randn(B, n, H * D, generator=g).cuda() for n in (Nq, Nk, Nk))
+    q = q * 2.0  # sharper softmax
+    mask = ac.ragged_mask(B, Nk, max(1, Nk // 3), g).cuda() if masked else None
+    ctx = ops.attention_raw(q.view(-1, H * D), k.view(-1, H * D), v.view(-1, H * D), mask, B, Nq, Nk, H).view(B, Nq, H * D)
+    qd = q.double().view(B, Nq, H, D).transpose(1, 2) / 6.0
+    kd = k.double().view(B, Nk, H, D).transpose(1, 2)
+    vd = v.double().view(B, Nk, H, D).transpose(1, 2)
+    s = qd @ kd.transpose(-1, -2)
+    if masked:
+        s = s.masked_fill(mask.view(B, 1, 1, Nk), float("-inf"))
+    ref = (torch.softmax(s, -1) @ vd).transpose(1, 2).reshape(B, Nq, H * D)
+    torch.testing.assert_close(ctx.double(), ref, **TOL)
+
+
+@pytest.mark.gpu
+def test_attention_fully_masked_row_is_nan_like_reference():
+    from eda_b200 import attn_ops as ops
+
+    H, D, B, Nq, Nk = 8, 36, 2, 40, 50
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(B, n, H * D, generator=g).cuda() for n in (Nq, Nk, Nk))
+    mask = torch.zeros(B, Nk, dtype=torch.bool).cuda()
+    mask[1] = True
+    ctx = ops.attention_raw(q.view(-1, H * D), k.view(-1, H * D), v.view(-1, H * D), mask, B, Nq, Nk, H).view(B, Nq, H * D)
+    assert torch.isfinite(ctx[0]).all() and torch.isnan(ctx[1]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(ac.CASES))
+def test_cuda_layers_match_reference_fixture(name):
+    kind = ac.CASES[name][0]
+    fx = np.load(os.path.join(HERE, "golden", f"attn_{name}.npz"))
+    m = ac.fill_params(build(kind), seed=100 + len(name)).eval().cuda()
+    with torch.no_grad():
+        out = module_run(kind, m, _cuda(ac.make_inputs(name)))
+    for k, v in out.items():
+        assert_layer_close(v.cpu(), torch.from_numpy(fx[k]), depth=3 if kind == "bi_encoder" else 1)
+
+
+def _full_inputs(B, V, L, D, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    return dict(vis=r(B, V, ac.E), pos=0.5 * r(B, V, ac.E), text=r(B, L, ac.E), text_mask=ac.ragged_mask(B, L, 20, g),
+                det=r(B, D, ac.E), det_mask=ac.ragged_mask(B, D, 20, g), query=r(B, K, ac.E),
+                query_pos=torch.cat([4 * torch.rand(B, K, 3, generator=g) - 2, torch.rand(B, K, 3, generator=g) + .2], -1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["bi_encoder_layer", "bi_encoder", "bi_decoder_layer"])
+def test_cuda_layers_match_oracle_at_baseline_sizes(kind):
+    """V=1024 seeds, L=80 tokens (ragged), D=132 boxes (ragged), K=256 queries (BASELINE.json configs[2])."""
+    B = 2
+    inp = _full_inputs(B, 1024, 80, 132, 256, seed=11)
+    m = ac.fill_params(build(kind), seed=21).eval()
+    with torch.no_grad():
+        want = oracle_run(kind, m.state_dict(), inp)
+        got = module_run(kind, m.cuda(), _cuda(inp))
+    for k in want:
+        assert_layer_close(got[k].cpu(), want[k], depth=3 if kind == "bi_encoder" else 1)
+
+
+@pytest.mark.gpu
+def test_cuda_masked_keys_have_no_influence():
+    m = ac.fill_params(build("bi_decoder_layer"), seed=4).eval().cuda()
+    inp = _cuda(ac.make_inputs("dec_layer"))
+    with torch.no_grad():
+        a = module_run("bi_decoder_layer", m, inp)["query"]
+        inp["det"] = inp["det"].clone()
+        inp["det"][inp["det_mask"]] = 1e3
+        inp["text"] = inp["text"].clone()
+        inp["text"][inp["text_mask"]] = -1e3
+        b = module_run("bi_decoder_layer", m, inp)["query"]
+    assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_seq_first_wrappers_match_reference_layout():
+    m = ac.fill_params(edl.PosTransformerEncoderLayerNoFFN(ac.E, ac.HEADS, 0.1), seed=9).eval()
+    g = torch.Generator().manual_seed(1)
+    src, pos = torch.randn(50, 2, ac.E, generator=g), torch.randn(50, 2, ac.E, generator=g)
+    with torch.no_grad():
+        want = ao.self_attention(m.state_dict(), "", src.transpose(0, 1), pos.transpose(0, 1)).transpose(0, 1)
+        got = m.cuda()(src.cuda(), pos.cuda())
+    assert got.shape == (50, 2, ac.E)
+    torch.testing.assert_close(got.cpu(), want, **TOL)
+
+
+@pytest.mark.gpu
+def test_backward_matches_torch_autograd():
+    """dropout = 0 training step through one decoder layer: grads of the CUDA path (recompute backward)
+    against autograd through the oracle maths run on the GPU in fp32."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.0, "relu", self_position_embedding="loc_learned", butd=True)
+    ac.fill_params(m, seed=5).cuda().eval()  # eval: BatchNorm1d of the pos-embed uses running stats in both paths
+    inp = _cuda(ac.make_inputs("dec_layer"))
+    q = inp["query"].clone().requires_grad_(True)
+    out = m(q, inp["vis"], inp["text"], inp["query_pos"], None, inp["text_mask"], detected_feats=inp["det"],
+            detected_mask=inp["det_mask"])
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    got = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    got_q = q.grad.clone()
+
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    q2 = inp["query"].clone().requires_grad_(True)
+    ref = ao.bi_decoder_layer(sd, "", q2, inp["vis"], inp["text"], inp["query_pos"], None, inp["text_mask"], inp["det"],
+                              inp["det_mask"])
+    (ref * w).sum().backward()
+
+    # Gradients are piecewise: a ReLU unit of the FFN / pos-embed whose pre-activation sits within the forward
+    # tolerance of zero flips between the two paths and changes one row of the gradient by O(0.1) (CPU check:
+    # 1e-3 input noise moves fp64 gradients by up to 0.3).  So: relative Frobenius error, not element-wise.
+    def rel(a, b):
+        return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+    assert rel(got_q, q2.grad) <= 3e-2
+    checked = 0
+    for n, gval in got.items():
+        assert rel(gval, sd[n].grad) <= 3e-2, n
+        checked += 1
+    assert checked > 20
