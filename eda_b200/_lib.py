@@ -38,9 +38,12 @@ PROTOTYPES = {
     "eda_linear_packed_floats": (_sz, [_c_int, _c_int]),
     "eda_linear_pack": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp]),
     "eda_linear_forward": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_float, _c_int, _vp]),
-    "eda_attention_forward": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp,
-                                       _vp]),
+    "eda_debug_timestamps": (_c_int, [_vp, _c_int]),
+    "eda_debug_timestamps_attn": (_c_int, [_vp, _c_int]),
+    "eda_attention_forward": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
+                                       _vp, _vp]),
     "eda_selftest_umma": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_selftest_umma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
 }
 
 
@@ -48,7 +51,7 @@ PROTOTYPES = {
 class LinearProblem(ctypes.Structure):
     """struct eda_linear_problem (include/eda_b200.h)."""
     _fields_ = [("x", _vp), ("pos", _vp), ("w_packed", _vp), ("bias", _vp), ("residual", _vp), ("y", _vp),
-                ("rows", _c_int)]
+                ("rows", _c_int), ("y_batch_rows", _c_int), ("y_ld", _c_int), ("round_tf32", _c_int)]
 
 
 _lib = None

@@ -97,7 +97,14 @@ def linear_raw(problems, K, N, relu=False, ln=None):
             pr["w_packed"].data_ptr()
         arr[i].bias = bias.data_ptr() if bias is not None else None
         arr[i].residual = res.data_ptr() if res is not None else None
+        tb = int(pr.get("y_batch_rows", 0))
+        if tb:
+            # channel-major output (batch, N, ld): what eda_attention_forward wants for V
+            ld = (tb + 3) & ~3
+            y = torch.empty((R // tb, N, ld), dtype=torch.float32, device=dev)
+            arr[i].y_batch_rows, arr[i].y_ld = tb, ld
         arr[i].y, arr[i].rows = y.data_ptr(), R
+        arr[i].round_tf32 = 1 if pr.get("round_tf32") else 0
         outs.append(y)
     g = b = None
     eps = 0.0
@@ -112,11 +119,14 @@ def linear_raw(problems, K, N, relu=False, ln=None):
     return outs
 
 
-def attention_raw(q, k, v, key_padding_mask, B, Nq, Nk, H):
-    """q (B*Nq,E), k, v (B*Nk,E) projected; mask (B,Nk) bool or None -> ctx (B*Nq,E)."""
+def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H):
+    """q (B*Nq,E), k (B*Nk,E) projected, vt (B,E,ld) channel-major projected values (ld >= Nk, ld % 4 == 0);
+    mask (B,Nk) bool or None -> ctx (B*Nq,E)."""
     lib = _lib.load()
     E = q.size(-1)
     D = E // H
+    assert vt.dim() == 3 and vt.size(0) == B and vt.size(1) == E and vt.is_contiguous()
+    ldv = vt.size(2)
     ctx = torch.empty((B * Nq, E), dtype=torch.float32, device=q.device)
     m = None
     if key_padding_mask is not None:
@@ -126,7 +136,7 @@ def attention_raw(q, k, v, key_padding_mask, B, Nq, Nk, H):
         m = m.contiguous().view(torch.uint8)
         assert m.shape == (B, Nk)
     with torch.cuda.device(q.device):
-        rc = lib.eda_attention_forward(_p(q), _p(k), _p(v), _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), _p(ctx),
+        rc = lib.eda_attention_forward(_p(q), _p(k), _p(vt), ldv, _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), _p(ctx),
                                        _stream(q.device))
     _lib.check(rc, "attention_forward")
     return ctx
@@ -171,8 +181,8 @@ class _MHABlockFn(torch.autograd.Function):
         ib = in_b.detach()
         q, k, v = linear_raw([
             dict(x=q_in, pos=qp, w_packed=wq, bias=ib[:E]),
-            dict(x=k_in, pos=kp, w_packed=wk, bias=ib[E:2 * E]),
-            dict(x=v_in, w_packed=wv, bias=ib[2 * E:]),
+            dict(x=k_in, pos=kp, w_packed=wk, bias=ib[E:2 * E], round_tf32=True),
+            dict(x=v_in, w_packed=wv, bias=ib[2 * E:], y_batch_rows=Nk, round_tf32=True),
         ], E, E)
         c = attention_raw(q, k, v, mask, B, Nq, Nk, H)
         res = residual.contiguous() if residual is not None else None

@@ -15,6 +15,32 @@ from .pointnet2 import pointnet2_utils
 from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
 
 
+def fps_chain(xyz, npoints, side, timing_events=None):
+    """Runs FPS(xyz, npoints[0]) -> FPS(of that subset, npoints[1]) -> ... on the CUDA stream `side`
+    (it first waits for the current stream).  Returns [(inds, event)] per stage; a consumer on another
+    stream waits for the event before using inds.  `timing_events` = (start, end) CUDA events recorded on
+    `side` around the FIRST stage (bench.py's roofline timing)."""
+    main = torch.cuda.current_stream(xyz.device)
+    side.wait_stream(main)
+    out = []
+    with torch.cuda.stream(side):
+        cur = xyz
+        for i, npoint in enumerate(npoints):
+            if i == 0 and timing_events is not None:
+                timing_events[0].record(side)
+            inds = pointnet2_utils.furthest_point_sample(cur, npoint)
+            if i == 0 and timing_events is not None:
+                timing_events[1].record(side)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            out.append((inds, ev))
+            if i + 1 < len(npoints):
+                cur = torch.gather(cur, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+                cur.record_stream(main)
+            inds.record_stream(main)
+    return out
+
+
 class Pointnet2Backbone(nn.Module):
     """Backbone network for point cloud feature learning (PointNet++ single-scale grouping)."""
 
@@ -49,25 +75,9 @@ class Pointnet2Backbone(nn.Module):
         return xyz, features
 
     def _fps_chain(self, xyz):
-        """All four FPS stages on a side stream.  Returns [(inds, event)] per stage."""
-        main = torch.cuda.current_stream(xyz.device)
         if self._side is None or self._side.device != xyz.device:
             self._side = torch.cuda.Stream(device=xyz.device)
-        side = self._side
-        side.wait_stream(main)
-        out = []
-        with torch.cuda.stream(side):
-            cur = xyz
-            for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
-                inds = pointnet2_utils.furthest_point_sample(cur, sa.npoint)
-                ev = torch.cuda.Event()
-                ev.record(side)
-                out.append((inds, ev))
-                if sa is not self.sa4:
-                    cur = torch.gather(cur, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
-                    cur.record_stream(main)
-                inds.record_stream(main)
-        return out
+        return fps_chain(xyz, [sa.npoint for sa in (self.sa1, self.sa2, self.sa3, self.sa4)], self._side)
 
     def forward(self, pointcloud, end_points=None):
         """pointcloud (B, N, 3 + input_feature_dim) -> end_points dict with sa{1..4}_{xyz,features},

@@ -23,11 +23,20 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, i
     mbar_init(&bar, 1);
     mbar_fence_init_cluster();
   }
-  for (int i = tid; i < (K / 4) * N; i += 128) {
-    const int c = i / N, n = i % N;
-    sW[i] = *reinterpret_cast<const float4 *>(W + (size_t)n * K + c * 4);
+  if (mode == 2) {
+    // MN-major B: float4 [N/4][K], one unit = 4 consecutive n of one k
+    for (int i = tid; i < (N / 4) * K; i += 128) {
+      const int j = i / K, k = i % K;
+      sW[i] = make_float4(W[(size_t)(4 * j) * K + k], W[(size_t)(4 * j + 1) * K + k], W[(size_t)(4 * j + 2) * K + k],
+                          W[(size_t)(4 * j + 3) * K + k]);
+    }
+  } else {
+    for (int i = tid; i < (K / 4) * N; i += 128) {
+      const int c = i / N, n = i % N;
+      sW[i] = *reinterpret_cast<const float4 *>(W + (size_t)n * K + c * 4);
+    }
   }
-  if (mode == 0) {
+  if (mode == 0 || mode == 2) {
     for (int c = 0; c < K / 4; ++c) sA[c * 128 + tid] = *reinterpret_cast<const float4 *>(A + (size_t)tid * K + c * 4);
   }
   umma::fence_proxy_async_smem();
@@ -50,10 +59,12 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, i
     umma::fence_after_thread_sync();
   }
   if (tid == 0) {
-    const uint32_t idesc = umma::idesc_tf32(128, N);
+    const uint32_t idesc = mode == 2 ? umma::idesc_tf32_bmn(128, N) : umma::idesc_tf32(128, N);
     for (int ks = 0; ks < K / 8; ++ks) {
-      const uint64_t bdesc = umma::smem_desc_kmajor_noswizzle(smem_u32(sW + ks * 2 * N), (uint32_t)N * 16u, 128u);
-      if (mode == 0) {
+      const uint64_t bdesc = mode == 2
+                                 ? umma::smem_desc_kmajor_noswizzle(smem_u32(sW + ks * 8), 128u, (uint32_t)K * 16u)
+                                 : umma::smem_desc_kmajor_noswizzle(smem_u32(sW + ks * 2 * N), (uint32_t)N * 16u, 128u);
+      if (mode == 0 || mode == 2) {
         const uint64_t adesc = umma::smem_desc_kmajor_noswizzle(smem_u32(sA + ks * 2 * 128), 128u * 16u, 128u);
         umma::mma_tf32_ss(tbase, adesc, bdesc, idesc, ks > 0);
       } else {
@@ -76,8 +87,63 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, i
   if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
+// Layout probe: one MMA (K = 8) with A = [I_8; 0] and the B region of shared memory filled with
+// float(i) at float index i, so D[k][n] = the shared-memory float index the hardware reads as B(n, k)
+// for the given descriptor strides / majorness.
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(int N, int lbo, int sbo, int b_mn, int layout, int start_off, float *__restrict__ D) {
+  __shared__ __align__(128) float4 sA[2 * 128];
+  __shared__ __align__(1024) float sB[4096];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_slot, 256);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init_cluster();
+  }
+  for (int c = 0; c < 2; ++c) {
+    float f[4];
+    for (int e = 0; e < 4; ++e) f[e] = (tid == c * 4 + e) ? 1.f : 0.f;
+    sA[c * 128 + tid] = make_float4(f[0], f[1], f[2], f[3]);
+  }
+  for (int i = tid; i < 4096; i += 128) sB[i] = (float)(i & 2047);
+  umma::fence_proxy_async_smem();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tbase = tmem_base_slot;
+  if (tid == 0) {
+    const uint32_t idesc = b_mn ? umma::idesc_tf32_bmn(128, N) : umma::idesc_tf32(128, N);
+    const uint64_t adesc = umma::smem_desc_kmajor_noswizzle(smem_u32(sA), 128u * 16u, 128u);
+    const uint64_t bdesc = umma::smem_desc_swizzled(smem_u32(sB) + (uint32_t)start_off, (uint32_t)lbo, (uint32_t)sbo, (uint32_t)layout);
+    umma::mma_tf32_ss(tbase, adesc, bdesc, idesc, 0);
+    umma::mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  umma::fence_after_thread_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    umma::tmem_ld16(umma::tmem_addr(tbase, (uint32_t)(warp * 32), c0), v);
+    umma::tmem_ld_wait();
+    if (tid < 8)
+      for (int j = 0; j < 16; ++j) D[(size_t)tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 256);
+}
+
 }  // namespace
 }  // namespace eda
+
+extern "C" int eda_selftest_umma_probe(int N, int lbo_bytes, int sbo_bytes, int b_mn_major, int layout_type,
+                                       int start_offset_bytes, float *D, void *stream) {
+  using namespace eda;
+  if (!D || N < 16 || N > 256 || N % 16) return EDA_ERR_INVALID_ARGUMENT;
+  umma_probe_kernel<<<1, 128, 0, as_stream(stream)>>>(N, lbo_bytes, sbo_bytes, b_mn_major, layout_type, start_offset_bytes, D);
+  return check_launch("umma_probe_kernel");
+}
 
 extern "C" int eda_selftest_umma(const float *A, const float *W, int N, int K, int mode, float *D, void *stream) {
   using namespace eda;

@@ -29,6 +29,15 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_noswizzle(uint32_t smem_add
   return d;
 }
 
+// Same descriptor with a swizzle mode: layout_type 0 = none, 1 = 128B (base 32B), 2 = 128B, 4 = 64B, 6 = 32B.
+// K-major SWIZZLE_128B: rows are 128 bytes (32 tf32), 8-row atoms of 1024 bytes (1024-byte aligned), the
+// 16-byte chunk j of row r sits at chunk position j ^ (r & 7); SBO = byte distance between 8-row atoms,
+// LBO unused; advancing K by 8 elements = +32 bytes on the start address.
+__device__ __forceinline__ uint64_t smem_desc_swizzled(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                       uint32_t layout_type) {
+  return smem_desc_kmajor_noswizzle(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)(layout_type & 7u) << 61);
+}
+
 // 32-bit instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4)                    // c_format = F32
@@ -37,6 +46,23 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
          | (0u << 15) | (0u << 16)    // a_major = K, b_major = K
          | ((uint32_t)(N >> 3) << 17) // n_dim
          | ((uint32_t)(M >> 4) << 24);// m_dim
+}
+
+// Same, B operand MN-major ("transposed": shared memory holds, per 16-byte unit, 4 consecutive N
+// elements of one k; 8 consecutive k are contiguous (128 B); descriptor SBO = byte distance between
+// 4-element N groups, LBO = byte distance between 8-k groups).
+__host__ __device__ constexpr uint32_t idesc_tf32_bmn(int M, int N) { return idesc_tf32(M, N) | (1u << 16); }
+
+// ---- Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS): many in flight, no registers.
+// src_bytes < 16 zero-fills the remainder (0 = pure zero fill, nothing is read).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ---- TMEM allocation ------------------------------------------------------------------------

@@ -1,0 +1,49 @@
+"""CUDA-graph capture of a forward pass built from the kernels of this package.
+
+The hot path is ~25 (SA backbone stage pair) to ~160 (3 encoder + 6 decoder layers) short kernel
+launches per forward; issued one by one from Python they are bound by host launch latency, not by the
+GPU.  `GraphedCallable` records one invocation — every kernel of libeda_b200.so launches on the
+current stream handed in through the C ABI, and the side-stream FPS chain of
+`backbone_module.fps_chain` forks from / joins the capturing stream, so the whole thing is
+capturable — and afterwards replays it with a single `cudaGraphLaunch`.
+
+Inference only: packed attention weights are cached across calls (attn_ops.pack_weight), so a graph
+recorded before an optimizer step would keep using the old packed copy.  Re-capture after changing
+weights.  Shapes are fixed at capture time (static input buffers, like any CUDA graph).
+"""
+import torch
+
+
+class GraphedCallable:
+    """graphed = GraphedCallable(fn, example_inputs); out = graphed(*inputs)
+
+    `fn` takes tensors positionally and returns a tensor or a (nested) tuple/list/dict of tensors.
+    Inputs are copied into static buffers before every replay; the returned tensors are the graph's
+    static outputs (valid until the next call — clone them if they must survive it)."""
+
+    def __init__(self, fn, example_inputs, warmup=3):
+        if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
+            raise RuntimeError("GraphedCallable needs CUDA tensor inputs")
+        self.device = example_inputs[0].device
+        self.static_inputs = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):  # fills caches (packed weights, smem attributes) outside the capture
+                fn(*self.static_inputs)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_outputs = fn(*self.static_inputs)
+
+    def __call__(self, *inputs):
+        if len(inputs) != len(self.static_inputs):
+            raise RuntimeError("GraphedCallable: wrong number of inputs")
+        for dst, src in zip(self.static_inputs, inputs):
+            if dst.shape != src.shape or dst.dtype != src.dtype:
+                raise RuntimeError("GraphedCallable: input shape/dtype differs from the captured one")
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_outputs

@@ -157,8 +157,11 @@ EDA_API int eda_transpose_last2(const float *in, int B, int R, int C, float *out
  *   16-byte aligned.  tcgen05 kind::tf32, fp32 accumulate.
  *
  * eda_attention_forward: ctx (B,Nq,H*D) = softmax(q k^T * scale + mask) v per head, q (B,Nq,H*D),
- *   k, v (B,Nk,H*D) already projected; key_padding_mask (B,Nk) bytes, nonzero = ignore (may be NULL).
- *   Replaces the bmm/softmax/bmm of the same math path.  D % 4 == 0, D <= 64.  A fully masked row
+ *   k (B,Nk,H*D) already projected, v CHANNEL-major vt (B,H*D,ldv) with ldv >= Nk, ldv % 4 == 0 (written
+ *   that way by eda_linear_forward with y_batch_rows = Nk: four consecutive keys of one channel are one
+ *   16-byte unit of the PV operand); k and vt are expected to hold tf32-representable values (eda_linear_forward
+ *   with round_tf32; other values are truncated by the tensor core); key_padding_mask (B,Nk) bytes, nonzero = ignore (may be NULL).
+ *   Replaces the bmm/softmax/bmm of the same math path.  Head dims compiled: D in {32, 36, 64}.  A fully masked row
  *   yields NaN as in the reference. */
 typedef struct eda_linear_problem {
   const float *x;        /* (rows, K) */
@@ -166,24 +169,38 @@ typedef struct eda_linear_problem {
   const float *w_packed; /* eda_linear_pack output for W (N, K) */
   const float *bias;     /* (N) or NULL */
   const float *residual; /* (rows, N) or NULL; only read when layer_norm != 0 */
-  float *y;              /* (rows, N) */
+  float *y;              /* (rows, N); or channel-major when y_batch_rows > 0 (below) */
   int rows;
+  int y_batch_rows;      /* 0: y row-major.  T > 0: rows are (batch, t < T) and y is (batch, N, y_ld) channel-major,
+                            y[(row / T * N + col) * y_ld + row % T] — how the attention kernel wants V */
+  int y_ld;              /* >= T; padding columns are not written */
+  int round_tf32;        /* != 0: round outputs to tf32 (round-to-nearest): K and V projections, whose outputs
+                            eda_attention_forward feeds to the tensor cores as they are */
 } eda_linear_problem;
 EDA_API size_t eda_linear_packed_floats(int N, int K);
 EDA_API int eda_linear_pack(const float *W, const float *scale, int N, int K, float *packed, void *stream);
 EDA_API int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu,
                                const float *ln_gamma, const float *ln_beta, float ln_eps, int layer_norm,
                                void *stream);
-EDA_API int eda_attention_forward(const float *q, const float *k, const float *v,
+/* Development aid: clock64() phase stamps of CTA 0 of the most recent eda_linear_forward launch (synchronises). */
+EDA_API int eda_debug_timestamps(long long *host_out, int n);
+EDA_API int eda_debug_timestamps_attn(long long *host_out, int n); /* same, attention kernel, key block 1 */
+EDA_API int eda_attention_forward(const float *q, const float *k, const float *vt, int ldv,
                                   const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
                                   float scale, float *ctx, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05/TMEM building blocks the fused kernels rely on (no reference
  * counterpart).  D[128,N] = A[128,K] * W[N,K]^T with kind::tf32, fp32 accumulate, one CTA.
- * mode 0: A from shared memory; mode 1: A from tensor memory.  N % 16 == 0, 16 <= N <= 256;
+ * mode 0: A from shared memory; mode 1: A from tensor memory; mode 2: A from shared memory, B staged
+ * MN-major (the layout the attention kernel uses for V).  N % 16 == 0, 16 <= N <= 256;
  * K % 16 == 0, 16 <= K <= 128. */
 EDA_API int eda_selftest_umma(const float *A, const float *W, int N, int K, int mode, float *D, void *stream);
+/* Shared-memory operand layout probe (development aid): one kind::tf32 MMA (K = 8) whose B descriptor has
+ * the given LBO / SBO / majorness / swizzle layout_type / start offset over a region holding float(i) at float index i; D (8, N) receives, for
+ * (k, n), the float index the hardware read as B(n, k). */
+EDA_API int eda_selftest_umma_probe(int N, int lbo_bytes, int sbo_bytes, int b_mn_major, int layout_type,
+                                    int start_offset_bytes, float *D, void *stream);
 
 #ifdef __cplusplus
 }

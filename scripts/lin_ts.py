@@ -1,0 +1,15 @@
+import ctypes, sys, os, torch
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from eda_b200 import _lib, attn_ops as ops
+lib = _lib.load()
+for R in (640, 8192):
+    x = torch.randn(R, 288, device="cuda"); W = torch.randn(288, 288, device="cuda") / 17; b = torch.randn(288, device="cuda")
+    pw = ops.pack_weight(W)
+    for ln in (False, True):
+        for it in range(3):
+            ops.linear_raw([dict(x=x, w_packed=pw, bias=b, residual=x if ln else None)], 288, 288, ln=(b, b, 1e-5) if ln else None)
+        torch.cuda.synchronize()
+        ts = (ctypes.c_longlong * 32)()
+        lib.eda_debug_timestamps(ts, 32)
+        t = list(ts)
+        print(f"R={R} ln={ln}: setup {t[1]-t[0]} staging_done {t[2]-t[1]} mma_done {t[3]-t[1]} epilogue: residual {t[8]-t[3]} tmem_pass {t[9]-t[8]} ln {t[10]-t[9]} copy_out {t[16]-t[10]} | epilogue_end {t[16]-t[1]} total {t[17]-t[0]} cycles")

@@ -125,6 +125,23 @@ def _cuda(d):
     return {k: v.cuda() for k, v in d.items()}
 
 
+def _round_tf32(t):
+    """cvt.rna.tf32.f32 (round to nearest, ties away) emulated on the fp32 bit pattern: what eda_linear_forward's
+    round_tf32 epilogue does to the K / V projections before eda_attention_forward consumes them."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _channel_major(v):
+    """(B, Nk, E) -> (B, E, ld) with ld = Nk rounded up to 4: the layout eda_attention_forward takes for V
+    (the V-projection GEMM writes it directly; here built with torch for the kernel-level tests)."""
+    B, Nk, E = v.shape
+    ld = (Nk + 3) & ~3
+    out = torch.full((B, E, ld), float("nan"), device=v.device)  # padding must never be read
+    out[:, :, :Nk] = v.transpose(1, 2)
+    return out
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("R,K,N,relu,ln,pos", [
     (300, 288, 288, False, False, True), (128, 288, 256, True, False, False), (1000, 256, 288, False, True, False),
@@ -180,8 +197,9 @@ def test_attention_kernel(B, Nq, Nk, masked):
     g = torch.Generator().manual_seed(B * 1000 + Nq + Nk)
     q, k, v = (torch.randn(B, n, H * D, generator=g).cuda() for n in (Nq, Nk, Nk))
     q = q * 2.0  # sharper softmax
+    k, v = _round_tf32(k), _round_tf32(v)  # the kernel's contract: K / V hold tf32-representable values
     mask = ac.ragged_mask(B, Nk, max(1, Nk // 3), g).cuda() if masked else None
-    ctx = ops.attention_raw(q.view(-1, H * D), k.view(-1, H * D), v.view(-1, H * D), mask, B, Nq, Nk, H).view(B, Nq, H * D)
+    ctx = ops.attention_raw(q.view(-1, H * D), k.view(-1, H * D), _channel_major(v), mask, B, Nq, Nk, H).view(B, Nq, H * D)
     qd = q.double().view(B, Nq, H, D).transpose(1, 2) / 6.0
     kd = k.double().view(B, Nk, H, D).transpose(1, 2)
     vd = v.double().view(B, Nk, H, D).transpose(1, 2)
@@ -198,10 +216,10 @@ def test_attention_fully_masked_row_is_nan_like_reference():
 
     H, D, B, Nq, Nk = 8, 36, 2, 40, 50
     g = torch.Generator().manual_seed(0)
-    q, k, v = (torch.randn(B, n, H * D, generator=g).cuda() for n in (Nq, Nk, Nk))
+    q, k, v = (_round_tf32(torch.randn(B, n, H * D, generator=g)).cuda() for n in (Nq, Nk, Nk))
     mask = torch.zeros(B, Nk, dtype=torch.bool).cuda()
     mask[1] = True
-    ctx = ops.attention_raw(q.view(-1, H * D), k.view(-1, H * D), v.view(-1, H * D), mask, B, Nq, Nk, H).view(B, Nq, H * D)
+    ctx = ops.attention_raw(q.view(-1, H * D), k.view(-1, H * D), _channel_major(v), mask, B, Nq, Nk, H).view(B, Nq, H * D)
     assert torch.isfinite(ctx[0]).all() and torch.isnan(ctx[1]).all()
 
 
