@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="eda_b200", choices=["eda_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (development)")
+    ap.add_argument("--no-pipeline", action="store_true", help="SA1 waits for the whole FPS result (development)")
     return ap.parse_args()
 
 
@@ -198,6 +199,9 @@ def gpu_arm(args):
 
     from eda_b200 import _lib, synthetic
     from eda_b200.backbone_module import fps_chain
+    from eda_b200.pointnet2 import fused
+
+    PIPELINE_EVERY = 0 if args.no_pipeline else (512, 256)
     from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,11 +234,18 @@ def gpu_arm(args):
         xyz = pc_dev[..., :3].contiguous()
         feats = pc_dev[..., 3:].transpose(1, 2).contiguous()
         main = torch.cuda.current_stream(dev)
-        (inds1, ev1), (inds2, ev2) = fps_chain(xyz, [SA1["npoint"], SA2["npoint"]], side, timed_fps)
-        main.wait_event(ev1)
-        x1, f1, _ = sa1(xyz, feats, inds1)
-        main.wait_event(ev2)
-        x2, f2, i2 = sa2(x1, f1, inds2)
+        (fps1, ev1), (fps2, ev2) = fps_chain(xyz, [SA1["npoint"], SA2["npoint"]], side, timed_fps,
+                                             pipeline_every=PIPELINE_EVERY)
+        if PIPELINE_EVERY:
+            # each SA stage consumes its sampler's centres in chunks while that FPS is still running (progress
+            # milestones + stream-ordered cuStreamWaitValue32): ball query + fused MLP fill the SMs FPS leaves idle
+            x1, f1, _, _ = fused.sa_forward_pipelined(sa1, xyz, feats, fps1)
+            x2, f2, _, i2 = fused.sa_forward_pipelined(sa2, x1, f1, fps2)
+        else:
+            main.wait_event(ev1)
+            x1, f1, _ = sa1(xyz, feats, fps1)
+            main.wait_event(ev2)
+            x2, f2, i2 = sa2(x1, f1, fps2)
         return x2, f2, i2
 
     def barrier():
@@ -319,6 +330,8 @@ def gpu_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "n_points": N_POINTS,
                    "l2": "512 MB memset between timed steps (inputs 9.6 MB < L2)", "sharding": "batch only, no collective",
+                   "overlap": ("ball query + fused MLP of each SA stage run on finished chunks of centres (512 / 256) while "
+                               "that stage's FPS continues on a side stream") if PIPELINE_EVERY else "SA2 FPS on a side stream",
                    "index_paths": "fp32, bit-exact", "mlp": "tcgen05 kind::tf32, fp32 accumulate"},
         "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},

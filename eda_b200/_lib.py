@@ -20,6 +20,12 @@ PROTOTYPES = {
     "eda_launch_count": (ctypes.c_ulonglong, []),
     "eda_fps_scratch_bytes": (_sz, [_c_int, _c_int, _c_int]),
     "eda_furthest_point_sampling": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "eda_furthest_point_sampling_progress": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp]),
+    "eda_stream_wait_value32": (_c_int, [_vp, _vp, _c_int]),
+    "eda_ball_query_range": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp]),
+    "eda_sa_mlp_forward_range": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
+                                          _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int,
+                                          _vp, _vp]),
     "eda_ball_query": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp]),
     "eda_group_points": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_group_points_grad": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),

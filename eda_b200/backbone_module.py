@@ -11,15 +11,17 @@ Results are identical to running the stages back to back.
 import torch
 import torch.nn as nn
 
-from .pointnet2 import pointnet2_utils
+from .pointnet2 import fused, pointnet2_utils
 from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
 
 
-def fps_chain(xyz, npoints, side, timing_events=None):
+def fps_chain(xyz, npoints, side, timing_events=None, pipeline_every=0):
     """Runs FPS(xyz, npoints[0]) -> FPS(of that subset, npoints[1]) -> ... on the CUDA stream `side`
     (it first waits for the current stream).  Returns [(inds, event)] per stage; a consumer on another
     stream waits for the event before using inds.  `timing_events` = (start, end) CUDA events recorded on
-    `side` around the FIRST stage (bench.py's roofline timing)."""
+    `side` around the FIRST stage (bench.py's roofline timing).  `pipeline_every` (an int for the first stage,
+    or one value per stage, 0 = off): that stage publishes progress milestones every so many samples and its
+    entry is (PipelinedFPS, event) — see fused.sa_forward_pipelined."""
     main = torch.cuda.current_stream(xyz.device)
     side.wait_stream(main)
     out = []
@@ -28,12 +30,19 @@ def fps_chain(xyz, npoints, side, timing_events=None):
         for i, npoint in enumerate(npoints):
             if i == 0 and timing_events is not None:
                 timing_events[0].record(side)
-            inds = pointnet2_utils.furthest_point_sample(cur, npoint)
+            handle = None
+            every = pipeline_every[i] if isinstance(pipeline_every, (list, tuple)) and i < len(pipeline_every) \
+                else (pipeline_every if (i == 0 and isinstance(pipeline_every, int)) else 0)
+            if every and every > 0:
+                handle = fused.launch_pipelined_fps(cur, npoint, every, side)
+                inds = handle.inds
+            else:
+                inds = pointnet2_utils.furthest_point_sample(cur, npoint)
             if i == 0 and timing_events is not None:
                 timing_events[1].record(side)
             ev = torch.cuda.Event()
             ev.record(side)
-            out.append((inds, ev))
+            out.append((handle if handle is not None else inds, ev))
             if i + 1 < len(npoints):
                 cur = torch.gather(cur, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
                 cur.record_stream(main)
@@ -67,6 +76,9 @@ class Pointnet2Backbone(nn.Module):
         self.fp1 = PointnetFPModule(mlp=[256 * width + 256 * width, 256 * width, 256 * width])
         self.fp2 = PointnetFPModule(mlp=[256 * width + 256 * width, 256 * width, output_dim])
         self.overlap_fps = True  # False: plain back-to-back stages (tests compare the two)
+        # inference only: SA1 consumes the sampler's output in chunks of this many centres while FPS is still
+        # running (0 = off; also off under autograd, in training mode and inside CUDA-graph capture)
+        self.pipeline_every = (512, 256)  # SA1, SA2 (SA3 / SA4 are too small to matter)
         self._side = None
 
     def _break_up_pc(self, pc):
@@ -74,10 +86,23 @@ class Pointnet2Backbone(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
-    def _fps_chain(self, xyz):
+    def _fps_chain(self, xyz, features):
         if self._side is None or self._side.device != xyz.device:
             self._side = torch.cuda.Stream(device=xyz.device)
-        return fps_chain(xyz, [sa.npoint for sa in (self.sa1, self.sa2, self.sa3, self.sa4)], self._side)
+        return fps_chain(xyz, [sa.npoint for sa in (self.sa1, self.sa2, self.sa3, self.sa4)], self._side,
+                         pipeline_every=self._pipeline_every(features))
+
+    def _pipeline_every(self, features):
+        if not self.pipeline_every or self.training or torch.is_grad_enabled():
+            return 0
+        if torch.cuda.is_current_stream_capturing() or self.sa1._fusable(features) is None:
+            return 0
+        # SA2's features are SA1's output: width known from the module, fusability checked the same way
+        f2 = torch.empty(1, self.sa2.mlp_module.fusable_layers()[0][0].in_channels - 3, 1, device=features.device) \
+            if self.sa2.mlp_module.fusable_layers() else None
+        if f2 is None or self.sa2._fusable(f2) is None:
+            return (self.pipeline_every[0],) if isinstance(self.pipeline_every, (list, tuple)) else self.pipeline_every
+        return self.pipeline_every
 
     def forward(self, pointcloud, end_points=None):
         """pointcloud (B, N, 3 + input_feature_dim) -> end_points dict with sa{1..4}_{xyz,features},
@@ -85,12 +110,15 @@ class Pointnet2Backbone(nn.Module):
         if not end_points:
             end_points = {}
         xyz, features = self._break_up_pc(pointcloud)
-        chain = self._fps_chain(xyz) if (self.overlap_fps and xyz.is_cuda) else None
+        chain = self._fps_chain(xyz, features) if (self.overlap_fps and xyz.is_cuda) else None
 
         def run(sa, k, xyz, features):
             if chain is None:
                 return sa(xyz, features)
             inds, ev = chain[k]
+            if isinstance(inds, fused.PipelinedFPS):
+                new_xyz, new_features, _, inds = fused.sa_forward_pipelined(sa, xyz, features, inds)
+                return new_xyz, new_features, inds
             torch.cuda.current_stream(xyz.device).wait_event(ev)
             return sa(xyz, features, inds)
 

@@ -26,8 +26,12 @@ constexpr int kTile = 2048;  // points per smem tile: 24 KB, x2 buffers
 constexpr unsigned kFull = 0xffffffffu;
 
 __global__ void __launch_bounds__(kBqThreads)
-ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict__ xyz_all, int N, int M, float r2,
-                  int nsample, int use_tma, int *__restrict__ idx_all) {
+ball_query_kernel(const float *__restrict__ new_xyz_all, const int *__restrict__ centre_idx,
+                  const float *__restrict__ xyz_all, int N, int M, int Mtot, int m0, float r2, int nsample, int use_tma,
+                  int *__restrict__ idx_all) {
+  // Centres m0 .. m0+M-1 of the Mtot centres of every scene (the plain op has m0 = 0, M = Mtot).  With
+  // centre_idx the centre coordinates are read through the FPS indices (xyz[centre_idx]) instead of new_xyz:
+  // bit-identical, and it lets the query start before the whole FPS result (and its gather) exists.
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *tile0 = reinterpret_cast<float *>(smem_raw);
   float *tile1 = tile0 + kTile * 3;
@@ -48,7 +52,8 @@ ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict
     const int c = centre0 + q;
     float x = 0.f, y = 0.f, z = 0.f;
     if (c < M) {
-      const float *p = new_xyz_all + ((size_t)b * M + c) * 3;
+      const size_t ci = (size_t)b * Mtot + m0 + c;
+      const float *p = centre_idx ? xyz + (size_t)__ldg(centre_idx + ci) * 3 : new_xyz_all + ci * 3;
       x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
     }
     if (q & 1) { cx[q >> 1].y = x; cy[q >> 1].y = y; cz[q >> 1].y = z; }
@@ -154,7 +159,7 @@ ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict
   for (int q = 0; q < kQ; ++q) {
     const int c = centre0 + q;
     if (c < M) {
-      int *out = idx_all + ((size_t)b * M + c) * nsample;
+      int *out = idx_all + ((size_t)b * Mtot + m0 + c) * nsample;
       const int have = cnt[q];
       const int first = have > 0 ? myhits[q * nsample] : 0;  // ball_query_gpu.cu:38-42 pads with the first hit
       for (int s = lane; s < nsample; s += 32) out[s] = s < have ? myhits[q * nsample + s] : first;
@@ -165,14 +170,15 @@ ball_query_kernel(const float *__restrict__ new_xyz_all, const float *__restrict
 }  // namespace
 }  // namespace eda
 
-extern "C" int eda_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius, int nsample,
-                              int *idx, void *stream) {
-  using namespace eda;
-  if (B < 0 || N < 0 || M < 0 || nsample < 0) return EDA_ERR_INVALID_ARGUMENT;
+namespace eda {
+namespace {
+int launch_ball_query(const float *new_xyz, const int *centre_idx, const float *xyz, int B, int N, int M, int Mtot, int m0,
+                      float radius, int nsample, int *idx, cudaStream_t st) {
+  if (B < 0 || N < 0 || M < 0 || nsample < 0 || m0 < 0 || m0 + M > Mtot) return EDA_ERR_INVALID_ARGUMENT;
   if (B == 0 || M == 0 || nsample == 0) return EDA_OK;
-  if (!new_xyz || !idx || (N > 0 && !xyz)) return EDA_ERR_INVALID_ARGUMENT;
-  cudaStream_t st = as_stream(stream);
+  if ((!new_xyz && !centre_idx) || !idx || (N > 0 && !xyz)) return EDA_ERR_INVALID_ARGUMENT;
   if (N == 0) {  // nothing to find: the reference returns its zero-initialised tensor
+    if (M != Mtot) return EDA_ERR_UNSUPPORTED;
     EDA_CUDA_TRY(cudaMemsetAsync(idx, 0, (size_t)B * M * nsample * sizeof(int), st), "ball_query memset");
     return EDA_OK;
   }
@@ -185,6 +191,21 @@ extern "C" int eda_ball_query(const float *new_xyz, const float *xyz, int B, int
   const int use_tma = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(xyz) & 15u) == 0);
   const float r2 = radius * radius;  // f32 product, ball_query_gpu.cu:27
   dim3 grid((unsigned)((M + kBqWarps * kQ - 1) / (kBqWarps * kQ)), (unsigned)B);
-  ball_query_kernel<<<grid, kBqThreads, smem, st>>>(new_xyz, xyz, N, M, r2, nsample, use_tma, idx);
+  ball_query_kernel<<<grid, kBqThreads, smem, st>>>(new_xyz, centre_idx, xyz, N, M, Mtot, m0, r2, nsample, use_tma, idx);
   return check_launch("ball_query_kernel");
+}
+}  // namespace
+}  // namespace eda
+
+extern "C" int eda_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius, int nsample,
+                              int *idx, void *stream) {
+  if (!new_xyz && B > 0 && M > 0 && nsample > 0) return EDA_ERR_INVALID_ARGUMENT;
+  return eda::launch_ball_query(new_xyz, nullptr, xyz, B, N, M, M, 0, radius, nsample, idx, eda::as_stream(stream));
+}
+
+extern "C" int eda_ball_query_range(const float *xyz, const int *centre_idx, int B, int N, int Mtot, int m0, int mc,
+                                    float radius, int nsample, int *idx, void *stream) {
+  if (!centre_idx && B > 0 && mc > 0 && nsample > 0) return EDA_ERR_INVALID_ARGUMENT;
+  return eda::launch_ball_query(nullptr, centre_idx, xyz, B, N, mc, Mtot, m0, radius, nsample, idx,
+                                eda::as_stream(stream));
 }

@@ -89,7 +89,8 @@ struct Layout {
 
 template <int P2, int CL, int T>
 __global__ void __launch_bounds__(T, 1)
-fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, int *__restrict__ idxs_all) {
+fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, int *__restrict__ idxs_all,
+                   int *__restrict__ progress, int every) {
   constexpr int P = 2 * P2;
   constexpr int kWarps = T / 32;
   extern __shared__ __align__(16) float s_xyz[];  // [P][T][3] copy of this CTA's points, then [P][T] ~codes
@@ -248,6 +249,13 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
         old = (int)(bitrev(code >> 23, lb) + ((code & 0x7fffffu) << lb));
       }
       idxs[it] = old;
+      // progress milestones (eda_furthest_point_sampling_progress): idxs[0..it] of this scene are final and
+      // visible device-wide before the counter moves, so a consumer released by a stream-ordered wait on the
+      // counter may start on the first (it + 1) centres while the sampling continues
+      if (progress != nullptr && ((it + 1) % every == 0 || it == m - 1)) {
+        __threadfence();
+        atomicAdd(progress, 1);
+      }
     }
   }
   if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still address its smem
@@ -259,7 +267,7 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
 constexpr int kGThreads = 1024;
 __global__ void __launch_bounds__(kGThreads, 1)
 fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float *__restrict__ temp_all,
-                  int *__restrict__ idxs_all) {
+                  int *__restrict__ idxs_all, int *__restrict__ progress, int every) {
   __shared__ Key s_warp[2][kGThreads / 32];
   const int scene = blockIdx.x;
   const float *__restrict__ xyz = xyz_all + (size_t)scene * N * 3;
@@ -307,7 +315,13 @@ fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float
       old = (int)(bitrev(code >> 23, lb) + ((code & 0x7fffffu) << lb));
     }
     ox = xyz[(size_t)old * 3]; oy = xyz[(size_t)old * 3 + 1]; oz = xyz[(size_t)old * 3 + 2];
-    if (tid == 0) idxs[it] = old;
+    if (tid == 0) {
+      idxs[it] = old;
+      if (progress != nullptr && ((it + 1) % every == 0 || it == m - 1)) {
+        __threadfence();
+        atomicAdd(progress, 1);
+      }
+    }
   }
 }
 
@@ -386,7 +400,8 @@ FpsPlan plan_fps(int B, int N, int lb) {
 }
 
 template <int P2, int CL, int T>
-int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int *idxs, cudaStream_t st) {
+int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int *idxs, int *progress, int every,
+                   cudaStream_t st) {
   auto kern = fps_cluster_kernel<P2, CL, T>;
   const size_t smem = (size_t)2 * P2 * T * 4 * sizeof(float);
   EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps smem attr");
@@ -404,37 +419,39 @@ int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, lay, idxs), "fps_cluster_kernel launch");
+  EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, lay, idxs, progress, every), "fps_cluster_kernel launch");
   return check_launch("fps_cluster_kernel");
 }
 
 template <int CL, int T>
-int dispatch_p(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, cudaStream_t st) {
+int dispatch_p(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, int *progress, int every,
+               cudaStream_t st) {
   if constexpr (T == 1024) {
     switch (pl.p2) {
-      case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-      case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-      case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+      case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+      case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+      case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
     }
     return EDA_ERR_UNSUPPORTED;
   }
   switch (pl.p2) {
-    case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-    case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-    case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-    case 6: return launch_cluster<6, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-    case 8: return launch_cluster<8, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-    case 10: return launch_cluster<10, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
-    case 13: return launch_cluster<13, CL, T>(xyz, B, N, m, pl.lay, idxs, st);
+    case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+    case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+    case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+    case 6: return launch_cluster<6, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+    case 8: return launch_cluster<8, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+    case 10: return launch_cluster<10, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+    case 13: return launch_cluster<13, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
   }
   return EDA_ERR_UNSUPPORTED;
 }
 
 template <int CL>
-int dispatch_t(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, cudaStream_t st) {
-  if (pl.t == 256) return dispatch_p<CL, 256>(pl, xyz, B, N, m, idxs, st);
-  if (pl.t == 512) return dispatch_p<CL, 512>(pl, xyz, B, N, m, idxs, st);
-  if (pl.t == 1024) return dispatch_p<CL, 1024>(pl, xyz, B, N, m, idxs, st);
+int dispatch_t(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, int *progress, int every,
+               cudaStream_t st) {
+  if (pl.t == 256) return dispatch_p<CL, 256>(pl, xyz, B, N, m, idxs, progress, every, st);
+  if (pl.t == 512) return dispatch_p<CL, 512>(pl, xyz, B, N, m, idxs, progress, every, st);
+  if (pl.t == 1024) return dispatch_p<CL, 1024>(pl, xyz, B, N, m, idxs, progress, every, st);
   return EDA_ERR_UNSUPPORTED;
 }
 
@@ -450,26 +467,62 @@ size_t eda_fps_scratch_bytes(int B, int N, int m) {
   return pl.cl == 0 ? (size_t)B * N * sizeof(float) : 0;
 }
 
-int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, void *scratch, int *idxs, void *stream) {
+static int fps_impl(const float *xyz, int B, int N, int m, void *scratch, int *idxs, int *progress, int every,
+                    void *stream) {
   using namespace eda;
   if (B < 0 || N < 0 || m < 0) return EDA_ERR_INVALID_ARGUMENT;
   if (B == 0 || m == 0) return EDA_OK;
   if (!xyz || !idxs || N == 0) return EDA_ERR_INVALID_ARGUMENT;
+  if (progress && every < 2) return EDA_ERR_INVALID_ARGUMENT;
   if (((long long)N >> 9) >= (1 << 23)) return EDA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   const int lb = ref_log2_block(N);
   const FpsPlan pl = plan_fps(B, N, lb);
   switch (pl.cl) {
-    case 1: return dispatch_t<1>(pl, xyz, B, N, m, idxs, st);
-    case 2: return dispatch_t<2>(pl, xyz, B, N, m, idxs, st);
-    case 4: return dispatch_t<4>(pl, xyz, B, N, m, idxs, st);
-    case 8: return dispatch_t<8>(pl, xyz, B, N, m, idxs, st);
-    case 16: return dispatch_t<16>(pl, xyz, B, N, m, idxs, st);
+    case 1: return dispatch_t<1>(pl, xyz, B, N, m, idxs, progress, every, st);
+    case 2: return dispatch_t<2>(pl, xyz, B, N, m, idxs, progress, every, st);
+    case 4: return dispatch_t<4>(pl, xyz, B, N, m, idxs, progress, every, st);
+    case 8: return dispatch_t<8>(pl, xyz, B, N, m, idxs, progress, every, st);
+    case 16: return dispatch_t<16>(pl, xyz, B, N, m, idxs, progress, every, st);
     default: break;
   }
   if (!scratch) return EDA_ERR_INVALID_ARGUMENT;
-  fps_global_kernel<<<B, kGThreads, 0, st>>>(xyz, N, m, lb, (float *)scratch, idxs);
+  fps_global_kernel<<<B, kGThreads, 0, st>>>(xyz, N, m, lb, (float *)scratch, idxs, progress, every);
   return check_launch("fps_global_kernel");
+}
+
+int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, void *scratch, int *idxs, void *stream) {
+  return fps_impl(xyz, B, N, m, scratch, idxs, nullptr, 0, stream);
+}
+
+int eda_furthest_point_sampling_progress(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
+                                         int *progress, int every, void *stream) {
+  if (!progress) return EDA_ERR_INVALID_ARGUMENT;
+  return fps_impl(xyz, B, N, m, scratch, idxs, progress, every, stream);
+}
+
+// Stream-ordered wait on a device word: work queued on `stream` after this call starts once
+// (int)(*addr - value) >= 0.  No SM is occupied while waiting (cuStreamWaitValue32, resolved through the runtime
+// so the library does not link against libcuda).
+int eda_stream_wait_value32(void *stream, const int *addr, int value) {
+  using namespace eda;
+  if (!addr) return EDA_ERR_INVALID_ARGUMENT;
+  typedef int (*wait_fn_t)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+  static wait_fn_t fn = nullptr;
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    EDA_CUDA_TRY(cudaGetDriverEntryPoint("cuStreamWaitValue32", &sym, cudaEnableDefault, &qres), "cuStreamWaitValue32 lookup");
+    if (!sym || qres != cudaDriverEntryPointSuccess) return EDA_ERR_UNSUPPORTED;
+    fn = reinterpret_cast<wait_fn_t>(sym);
+  }
+  const int rc = fn(as_stream(stream), (unsigned long long)reinterpret_cast<uintptr_t>(addr), (unsigned int)value,
+                    0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+  if (rc != 0) {
+    set_last_cuda_error(cudaErrorUnknown, "cuStreamWaitValue32");
+    return EDA_ERR_CUDA_LAUNCH;
+  }
+  return EDA_OK;
 }
 
 }  // extern "C"

@@ -43,7 +43,9 @@ struct SaParams {
   const float *xyz;      // (B,N,3)
   const float *new_xyz;  // (B,M,3)
   const float *feat;     // point-major features: row (b,i) at feat + (b*N+i)*feat_stride, C floats; null if C == 0
-  const int *idx;        // (B,M,S)
+  const int *idx;        // (B,Mtot,S)
+  const int *centre_idx; // optional (B,Mtot): centre j of scene b = xyz[b][centre_idx[b*Mtot+j]] instead of new_xyz
+  int Mtot, m0;          // this launch covers centres m0 .. m0+M-1 of the Mtot centres of every scene
   const float *packed;   // pre-packed weights (eda_sa_mlp_pack)
   const float *shift[3]; // per-layer additive term after the (scale-folded) conv; null = 0
   float *out;            // (B,M,C3) zero-initialised, stats_layer == 0
@@ -266,9 +268,11 @@ sa_mlp_kernel(const SaParams p) {
       const float *frow = nullptr;
       if (valid) {
         b = row / MS;
-        j = (row - b * MS) >> p.log2S;
-        const int pi = __ldg(p.idx + row);
-        const float *q = p.new_xyz + (b * p.M + j) * 3;
+        const long long rem = row - b * MS;
+        j = p.m0 + (rem >> p.log2S);
+        const int pi = __ldg(p.idx + (b * p.Mtot + j) * p.S + (rem & (p.S - 1)));
+        const float *q = p.centre_idx ? p.xyz + (b * p.N + __ldg(p.centre_idx + b * p.Mtot + j)) * 3
+                                      : p.new_xyz + (b * p.Mtot + j) * 3;
         const float *x = p.xyz + (b * p.N + pi) * 3;
         gx = __fsub_rn(__ldg(x), __ldg(q));  // pointnet2_utils.py:350  grouped_xyz -= new_xyz
         gy = __fsub_rn(__ldg(x + 1), __ldg(q + 1));
@@ -347,7 +351,7 @@ sa_mlp_kernel(const SaParams p) {
               // S >= 16 and a power of two: a centre's rows are one aligned 16-lane segment, one
               // warp, or several whole warps.
               const float *sh3 = s_shift + 2 * kMaxC + h * 128;
-              int *orow = reinterpret_cast<int *>(p.out) + (valid ? (b * p.M + j) * (long long)C3 + h * 128 : 0);
+              int *orow = reinterpret_cast<int *>(p.out) + (valid ? (b * p.Mtot + j) * (long long)C3 + h * 128 : 0);
               for (int c0 = 0; c0 < nblk; c0 += 16) {
                 uint32_t u[16];
                 umma::tmem_ld16(t_r1 + (uint32_t)c0, u);
@@ -529,18 +533,19 @@ int eda_sa_mlp_pack(const float *W1, const float *W2, const float *W3, const flo
   return check_launch("pack_layer_kernel", nlayers);
 }
 
-int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const float *feat, int feat_stride, const int *idx,
-                       const float *packed, const float *shift1, const float *shift2, const float *shift3, int B,
-                       int N, int M, int S, int C, int C1, int C2, int C3, float radius, int normalize_xyz,
-                       int stats_layer, float *out, float *stats, void *stream) {
+static int sa_mlp_forward_impl(const float *xyz, const float *new_xyz, const int *centre_idx, const float *feat,
+                               int feat_stride, const int *idx, const float *packed, const float *shift1,
+                               const float *shift2, const float *shift3, int B, int N, int M, int Mtot, int m0, int S,
+                               int C, int C1, int C2, int C3, float radius, int normalize_xyz, int stats_layer,
+                               int zero_fill, float *out, float *stats, void *stream) {
   using namespace eda;
-  if (B < 0 || N <= 0 || M < 0 || S <= 0) return EDA_ERR_INVALID_ARGUMENT;
+  if (B < 0 || N <= 0 || M < 0 || S <= 0 || m0 < 0 || m0 + M > Mtot) return EDA_ERR_INVALID_ARGUMENT;
   if (!dims_supported(C, C1, C2, C3) || stats_layer < 0 || stats_layer > 3) return EDA_ERR_UNSUPPORTED;
   const int log2S = ilog2_exact(S);
   if (log2S < 4) return EDA_ERR_UNSUPPORTED;  // S must be a power of two >= 16 (rows of a centre = aligned lane segments)
   const long long total = (long long)B * M * S;
   if (total == 0) return EDA_OK;
-  if (!xyz || !new_xyz || !idx || !packed || (C > 0 && !feat) || (stats_layer == 0 ? !out : !stats))
+  if (!xyz || (!new_xyz && !centre_idx) || !idx || !packed || (C > 0 && !feat) || (stats_layer == 0 ? !out : !stats))
     return EDA_ERR_INVALID_ARGUMENT;
   if (C > 0 && feat_stride < C) return EDA_ERR_INVALID_ARGUMENT;
   const long long ntiles = (total + kRows - 1) / kRows;
@@ -548,29 +553,53 @@ int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const float *feat
   cudaStream_t st = as_stream(stream);
 
   SaParams p = {};
-  p.xyz = xyz; p.new_xyz = new_xyz; p.feat = feat; p.idx = idx; p.packed = packed;
+  p.xyz = xyz; p.new_xyz = new_xyz; p.centre_idx = centre_idx; p.feat = feat; p.idx = idx; p.packed = packed;
   p.shift[0] = shift1; p.shift[1] = shift2; p.shift[2] = shift3;
   p.out = out; p.stats = stats; p.total_rows = total;
-  p.N = N; p.M = M; p.S = S; p.log2S = log2S; p.C = C; p.feat_stride = feat_stride;
+  p.N = N; p.M = M; p.Mtot = Mtot; p.m0 = m0; p.S = S; p.log2S = log2S; p.C = C; p.feat_stride = feat_stride;
   packed_floats(C, C1, C2, C3, &p.K0pad);
   p.Cout[0] = C1; p.Cout[1] = C2; p.Cout[2] = C3;
   p.normalize = normalize_xyz; p.radius = radius; p.stats_layer = stats_layer; p.ntiles = (int)ntiles;
 
   const int Cl = stats_layer ? p.Cout[stats_layer - 1] : 0;
-  if (stats_layer == 0)
-    EDA_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * M * C3 * sizeof(float), st), "sa out memset");
-  else
-    EDA_CUDA_TRY(cudaMemsetAsync(stats, 0, (size_t)2 * Cl * sizeof(float), st), "sa stats memset");
+  if (zero_fill) {
+    if (stats_layer == 0)
+      EDA_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * Mtot * C3 * sizeof(float), st), "sa out memset");
+    else
+      EDA_CUDA_TRY(cudaMemsetAsync(stats, 0, (size_t)2 * Cl * sizeof(float), st), "sa stats memset");
+  }
 
   const size_t smem = (size_t)kRing * kSlotBytes + 3 * kMaxC * sizeof(float);
-  EDA_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-               "sa smem attr");
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDA_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "sa smem attr");
+    attr_set = true;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
   sa_mlp_kernel<<<grid, kThreads, smem, st>>>(p);
   return check_launch("sa_mlp_kernel");
+}
+
+int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const float *feat, int feat_stride, const int *idx,
+                       const float *packed, const float *shift1, const float *shift2, const float *shift3, int B,
+                       int N, int M, int S, int C, int C1, int C2, int C3, float radius, int normalize_xyz,
+                       int stats_layer, float *out, float *stats, void *stream) {
+  if (!new_xyz && (long long)B * M * S > 0) return EDA_ERR_INVALID_ARGUMENT;
+  return sa_mlp_forward_impl(xyz, new_xyz, nullptr, feat, feat_stride, idx, packed, shift1, shift2, shift3, B, N, M, M, 0,
+                             S, C, C1, C2, C3, radius, normalize_xyz, stats_layer, 1, out, stats, stream);
+}
+
+int eda_sa_mlp_forward_range(const float *xyz, const int *centre_idx, const float *feat, int feat_stride,
+                             const int *idx, const float *packed, const float *shift1, const float *shift2,
+                             const float *shift3, int B, int N, int Mtot, int m0, int mc, int S, int C, int C1, int C2,
+                             int C3, float radius, int normalize_xyz, float *out, void *stream) {
+  if (!centre_idx && (long long)B * mc * S > 0) return EDA_ERR_INVALID_ARGUMENT;
+  return sa_mlp_forward_impl(xyz, nullptr, centre_idx, feat, feat_stride, idx, packed, shift1, shift2, shift3, B, N, mc,
+                             Mtot, m0, S, C, C1, C2, C3, radius, normalize_xyz, 0, 0, out, nullptr, stream);
 }
 
 int eda_bn_finalize(const float *stats, double count, const float *gamma, const float *beta, float eps,

@@ -106,6 +106,16 @@ def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, tr
                                     float(radius), 1 if normalize_xyz else 0, stats_layer, _p(out), _p(stats), stream)
         _lib.check(rc, "sa_mlp_forward")
 
+    if not (training and any(bn is not None for _, bn in layers)):
+        # eval mode: folded + packed weights are cached on the owning module
+        owner = layers[0][0]
+        packed_c, shifts_c = eval_packed(owner, layers, C, widths, dev)
+        packed = packed_c
+        shifts = list(shifts_c)
+        with torch.cuda.device(dev):
+            out = torch.empty((B, M, widths[2]), dtype=torch.float32, device=dev)
+            run(0, out, None)
+        return out
     with torch.cuda.device(dev):
         for l, (conv, bn) in enumerate(layers):
             batch_stats = training and bn is not None
@@ -194,3 +204,128 @@ def sa_params(layers):
             out.append(bn.weight)
             out.append(bn.bias)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Pipelined inference path: ball query + fused MLP on the centres FPS has already produced
+# ---------------------------------------------------------------------------------------------------
+class ProgressCounter:
+    """A device word that eda_furthest_point_sampling_progress increments (never reset) plus the host-side
+    running total, so every launch knows which absolute values its milestones will reach."""
+    _by_device = {}
+
+    def __init__(self, device):
+        self.word = torch.zeros(1, dtype=torch.int32, device=device)
+        self.total = 0
+
+    @classmethod
+    def get(cls, device):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        pc = cls._by_device.get(key)
+        if pc is None:
+            pc = cls._by_device[key] = ProgressCounter(device)
+        return pc
+
+
+class PipelinedFPS:
+    """Handle of an in-flight furthest-point sampling launched with progress milestones every `every` samples."""
+
+    def __init__(self, inds, counter, base, every, done_event):
+        self.inds, self.counter, self.base, self.every, self.done_event = inds, counter, base, every, done_event
+        self.B, self.m = inds.shape
+        self.nchunks = (self.m + every - 1) // every
+
+    def wait_chunk(self, stream, j):
+        """Makes `stream` wait (on the device, no SM occupied) until centres [0, (j+1)*every) of every scene exist."""
+        rc = _lib.load().eda_stream_wait_value32(ctypes.c_void_p(stream.cuda_stream), _p(self.counter.word),
+                                                 int(self.base + self.B * (j + 1)))
+        _lib.check(rc, "stream_wait_value32")
+
+
+def launch_pipelined_fps(xyz, npoint, every, stream):
+    """Launches FPS(xyz, npoint) on `stream` with progress milestones.  Returns a PipelinedFPS."""
+    lib = _lib.load()
+    B, N, _ = xyz.shape
+    counter = ProgressCounter.get(xyz.device)
+    with torch.cuda.stream(stream):
+        inds = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+        nbytes = lib.eda_fps_scratch_bytes(B, N, npoint)
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=xyz.device) if nbytes else None
+        with torch.cuda.device(xyz.device):
+            rc = lib.eda_furthest_point_sampling_progress(_p(xyz), B, N, npoint, _p(scratch), _p(inds), _p(counter.word),
+                                                          int(every), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "furthest_point_sampling_progress")
+        base = counter.total
+        counter.total += B * ((npoint + every - 1) // every)
+        done = torch.cuda.Event()
+        done.record(stream)
+    return PipelinedFPS(inds, counter, base, every, done)
+
+
+def eval_packed(module, layers, C, widths, dev):
+    """Eval-mode (running-statistics) folded + packed weights and per-layer shifts of a fused SA module, cached on
+    the module until a parameter or BatchNorm buffer changes (in-place update bumps `_version`; .to() / load
+    reallocates)."""
+    lib = _lib.load()
+    tensors = []
+    for conv, bn in layers:
+        tensors += [conv.weight, conv.bias]
+        if bn is not None:
+            tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (C, str(dev))
+    hit = module.__dict__.get("_eda_sa_eval_cache")
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    nfl = lib.eda_sa_mlp_packed_floats(C, *widths)
+    Ws = [conv.weight.detach().reshape(conv.out_channels, -1).contiguous() for conv, _ in layers]
+    scales, shifts = [None] * 3, [None] * 3
+    with torch.cuda.device(dev):
+        for l, (conv, bn) in enumerate(layers):
+            scales[l], shifts[l] = _bn_scale_shift(lib, dev, None, 0.0, bn, conv.bias, widths[l], False)
+        packed = torch.empty(nfl, dtype=torch.float32, device=dev)
+        rc = lib.eda_sa_mlp_pack(_p(Ws[0]), _p(Ws[1]), _p(Ws[2]), _p(scales[0]), _p(scales[1]), _p(scales[2]), C, *widths,
+                                 3, _p(packed), _stream(dev))
+        _lib.check(rc, "sa_mlp_pack")
+    module.__dict__["_eda_sa_eval_cache"] = (key, packed, shifts)
+    return packed, shifts
+
+
+def sa_forward_pipelined(module, xyz, features, fps):
+    """Eval-mode fused set abstraction consuming `fps` chunk by chunk on the current stream: for every chunk of
+    centres, wait for the sampler's milestone, ball-query it, run the fused group + MLP + max-pool on it.
+    Results are identical to the unpipelined path (same kernels, same arithmetic).
+    Returns new_xyz (B,M,3), new_features (B,C3,M), feat_pm (B,M,C3), inds (B,M)."""
+    lib = _lib.load()
+    dev = xyz.device
+    layers = module.mlp_module.fusable_layers()
+    assert layers is not None and len(layers) == 3 and not module.training
+    B, N, _ = xyz.shape
+    M, S = fps.m, module.nsample
+    feat_pm = None if features is None else point_major(features)
+    C = 0 if feat_pm is None else feat_pm.size(2)
+    widths = [conv.out_channels for conv, _ in layers]
+    nfl = lib.eda_sa_mlp_packed_floats(C, *widths)
+    assert nfl > 0
+    main = torch.cuda.current_stream(dev)
+    stream = _stream(dev)
+    packed, shifts = eval_packed(layers[0][0], layers, C, widths, dev)
+    with torch.cuda.device(dev):
+        idx = torch.empty((B, M, S), dtype=torch.int32, device=dev)
+        out = torch.zeros((B, M, widths[2]), dtype=torch.float32, device=dev)
+        feat_stride = 0 if feat_pm is None else feat_pm.stride(1)
+        fps.inds.record_stream(main)
+        for j in range(fps.nchunks):
+            m0 = j * fps.every
+            mc = min(fps.every, M - m0)
+            fps.wait_chunk(main, j)
+            rc = lib.eda_ball_query_range(_p(xyz), _p(fps.inds), B, N, M, m0, mc, float(module.radius), S, _p(idx), stream)
+            _lib.check(rc, "ball_query_range")
+            rc = lib.eda_sa_mlp_forward_range(_p(xyz), _p(fps.inds), _p(feat_pm), feat_stride, _p(idx), _p(packed),
+                                              _p(shifts[0]), _p(shifts[1]), _p(shifts[2]), B, N, M, m0, mc, S, C, *widths,
+                                              float(module.radius), 1 if module.normalize_xyz else 0, _p(out), stream)
+            _lib.check(rc, "sa_mlp_forward_range")
+    main.wait_event(fps.done_event)
+    new_xyz = torch.gather(xyz, 1, fps.inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    new_features = transpose_last2(out)
+    new_features._eda_point_major = out
+    return new_xyz, new_features, out, fps.inds

@@ -61,6 +61,17 @@ EDA_API size_t eda_fps_scratch_bytes(int B, int N, int m);
 EDA_API int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
                                 void *stream);
 
+/* Same sampling, publishing progress: after every `every` samples (and after the last one) of a scene, that
+ * scene's cluster makes its indices so far visible device-wide and adds 1 to *progress (never reset by the
+ * library: the caller tracks the running total, B increments per milestone).  Together with
+ * eda_stream_wait_value32 this lets a second stream run ball query + the fused MLP on the first centres while
+ * the strictly serial sampling of the remaining ones continues on otherwise idle SMs.  every >= 2. */
+EDA_API int eda_furthest_point_sampling_progress(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
+                                                 int *progress, int every, void *stream);
+/* Stream-ordered wait on a device word: work queued on `stream` after this call starts once
+ * (int)(*addr - value) >= 0 (cuStreamWaitValue32; no SM is occupied while waiting). */
+EDA_API int eda_stream_wait_value32(void *stream, const int *addr, int value);
+
 /* Ball query.
  * Replaces: at::Tensor ball_query(at::Tensor new_xyz, at::Tensor xyz, const float radius,
  *           const int nsample)  pointnet2/_ext_src/src/ball_query.cpp:13-37
@@ -69,6 +80,11 @@ EDA_API int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, v
  * an empty ball), so idx need not be pre-zeroed.  Bit-exact. */
 EDA_API int eda_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
                    int nsample, int *idx, void *stream);
+
+/* Ball query for centres m0 .. m0+mc-1 of the Mtot centres of every scene, centre coordinates read through
+ * the FPS indices (xyz[centre_idx[b*Mtot + j]], bit-identical to new_xyz); writes rows m0.. of idx (B,Mtot,nsample). */
+EDA_API int eda_ball_query_range(const float *xyz, const int *centre_idx, int B, int N, int Mtot, int m0, int mc,
+                                 float radius, int nsample, int *idx, void *stream);
 
 /* Grouping.  Replaces group_points / group_points_grad,
  * pointnet2/_ext_src/src/group_points.cpp:17-65 (kernels group_points_gpu.cu:13-80).
@@ -135,6 +151,12 @@ EDA_API int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const flo
                                const float *shift3, int B, int N, int M, int S, int C, int C1, int C2, int C3,
                                float radius, int normalize_xyz, int stats_layer, float *out, float *stats,
                                void *stream);
+/* eda_sa_mlp_forward (stats_layer 0) for centres m0 .. m0+mc-1 only, centres given by FPS index; `out`
+ * (B,Mtot,C3) must have been zero-filled by the caller (once, before the first range). */
+EDA_API int eda_sa_mlp_forward_range(const float *xyz, const int *centre_idx, const float *feat, int feat_stride,
+                                     const int *idx, const float *packed, const float *shift1, const float *shift2,
+                                     const float *shift3, int B, int N, int Mtot, int m0, int mc, int S, int C, int C1,
+                                     int C2, int C3, float radius, int normalize_xyz, float *out, void *stream);
 EDA_API int eda_bn_finalize(const float *stats, double count, const float *gamma, const float *beta, float eps,
                             float momentum, float *running_mean, float *running_var, int update_running, int C,
                             float *scale, float *shift, float *save_mean, float *save_invstd, void *stream);

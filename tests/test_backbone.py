@@ -56,3 +56,30 @@ def test_backbone_matches_oracle_and_overlap_is_invisible():
         assert err.pow(2).mean().sqrt() <= 2e-3, (k, err.pow(2).mean().sqrt().item())
         assert torch.equal(got[k], plain[k]), k  # side-stream FPS chain changes nothing
     assert got["fp2_features"].shape == (2, 288, 1024)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("every", [512, 300, 2048])
+def test_pipelined_sa1_equals_plain(every):
+    """SA1 fed chunk by chunk from the in-flight sampler (progress milestones + stream-ordered waits) gives
+    exactly what the plain path gives: same indices, same neighbour lists, same features."""
+    from eda_b200.backbone_module import fps_chain
+    from eda_b200.pointnet2 import fused
+    from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
+
+    torch.manual_seed(0)
+    sa = PointnetSAModuleVotes(npoint=2048, radius=0.2, nsample=64, mlp=[3, 64, 64, 128], use_xyz=True,
+                               normalize_xyz=True).cuda().eval()
+    _randomise_bn(sa, 2)
+    pc = synthetic.point_clouds(3, 20000, "surface").cuda()
+    xyz, feats = pc[..., :3].contiguous(), pc[..., 3:].transpose(1, 2).contiguous()
+    side = torch.cuda.Stream()
+    with torch.no_grad():
+        want_xyz, want_f, want_inds = sa(xyz, feats)
+        for _ in range(2):  # twice: the progress counter is never reset, the second call starts from a non-zero base
+            (handle, _ev), = fps_chain(xyz, [2048], side, pipeline_every=every)
+            got_xyz, got_f, _, got_inds = fused.sa_forward_pipelined(sa, xyz, feats, handle)
+            torch.cuda.synchronize()
+            assert torch.equal(got_inds, want_inds)
+            assert torch.equal(got_xyz, want_xyz)
+            assert torch.equal(got_f, want_f)
