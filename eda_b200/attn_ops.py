@@ -6,7 +6,9 @@ encoder_decoder_layers.py are made of:
     ffn_block  : LayerNorm(x + W2 relu(W1 x + b1) + b2)
     linear     : act(x W^T + b)
 
-Forward = hand-written CUDA only (3 launches per mha_block, 2 per ffn_block).  Backward (round 1) =
+Forward = hand-written CUDA only (3 launches per mha_block, 2 per ffn_block); train-mode dropout (attention
+probabilities, block outputs, FFN hidden) is applied inside those kernels from a counter-based hash and the
+backward pass regenerates the same masks (eda_dropout_mask).  Backward (round 1) =
 recompute of the same maths with differentiable torch ops on the GPU, as for the fused SA kernel.
 There is no CPU path: CPU tensors raise RuntimeError like the rest of the package.
 """
@@ -73,8 +75,24 @@ def pack_weight(W, scale=None, cache_key=None):
     return packed
 
 
-def linear_raw(problems, K, N, relu=False, ln=None):
-    """problems: list (<= 3) of dicts x (R,K), w_packed, optional pos, bias, residual.  Returns [y (R,N)]."""
+def new_seed():
+    """A 32-bit dropout seed drawn from torch's default CPU generator (so torch.manual_seed makes runs repeatable)."""
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
+def dropout_mask(seed, p, rows, cols, a_mul, a_add, device):
+    """(rows, cols) f32 keep-mask (1 / 0) that a forward kernel seeded `seed` applied (see include/eda_b200.h)."""
+    out = torch.empty((rows, cols), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = _lib.load().eda_dropout_mask(int(seed), float(p), int(rows), int(cols), int(a_mul), int(a_add), _p(out),
+                                          _stream(device))
+    _lib.check(rc, "dropout_mask")
+    return out
+
+
+def linear_raw(problems, K, N, relu=False, ln=None, dropout=None):
+    """problems: list (<= 3) of dicts x (R,K), w_packed, optional pos, bias, residual.  Returns [y (R,N)].
+    dropout = (p, seed): zero each output element with probability p (after bias / ReLU, before the residual)."""
     lib = _lib.load()
     dev = problems[0]["x"].device
     arr = (_lib.LinearProblem * len(problems))()
@@ -113,13 +131,14 @@ def linear_raw(problems, K, N, relu=False, ln=None):
         g = g.detach().contiguous() if g is not None else None
         b = b.detach().contiguous() if b is not None else None
     with torch.cuda.device(dev):
+        dp, dseed = dropout if dropout is not None else (0.0, 0)
         rc = lib.eda_linear_forward(ctypes.cast(arr, ctypes.c_void_p), len(problems), K, N, 1 if relu else 0, _p(g),
-                                    _p(b), float(eps), 1 if ln is not None else 0, _stream(dev))
+                                    _p(b), float(eps), 1 if ln is not None else 0, float(dp), int(dseed), _stream(dev))
     _lib.check(rc, "linear_forward")
     return outs
 
 
-def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H):
+def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H, dropout=None):
     """q (B*Nq,E), k (B*Nk,E) projected, vt (B,E,ld) channel-major projected values (ld >= Nk, ld % 4 == 0);
     mask (B,Nk) bool or None -> ctx (B*Nq,E)."""
     lib = _lib.load()
@@ -136,8 +155,9 @@ def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H):
         m = m.contiguous().view(torch.uint8)
         assert m.shape == (B, Nk)
     with torch.cuda.device(q.device):
-        rc = lib.eda_attention_forward(_p(q), _p(k), _p(vt), ldv, _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), _p(ctx),
-                                       _stream(q.device))
+        dp, dseed = dropout if dropout is not None else (0.0, 0)
+        rc = lib.eda_attention_forward(_p(q), _p(k), _p(vt), ldv, _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), float(dp),
+                                       int(dseed), _p(ctx), _stream(q.device))
     _lib.check(rc, "attention_forward")
     return ctx
 
@@ -145,7 +165,7 @@ def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H):
 # ---------------------------------------------------------------------------------------------------
 # differentiable restatements (backward only)
 # ---------------------------------------------------------------------------------------------------
-def _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H):
+def _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H, attn_keep=None, attn_scale=1.0):
     E = q_in.size(-1)
     D = E // H
     B, Nq, _ = q_in.shape
@@ -159,13 +179,17 @@ def _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H
     s = q @ k.transpose(-1, -2)
     if mask is not None:
         s = s.masked_fill(mask.view(B, 1, 1, Nk), float("-inf"))
-    ctx = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, Nq, E)
+    pr = torch.softmax(s, dim=-1)
+    if attn_keep is not None:
+        pr = pr * (attn_keep.view(B, H, Nq, Nk) * attn_scale)
+    ctx = (pr @ v).transpose(1, 2).reshape(B, Nq, E)
     return F.linear(ctx, out_w, out_b)
 
 
 class _MHABlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, H, eps, key, mask, q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b):
+    def forward(ctx, H, eps, key, mask, q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b,
+                drop=(0.0, 0, 0.0, 0)):
         E = q_in.size(-1)
         B, Nq, _ = q_in.shape
         Nk = k_in.size(1)
@@ -184,25 +208,35 @@ class _MHABlockFn(torch.autograd.Function):
             dict(x=k_in, pos=kp, w_packed=wk, bias=ib[E:2 * E], round_tf32=True),
             dict(x=v_in, w_packed=wv, bias=ib[2 * E:], y_batch_rows=Nk, round_tf32=True),
         ], E, E)
-        c = attention_raw(q, k, v, mask, B, Nq, Nk, H)
+        p_attn, seed_attn, p_out, seed_out = drop
+        c = attention_raw(q, k, v, mask, B, Nq, Nk, H, dropout=(p_attn, seed_attn) if p_attn > 0 else None)
         res = residual.contiguous() if residual is not None else None
         ln = (ln_w, ln_b, eps) if ln_w is not None else None
-        (y,) = linear_raw([dict(x=c, w_packed=wo, bias=out_b, residual=res)], E, E, ln=ln)
+        (y,) = linear_raw([dict(x=c, w_packed=wo, bias=out_b, residual=res)], E, E, ln=ln,
+                          dropout=(p_out, seed_out) if p_out > 0 else None)
         if ln is None and res is not None:
             y = y + res.view(-1, E)
         ctx.save_for_backward(q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b)
-        ctx.meta = (H, eps, mask)
+        ctx.meta = (H, eps, mask, drop)
         return y.view(B, Nq, E)
 
     @staticmethod
     def backward(ctx, grad):
-        H, eps, mask = ctx.meta
+        H, eps, mask, drop = ctx.meta
+        p_attn, seed_attn, p_out, seed_out = drop
         saved = ctx.saved_tensors
         with torch.enable_grad():
             ts = [None if t is None else t.detach().requires_grad_(ctx.needs_input_grad[4 + i])
                   for i, t in enumerate(saved)]
             q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b = ts
-            y = _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H)
+            B_, Nq_, E_ = q_in.shape
+            attn_keep = None
+            if p_attn > 0:  # the exact keep-mask the forward kernel applied
+                attn_keep = dropout_mask(seed_attn, p_attn, B_ * H * Nq_, k_in.size(1), 1, 0, q_in.device)
+            y = _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H, attn_keep,
+                           1.0 / (1.0 - p_attn))
+            if p_out > 0:
+                y = y * (dropout_mask(seed_out, p_out, B_ * Nq_, E_, 3, 0, q_in.device).view_as(y) * (1.0 / (1.0 - p_out)))
             if residual is not None:
                 y = residual + y
             if ln_w is not None:
@@ -210,35 +244,39 @@ class _MHABlockFn(torch.autograd.Function):
             wanted = [t for t in ts if t is not None and t.requires_grad]
             grads = torch.autograd.grad(y, wanted, grad, allow_unused=True) if wanted else []
         gmap = {id(t): g for t, g in zip(wanted, grads)}
-        return (None, None, None, None, *[gmap.get(id(t)) if t is not None else None for t in ts])
+        return (None, None, None, None, *[gmap.get(id(t)) if t is not None else None for t in ts], None)
 
 
-def mha_block(mha, q_in, k_in, v_in, q_pos=None, k_pos=None, key_padding_mask=None, residual=None, norm=None):
+def mha_block(mha, q_in, k_in, v_in, q_pos=None, k_pos=None, key_padding_mask=None, residual=None, norm=None,
+              out_dropout=None):
     """LayerNorm(residual + MHA(q_in + q_pos, k_in + k_pos, v_in)) with `mha` an nn.MultiheadAttention
     (parameters only) and `norm` an nn.LayerNorm (or None: no residual LayerNorm, plain attention output
     [+ residual]).  All activations batch-first (B, S, E)."""
-    if mha.training and mha.dropout > 0.0:
-        raise RuntimeError("eda_b200: train-mode attention dropout > 0 is not fused yet; set dropout=0 "
-                           "(parity configuration, SURVEY.md 8c) or call .eval()")
+    p_attn = float(mha.dropout) if mha.training else 0.0
+    p_out = float(out_dropout.p) if (out_dropout is not None and out_dropout.training) else 0.0
+    drop = (p_attn, new_seed() if p_attn > 0 else 0, p_out, new_seed() if p_out > 0 else 0)
     return _MHABlockFn.apply(mha.num_heads, norm.eps if norm is not None else 0.0, mha, key_padding_mask, q_in,
                              q_pos, k_in, k_pos, v_in, residual, mha.in_proj_weight, mha.in_proj_bias,
                              mha.out_proj.weight, mha.out_proj.bias, norm.weight if norm is not None else None,
-                             norm.bias if norm is not None else None)
+                             norm.bias if norm is not None else None, drop)
 
 
 class _FFNBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eps, key, x, w1, b1, w2, b2, ln_w, ln_b):
+    def forward(ctx, eps, key, x, w1, b1, w2, b2, ln_w, ln_b, drop=(0.0, 0, 0.0, 0)):
         _require_cuda(x)
         shape = x.shape
         E, Fh = w1.size(1), w1.size(0)
         x2 = x.contiguous().view(-1, E)
         p1 = pack_weight(w1, cache_key=(key, "w1"))
         p2 = pack_weight(w2, cache_key=(key, "w2"))
-        (hdn,) = linear_raw([dict(x=x2, w_packed=p1, bias=b1)], E, Fh, relu=True)
-        (y,) = linear_raw([dict(x=hdn, w_packed=p2, bias=b2, residual=x2)], Fh, E, ln=(ln_w, ln_b, eps))
+        pa, sa, pb, sb = drop
+        (hdn,) = linear_raw([dict(x=x2, w_packed=p1, bias=b1)], E, Fh, relu=True, dropout=(pa, sa) if pa > 0 else None)
+        (y,) = linear_raw([dict(x=hdn, w_packed=p2, bias=b2, residual=x2)], Fh, E, ln=(ln_w, ln_b, eps),
+                          dropout=(pb, sb) if pb > 0 else None)
         ctx.save_for_backward(x, w1, b1, w2, b2, ln_w, ln_b)
         ctx.eps = eps
+        ctx.drop = drop
         return y.view(shape)
 
     @staticmethod
@@ -246,20 +284,28 @@ class _FFNBlockFn(torch.autograd.Function):
         with torch.enable_grad():
             ts = [t.detach().requires_grad_(ctx.needs_input_grad[2 + i]) for i, t in enumerate(ctx.saved_tensors)]
             x, w1, b1, w2, b2, ln_w, ln_b = ts
-            y = F.layer_norm(x + F.linear(F.relu(F.linear(x, w1, b1)), w2, b2), (x.size(-1),), ln_w, ln_b, ctx.eps)
+            pa, sa, pb, sb = ctx.drop
+            hdn = F.relu(F.linear(x, w1, b1))
+            R = hdn.numel() // hdn.size(-1)
+            if pa > 0:
+                hdn = hdn * (dropout_mask(sa, pa, R, hdn.size(-1), 3, 0, x.device).view_as(hdn) * (1.0 / (1.0 - pa)))
+            o = F.linear(hdn, w2, b2)
+            if pb > 0:
+                o = o * (dropout_mask(sb, pb, R, o.size(-1), 3, 0, x.device).view_as(o) * (1.0 / (1.0 - pb)))
+            y = F.layer_norm(x + o, (x.size(-1),), ln_w, ln_b, ctx.eps)
             wanted = [t for t in ts if t.requires_grad]
             grads = torch.autograd.grad(y, wanted, grad, allow_unused=True) if wanted else []
         gmap = {id(t): g for t, g in zip(wanted, grads)}
-        return (None, None, *[gmap.get(id(t)) for t in ts])
+        return (None, None, *[gmap.get(id(t)) for t in ts], None)
 
 
 def ffn_block(ffn, x, norm):
     """norm(x + ffn(x)) for ffn = Sequential(Linear, ReLU, Dropout, Linear, Dropout) (indices 0 and 3)."""
-    for mod in ffn:
-        if isinstance(mod, torch.nn.Dropout) and mod.training and mod.p > 0.0:
-            raise RuntimeError("eda_b200: train-mode FFN dropout > 0 is not fused yet; set dropout=0 or call .eval()")
     l1, l2 = ffn[0], ffn[3]
-    return _FFNBlockFn.apply(norm.eps, ffn, x, l1.weight, l1.bias, l2.weight, l2.bias, norm.weight, norm.bias)
+    pa = float(ffn[2].p) if ffn[2].training else 0.0
+    pb = float(ffn[4].p) if ffn[4].training else 0.0
+    drop = (pa, new_seed() if pa > 0 else 0, pb, new_seed() if pb > 0 else 0)
+    return _FFNBlockFn.apply(norm.eps, ffn, x, l1.weight, l1.bias, l2.weight, l2.bias, norm.weight, norm.bias, drop)
 
 
 class _LinearFn(torch.autograd.Function):

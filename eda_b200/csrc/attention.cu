@@ -44,6 +44,8 @@ struct AttnParams {
   float *ctx;
   int Nq, Nk, H, ldv;
   float scale;
+  uint32_t drop_thresh, drop_seed;  // dropout on the attention probabilities (nn.MultiheadAttention(dropout=p)); 0 = off
+  float drop_scale;
 };
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -255,8 +257,12 @@ attention_kernel(const AttnParams p) {
       if (i * 16 < ncol) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float pe = ex2_approx(fmaf(__uint_as_float(s[i][e]), kLog2e, -moff));
-          sum += pe;
+          float pe = ex2_approx(fmaf(__uint_as_float(s[i][e]), kLog2e, -moff));
+          sum += pe;  // the softmax denominator is taken BEFORE dropout, as in F.multi_head_attention_forward
+          if (p.drop_thresh) {
+            const uint32_t ra = (uint32_t)((b * p.H + h) * p.Nq + qrow);
+            pe = dropout_keep(p.drop_seed, ra, (uint32_t)(k0 + half * 64 + i * 16 + e), p.drop_thresh) ? pe * p.drop_scale : 0.f;
+          }
           s[i][e] = __float_as_uint(to_tf32(pe));
         }
         umma::tmem_st16(tS + (uint32_t)(i * 16), s[i]);
@@ -358,7 +364,8 @@ extern "C" int eda_debug_timestamps_attn(long long *host_out, int n) {
 
 extern "C" int eda_attention_forward(const float *q, const float *k, const float *v, int ldv,
                                      const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                     float scale, float *ctx, void *stream) {
+                                     float scale, float dropout_p, unsigned int dropout_seed, float *ctx,
+                                     void *stream) {
   using namespace eda;
   if (B < 0 || Nq < 0 || Nk < 1 || H < 1 || D < 1) return EDA_ERR_INVALID_ARGUMENT;
   if (H > 65535 || B > 65535) return EDA_ERR_UNSUPPORTED;
@@ -371,6 +378,8 @@ extern "C" int eda_attention_forward(const float *q, const float *k, const float
   AttnParams p = {};
   p.q = q; p.k = k; p.vt = v; p.mask = key_padding_mask; p.ctx = ctx;
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.ldv = ldv; p.scale = scale;
+  if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
+  p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
   cudaStream_t st = as_stream(stream);
   switch (D) {  // head dims the compiled template set covers (EDA: 288 / 8 = 36)
     case 32: return launch_attention<32>(p, B, st);

@@ -120,6 +120,27 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
+// Counter-based dropout decision shared by the linear / attention kernels and eda_dropout_mask (the backward
+// pass regenerates exactly the mask the forward kernel applied): element (a, b) of a call seeded `seed` is KEPT
+// iff the top 24 bits of a 32-bit mix of (seed, a, b) are >= thresh = round(p * 2^24).
+__host__ __device__ __forceinline__ uint32_t dropout_mix(uint32_t seed, uint32_t a, uint32_t b) {
+  uint32_t h = seed ^ (a * 0x9E3779B1u);
+  h ^= h >> 15; h *= 0x85EBCA77u;
+  h ^= b * 0xC2B2AE3Du;
+  h ^= h >> 13; h *= 0x27D4EB2Fu;
+  h ^= h >> 16; h *= 0x165667B1u;
+  h ^= h >> 15;
+  return h;
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t a, uint32_t b, uint32_t thresh) {
+  return (dropout_mix(seed, a, b) >> 8) >= thresh;
+}
+inline uint32_t dropout_thresh(float p) {
+  if (!(p > 0.f)) return 0u;
+  const double t = (double)p * 16777216.0;
+  return t >= 16777216.0 ? 16777216u : (uint32_t)(t + 0.5);
+}
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace eda

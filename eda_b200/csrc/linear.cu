@@ -60,6 +60,8 @@ struct LinParams {
   const float *gamma, *beta;
   float eps;
   uint32_t tmem_cols, stage_bytes;
+  uint32_t drop_thresh, drop_seed;  // output dropout (after bias / ReLU, before residual): thresh 0 = off
+  float drop_scale;                 // 1 / (1 - p)
 };
 
 __device__ __forceinline__ void named_bar_sync_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -314,6 +316,13 @@ linear_kernel(const LinParams p) {
         o.z = __uint_as_float(u[q4 * 4 + 2]) + b4.z;
         o.w = __uint_as_float(u[q4 * 4 + 3]) + b4.w;
         if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (p.drop_thresh) {  // nn.Dropout on this block's output: element (row, column) of problem pi
+          const uint32_t ra = (uint32_t)row * (uint32_t)kMaxProbs + (uint32_t)pi;
+          o.x = dropout_keep(p.drop_seed, ra, (uint32_t)c + 0u, p.drop_thresh) ? o.x * p.drop_scale : 0.f;
+          o.y = dropout_keep(p.drop_seed, ra, (uint32_t)c + 1u, p.drop_thresh) ? o.y * p.drop_scale : 0.f;
+          o.z = dropout_keep(p.drop_seed, ra, (uint32_t)c + 2u, p.drop_thresh) ? o.z * p.drop_scale : 0.f;
+          o.w = dropout_keep(p.drop_seed, ra, (uint32_t)c + 3u, p.drop_thresh) ? o.w * p.drop_scale : 0.f;
+        }
         if (pr.round_out) o = tf32x4(o);
         if (p.ln) {
           if (pr.residual && valid) {
@@ -404,6 +413,17 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, const float *__r
   }
 }
 
+// keep-mask (1.0 / 0.0) of the dropout decisions above, for the backward pass: out[a * cols + b]
+__global__ void dropout_mask_kernel(uint32_t seed, uint32_t thresh, long long rows, int cols, uint32_t a_mul, uint32_t a_add,
+                                    float *__restrict__ out) {
+  const long long total = rows * cols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long a = e / cols;
+    const int b = (int)(e - a * cols);
+    out[e] = dropout_keep(seed, (uint32_t)a * a_mul + a_add, (uint32_t)b, thresh) ? 1.f : 0.f;
+  }
+}
+
 inline int kpad_of(int K) { return (K + 7) & ~7; }
 inline bool lin_supported(int N, int K) { return N >= 16 && N <= kMaxN && (N & 15) == 0 && K >= 1 && K <= 4096; }
 
@@ -416,6 +436,18 @@ int eda_debug_timestamps(long long *host_out, int n) {
   if (!host_out || n < 0 || n > 32) return EDA_ERR_INVALID_ARGUMENT;
   EDA_CUDA_TRY(cudaMemcpyFromSymbol(host_out, eda::g_lin_ts, sizeof(long long) * n), "debug timestamps");
   return EDA_OK;
+}
+
+int eda_dropout_mask(unsigned int seed, float p, long long rows, int cols, unsigned int a_mul, unsigned int a_add,
+                     float *out, void *stream) {
+  using namespace eda;
+  if (rows < 0 || cols < 0 || p < 0.f || p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
+  if (rows == 0 || cols == 0) return EDA_OK;
+  if (!out) return EDA_ERR_INVALID_ARGUMENT;
+  const long long total = rows * cols;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  dropout_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(seed, dropout_thresh(p), rows, cols, a_mul, a_add, out);
+  return check_launch("dropout_mask_kernel");
 }
 
 size_t eda_linear_packed_floats(int N, int K) {
@@ -433,7 +465,8 @@ int eda_linear_pack(const float *W, const float *scale, int N, int K, float *pac
 }
 
 int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu, const float *ln_gamma,
-                       const float *ln_beta, float ln_eps, int layer_norm, void *stream) {
+                       const float *ln_beta, float ln_eps, int layer_norm, float dropout_p, unsigned int dropout_seed,
+                       void *stream) {
   using namespace eda;
   if (!probs || nprobs < 1 || nprobs > kMaxProbs) return EDA_ERR_INVALID_ARGUMENT;
   if (!lin_supported(N, K)) return EDA_ERR_UNSUPPORTED;
@@ -456,6 +489,8 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   if (tiles == 0) return EDA_OK;
   p.nprobs = nprobs; p.K = K; p.Kpad = kpad_of(K); p.N = N; p.relu = relu; p.ln = layer_norm ? 1 : 0;
   p.gamma = ln_gamma; p.beta = ln_beta; p.eps = ln_eps;
+  if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
+  p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
   p.tmem_cols = N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : N <= 256 ? 256u : 512u;
   // stage = A tile + P tile + W block, padded to 1024 bytes (SWIZZLE_128B atoms must stay 1024-aligned)
   p.stage_bytes = (uint32_t)((kABytes + kKBlock * N * 4 + 1023) & ~1023);

@@ -95,27 +95,22 @@ class CrossAttentionLayer(nn.Module):
     def forward(self, vis_feats, vis_key_padding_mask, text_feats, text_key_padding_mask, pos_feats,
                 detected_feats=None, detected_mask=None):
         """Forward pass, vis/pos_feats (B, V, F), lang_feats (B, L, F)."""
-        _no_dropout(self, (self.dropout_lv, self.dropout_vl, getattr(self, "dropout_d", None)))
         # language attends to vision (keys/values without pos), then its FFN
         text_new = ops.mha_block(self.cross_lv, text_feats, vis_feats, vis_feats,
-                                 key_padding_mask=vis_key_padding_mask, residual=text_feats, norm=self.norm_lv)
+                                 key_padding_mask=vis_key_padding_mask, residual=text_feats, norm=self.norm_lv,
+                                 out_dropout=self.dropout_lv)
         text_new = ops.ffn_block(self.ffn_lv, text_new, self.norm_lv2)
         # vision (+pos on the query only) attends to the ORIGINAL language features
         vis_new = ops.mha_block(self.cross_vl, vis_feats, text_feats, text_feats, q_pos=pos_feats,
-                                key_padding_mask=text_key_padding_mask, residual=vis_feats, norm=self.norm_vl)
+                                key_padding_mask=text_key_padding_mask, residual=vis_feats, norm=self.norm_vl,
+                                out_dropout=self.dropout_vl)
         # vision attends to detected boxes
         if detected_feats is not None and self.use_butd_enc_attn:
             vis_new = ops.mha_block(self.cross_d, vis_new, detected_feats, detected_feats,
-                                    key_padding_mask=detected_mask, residual=vis_new, norm=self.norm_d)
+                                    key_padding_mask=detected_mask, residual=vis_new, norm=self.norm_d,
+                                    out_dropout=self.dropout_d)
         vis_new = ops.ffn_block(self.ffn_vl, vis_new, self.norm_vl2)
         return vis_new, text_new
-
-
-def _no_dropout(module, drops):
-    for d in drops:
-        if d is not None and d.training and d.p > 0.0:
-            raise RuntimeError("eda_b200: train-mode residual dropout > 0 is not fused yet; build the layer with "
-                               "dropout=0 (parity configuration, SURVEY.md 8c) or call .eval()")
 
 
 class TransformerEncoderLayerNoFFN(nn.Module):
@@ -129,9 +124,8 @@ class TransformerEncoderLayerNoFFN(nn.Module):
 
     def forward_rows(self, src, src_key_padding_mask=None):
         """src (B, S, F) batch-first."""
-        _no_dropout(self, (self.dropout1,))
         return ops.mha_block(self.self_attn, src, src, src, key_padding_mask=src_key_padding_mask, residual=src,
-                             norm=self.norm1)
+                             norm=self.norm1, out_dropout=self.dropout1)
 
     def forward(self, src, src_mask=None, src_key_padding_mask=None):
         """src (S, B, F) seq-first like the reference; returns (S, B, F)."""
@@ -147,9 +141,9 @@ class PosTransformerEncoderLayerNoFFN(TransformerEncoderLayerNoFFN):
         super().__init__(d_model, nhead, dropout)
 
     def forward_rows(self, src, pos, src_key_padding_mask=None):
-        _no_dropout(self, (self.dropout1,))
         return ops.mha_block(self.self_attn, src, src, src, q_pos=pos, k_pos=pos,
-                             key_padding_mask=src_key_padding_mask, residual=src, norm=self.norm1)
+                             key_padding_mask=src_key_padding_mask, residual=src, norm=self.norm1,
+                             out_dropout=self.dropout1)
 
     def forward(self, src, pos, src_mask=None, src_key_padding_mask=None):
         """src, pos (S, B, F) seq-first; returns (S, B, F)."""
@@ -235,19 +229,20 @@ class BiDecoderLayer(nn.Module):
                 detected_feats=None, detected_mask=None):
         """query (B,N,F), vis_feats (B,V,F), lang_feats (B,L,F), query_pos (B,N,3or6), padding_mask (B,N)
         for the queries, text_key_padding_mask (B,L) -> query (B,N,F)."""
-        _no_dropout(self, (self.dropout1, self.dropout_l, getattr(self, "dropout_d", None), self.dropout_v))
         if self.self_posembed is not None:
             pos = self.self_posembed.forward_rows(query_pos)
         else:
             pos = None  # the reference adds an all-zero tensor
         query = ops.mha_block(self.self_attn, query, query, query, q_pos=pos, k_pos=pos,
-                              key_padding_mask=padding_mask, residual=query, norm=self.norm1)
+                              key_padding_mask=padding_mask, residual=query, norm=self.norm1, out_dropout=self.dropout1)
         query = ops.mha_block(self.cross_l, query, lang_feats, lang_feats, q_pos=pos,
-                              key_padding_mask=text_key_padding_mask, residual=query, norm=self.norm_l)
+                              key_padding_mask=text_key_padding_mask, residual=query, norm=self.norm_l,
+                              out_dropout=self.dropout_l)
         if detected_feats is not None:
             query = ops.mha_block(self.cross_d, query, detected_feats, detected_feats, q_pos=pos,
-                                  key_padding_mask=detected_mask, residual=query, norm=self.norm_d)
+                                  key_padding_mask=detected_mask, residual=query, norm=self.norm_d,
+                                  out_dropout=self.dropout_d)
         query = ops.mha_block(self.cross_v, query, vis_feats, vis_feats, q_pos=pos, key_padding_mask=None,
-                              residual=query, norm=self.norm_v)
+                              residual=query, norm=self.norm_v, out_dropout=self.dropout_v)
         query = ops.ffn_block(self.ffn, query, self.norm2)
         return query.contiguous()

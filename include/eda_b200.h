@@ -203,13 +203,24 @@ EDA_API size_t eda_linear_packed_floats(int N, int K);
 EDA_API int eda_linear_pack(const float *W, const float *scale, int N, int K, float *packed, void *stream);
 EDA_API int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu,
                                const float *ln_gamma, const float *ln_beta, float ln_eps, int layer_norm,
-                               void *stream);
+                               float dropout_p, unsigned int dropout_seed, void *stream);
 /* Development aid: clock64() phase stamps of CTA 0 of the most recent eda_linear_forward launch (synchronises). */
 EDA_API int eda_debug_timestamps(long long *host_out, int n);
 EDA_API int eda_debug_timestamps_attn(long long *host_out, int n); /* same, attention kernel, key block 1 */
 EDA_API int eda_attention_forward(const float *q, const float *k, const float *vt, int ldv,
                                   const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                  float scale, float *ctx, void *stream);
+                                  float scale, float dropout_p, unsigned int dropout_seed, float *ctx, void *stream);
+/* Train-mode dropout (nn.Dropout after attention / FFN blocks, attention-probability dropout of
+ * nn.MultiheadAttention(dropout=p), encoder_decoder_layers.py:47-59,94,106,118 ...): dropout_p > 0 makes
+ * eda_linear_forward zero each output element (after bias / ReLU, before the residual) and eda_attention_forward each
+ * softmax probability (after normalisation) with probability p and scale the rest by 1/(1-p).  The decision is a
+ * counter-based hash of (dropout_seed, element position) — not torch's Philox stream, so masks differ from the
+ * reference's for the same torch seed (train-mode parity is defined at p = 0).  eda_dropout_mask regenerates the
+ * keep-mask (1.0 / 0.0) a forward call applied, out[a * cols + b] for a < rows, b < cols, hashing
+ * (a * a_mul + a_add, b):  linear problem i of a launch: a_mul = 3, a_add = i, rows = R, cols = N;
+ * attention: a_mul = 1, a_add = 0, rows = B*H*Nq (row (b*H + h)*Nq + q), cols = Nk. */
+EDA_API int eda_dropout_mask(unsigned int seed, float p, long long rows, int cols, unsigned int a_mul,
+                             unsigned int a_add, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05/TMEM building blocks the fused kernels rely on (no reference

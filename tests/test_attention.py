@@ -98,13 +98,6 @@ def test_layers_refuse_cpu_tensors():
         module_run("bi_decoder_layer", m, inp)
 
 
-def test_train_mode_dropout_is_loud():
-    m = build("bi_encoder_layer").train()
-    inp = ac.make_inputs("enc_layer")
-    with pytest.raises(RuntimeError):
-        module_run("bi_encoder_layer", m, inp)
-
-
 def test_oracle_masked_keys_have_no_influence():
     m = ac.fill_params(build("bi_encoder_layer"), seed=3).eval()
     sd = m.state_dict()
@@ -317,3 +310,77 @@ def test_backward_matches_torch_autograd():
         assert rel(gval, sd[n].grad) <= 5e-2, n
         checked += 1
     assert checked > 20
+
+
+# ------------------------------------------------------------------------------------------------
+# train-mode dropout (in-kernel counter-based masks; the backward pass regenerates them)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_linear_dropout_matches_regenerated_mask():
+    from eda_b200 import attn_ops as ops
+
+    g = torch.Generator().manual_seed(3)
+    R, K, N, p, seed = 700, 288, 288, 0.1, 12345
+    x = torch.randn(R, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    res = torch.randn(R, N, generator=g).cuda()
+    gam, bet = (1 + 0.1 * torch.randn(N, generator=g)).cuda(), (0.1 * torch.randn(N, generator=g)).cuda()
+    (y,) = ops.linear_raw([dict(x=x, w_packed=ops.pack_weight(W), bias=b, residual=res)], K, N, relu=True,
+                          ln=(gam, bet, 1e-5), dropout=(p, seed))
+    keep = ops.dropout_mask(seed, p, R, N, 3, 0, x.device)
+    assert abs(keep.mean().item() - (1 - p)) < 5e-3  # 200k Bernoulli(0.9) draws
+    assert not torch.equal(keep, ops.dropout_mask(seed + 1, p, R, N, 3, 0, x.device))
+    ref = (x.double() @ W.double().t() + b.double()).clamp_min(0) * keep.double() / (1 - p)
+    ref = torch.nn.functional.layer_norm(ref + res.double(), (N,), gam.double(), bet.double(), 1e-5)
+    torch.testing.assert_close(y.double(), ref, **TOL)
+
+
+@pytest.mark.gpu
+def test_attention_dropout_matches_regenerated_mask():
+    from eda_b200 import attn_ops as ops
+
+    H, D, B, Nq, Nk, p, seed = 8, 36, 2, 200, 300, 0.1, 777
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(B, Nq, H * D, generator=g).cuda()
+    k, v = (_round_tf32(torch.randn(B, Nk, H * D, generator=g)).cuda() for _ in range(2))
+    mask = ac.ragged_mask(B, Nk, 100, g).cuda()
+    ctx = ops.attention_raw(q.view(-1, H * D), k.view(-1, H * D), _channel_major(v), mask, B, Nq, Nk, H,
+                            dropout=(p, seed)).view(B, Nq, H * D)
+    keep = ops.dropout_mask(seed, p, B * H * Nq, Nk, 1, 0, q.device).view(B, H, Nq, Nk)
+    assert abs(keep.mean().item() - (1 - p)) < 5e-3
+    qd = q.double().view(B, Nq, H, D).transpose(1, 2) / 6.0
+    kd = k.double().view(B, Nk, H, D).transpose(1, 2)
+    vd = v.double().view(B, Nk, H, D).transpose(1, 2)
+    s_ = (qd @ kd.transpose(-1, -2)).masked_fill(mask.view(B, 1, 1, Nk), float("-inf"))
+    pr = torch.softmax(s_, -1) * keep.double() / (1 - p)
+    ref = (pr @ vd).transpose(1, 2).reshape(B, Nq, H * D)
+    torch.testing.assert_close(ctx.double(), ref, **TOL)
+
+
+@pytest.mark.gpu
+def test_train_mode_dropout_layer_forward_backward():
+    """The reference's default configuration (dropout 0.1, train mode) runs on the CUDA path: repeatable under
+    torch.manual_seed, different from eval mode, and its backward uses exactly the masks the forward applied
+    (a second backward with the same seeds gives identical gradients; with p -> eval the eval output returns)."""
+    m = ac.fill_params(build("bi_encoder_layer"), seed=8).cuda().train()
+    inp = _cuda(ac.make_inputs("enc_layer"))
+
+    def run():
+        torch.manual_seed(1234)
+        vis = inp["vis"].clone().requires_grad_(True)
+        v, t = m(vis, inp["pos"], None, inp["text"], inp["text_mask"], {}, detected_feats=inp["det"],
+                 detected_mask=inp["det_mask"])
+        (v.pow(2).mean() + t.pow(2).mean()).backward()
+        return v.detach(), t.detach(), vis.grad.clone()
+
+    v1, t1, g1 = run()
+    for prm in m.parameters():
+        prm.grad = None
+    v2, t2, g2 = run()
+    assert torch.equal(v1, v2) and torch.equal(t1, t2) and torch.allclose(g1, g2, rtol=1e-4, atol=1e-6)
+    assert torch.isfinite(g1).all() and g1.abs().sum() > 0
+    with torch.no_grad():
+        ve, te = m.eval()(inp["vis"], inp["pos"], None, inp["text"], inp["text_mask"], {}, detected_feats=inp["det"],
+                          detected_mask=inp["det_mask"])
+    assert (v1 - ve).abs().max() > 1e-2  # dropout really happened
