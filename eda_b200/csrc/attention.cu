@@ -79,7 +79,7 @@ struct Dims {
 __device__ long long g_attn_ts[32];
 #define ATT_TS(i) do { if (blk == 1 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_attn_ts[i] = clock64(); } while (0)
 
-template <int D>
+template <int D, bool kDrop>
 __global__ void __launch_bounds__(kThreads, 2)
 attention_kernel(const AttnParams p) {
   using DM = Dims<D>;
@@ -259,7 +259,7 @@ attention_kernel(const AttnParams p) {
         for (int e = 0; e < 16; ++e) {
           float pe = ex2_approx(fmaf(__uint_as_float(s[i][e]), kLog2e, -moff));
           sum += pe;  // the softmax denominator is taken BEFORE dropout, as in F.multi_head_attention_forward
-          if (p.drop_thresh) {
+          if (kDrop) {
             const uint32_t ra = (uint32_t)((b * p.H + h) * p.Nq + qrow);
             pe = dropout_keep(p.drop_seed, ra, (uint32_t)(k0 + half * 64 + i * 16 + e), p.drop_thresh) ? pe * p.drop_scale : 0.f;
           }
@@ -344,12 +344,17 @@ int launch_attention(const AttnParams &p, int B, cudaStream_t st) {
   if (smem < 80 * 1024) smem = 80 * 1024;  // at most two CTAs per SM: their 2 x 256 TMEM columns always fit
   static bool attr_set = false;
   if (!attr_set) {
-    EDA_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    EDA_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                 "attention smem attr");
+    EDA_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                  "attention smem attr");
     attr_set = true;
   }
   dim3 grid((unsigned)((p.Nq + kRows - 1) / kRows), (unsigned)p.H, (unsigned)B);
-  attention_kernel<D><<<grid, kThreads, smem, st>>>(p);
+  if (p.drop_thresh)
+    attention_kernel<D, true><<<grid, kThreads, smem, st>>>(p);
+  else
+    attention_kernel<D, false><<<grid, kThreads, smem, st>>>(p);
   return check_launch("attention_kernel");
 }
 

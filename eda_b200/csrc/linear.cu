@@ -14,30 +14,31 @@
 // Up to three independent problems (same K, N, epilogue) share one launch: the q / k / v
 // in-projections of one attention block are one grid.
 //
-// CTA = one 128-row tile, 10 warps with fixed roles, K streamed in 32-wide blocks through a 3-stage ring:
-//   warps 0-7  A staging: coalesced 16-byte cp.async copies (8 lanes = one 128-byte row segment) into the
+// CTA = one 128-row tile, 18 warps with fixed roles, K streamed in 32-wide blocks through a 3-stage ring:
+//   warps 0-15 A staging: coalesced 16-byte cp.async copies (8 lanes = one 128-byte row segment) into the
 //              K-major SWIZZLE_128B tile the tensor core reads, one block ahead of the maths; then every
 //              thread adds "+ pos" to and rounds (cvt.rna.tf32) the chunks it copied, in place, and
 //              arrives on the stage's `a_ready` mbarrier.  Later: the epilogue.
-//   warp 8     one thread issues tcgen05.mma kind::tf32 (M = 128, N <= 256 per instruction, N = 288 ->
+//   warp 16    one thread issues tcgen05.mma kind::tf32 (M = 128, N <= 256 per instruction, N = 288 ->
 //              2 x 144; fp32 accumulator 128 x N in tensor memory) and commits each stage back to `empty`
-//   warp 9     one thread streams the pre-packed weight blocks (eda_linear_pack) with 1-D TMA bulk copies
+//   warp 17    one thread streams the pre-packed weight blocks (eda_linear_pack) with 1-D TMA bulk copies
 // Measured on B200 (scripts/lin_ts.py): a tf32 MMA of this shape occupies the tensor pipe ~100 cycles, so
 // the 72 MMAs of a 128x288x288 tile are the floor (~7.5k cycles); staging runs in their shadow.
-// Epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (its hardware quadrant) and the column half w / 4, so
-// two warps per scheduler hide each other's latency.  Results go through a padded shared-memory tile (the
-// ring is free by then) and leave with coalesced 16-byte stores; the residual tile arrives by coalesced
-// cp.async.  LayerNorm: per-row (sum, sum of squares) of the two column halves meet in shared memory and the
-// normalisation is applied on the way out.
+// Epilogue, two phases over a padded shared-memory tile (the ring is free by then).  Phase 1, thread = (row,
+// column quarter): warp w reads TMEM lanes 32 (w % 4).. (its hardware quadrant), four warps per scheduler hide
+// each other's TMEM latency: bias, ReLU, dropout, rounding.  Phase 2, warp = row: residual read with coalesced
+// 16-byte loads, LayerNorm statistics by warp shuffle, coalesced 16-byte stores.
+#include <stdlib.h>
 #include "umma.cuh"
 
 namespace eda {
 namespace {
 
 constexpr int kRows = 128;
-constexpr int kWorkers = 256;   // warps 0-7: staging + epilogue
-constexpr int kThreads = 320;   // + warp 8 MMA issue, warp 9 weight producer
-constexpr int kStages = 3;
+constexpr int kWorkers = 512;   // warps 0-15: staging + epilogue
+constexpr int kWorkerWarps = kWorkers / 32;
+constexpr int kThreads = 576;   // + warp 16 MMA issue, warp 17 weight producer
+constexpr int kStages = 4;  // ring slots allocated at most; p.nstages (3 or 4) are used
 constexpr int kKBlock = 32;                      // 32 fp32 = one 128-byte swizzle row
 constexpr int kTileBytes = kRows * kKBlock * 4;  // 16 KB
 constexpr int kABytes = 2 * kTileBytes;          // A tile + P ("+ pos") tile
@@ -57,14 +58,16 @@ struct LinProblem {
 struct LinParams {
   LinProblem pr[kMaxProbs];
   int nprobs, K, Kpad, N, relu, ln;
+  int S, NS;  // the N columns are split over S CTAs of NS columns each (a cluster when LayerNorm needs whole rows)
   const float *gamma, *beta;
   float eps;
   uint32_t tmem_cols, stage_bytes;
+  int nstages, prefetch;  // ring depth in use and how many blocks the staging warps run ahead (nstages - 2)
   uint32_t drop_thresh, drop_seed;  // output dropout (after bias / ReLU, before residual): thresh 0 = off
   float drop_scale;                 // 1 / (1 - p)
 };
 
-__device__ __forceinline__ void named_bar_sync_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync_workers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -73,6 +76,11 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 __device__ __forceinline__ float4 tf32x4(float4 a) {
   return make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
+}
+__device__ __forceinline__ float2 ld_shared_cluster_f32x2(uint32_t cluster_addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -112,21 +120,23 @@ linear_kernel(const LinParams p) {
   __shared__ __align__(8) uint64_t full_w[kStages], a_ready[kStages], empty[kStages], mma_done, res_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[kMaxN], s_gamma[kMaxN], s_beta[kMaxN];
-  __shared__ float s_part[2][kRows], s_part2[2][kRows];
+  __shared__ __align__(8) float2 s_stat[kRows];  // per-row (sum, sum of squares) of this CTA's column slice
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   LIN_TS(0);
+  const int gtile = (int)blockIdx.x / p.S, split = (int)blockIdx.x - gtile * p.S;
   int pi = 0;
-  while (pi + 1 < p.nprobs && (int)blockIdx.x >= p.pr[pi + 1].tile0) ++pi;
+  while (pi + 1 < p.nprobs && gtile >= p.pr[pi + 1].tile0) ++pi;
   const LinProblem &pr = p.pr[pi];
-  const int tile = (int)blockIdx.x - pr.tile0;
-  const int N = p.N, K = p.K;
+  const int tile = gtile - pr.tile0;
+  const int Nf = p.N, N = p.NS, n0 = split * p.NS, K = p.K;  // N: this CTA's slice [n0, n0 + N) of the Nf columns
+  const bool clustered = p.ln && p.S > 1;
 
   if (warp == 0) umma::tmem_alloc(&tmem_slot, p.tmem_cols);
   if (tid == 32) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_w[s], 1);
-      mbar_init(&a_ready[s], kWorkers);
+      mbar_init(&a_ready[s], kWorkerWarps);  // one arrival per staging warp
       mbar_init(&empty[s], 1);
     }
     mbar_init(&mma_done, 1);
@@ -134,9 +144,9 @@ linear_kernel(const LinParams p) {
     mbar_fence_init_cluster();
   }
   for (int i = tid; i < N; i += kThreads) {
-    s_bias[i] = pr.bias ? __ldg(pr.bias + i) : 0.f;
-    s_gamma[i] = (p.ln && p.gamma) ? __ldg(p.gamma + i) : 1.f;
-    s_beta[i] = (p.ln && p.beta) ? __ldg(p.beta + i) : 0.f;
+    s_bias[i] = pr.bias ? __ldg(pr.bias + n0 + i) : 0.f;
+    s_gamma[i] = (p.ln && p.gamma) ? __ldg(p.gamma + n0 + i) : 1.f;
+    s_beta[i] = (p.ln && p.beta) ? __ldg(p.beta + n0 + i) : 0.f;
   }
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -145,20 +155,21 @@ linear_kernel(const LinParams p) {
   const int nkb = (p.Kpad + kKBlock - 1) / kKBlock;
   LIN_TS(1);
 
-  if (warp == 9) {
+  if (warp == kWorkerWarps + 1) {
     // ---------------- weight producer ----------------------------------------------------------
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % kStages;
+        const int slot = kb % p.nstages;
         const int kcnt = min(kKBlock, p.Kpad - kb * kKBlock);
         const uint32_t bytes = (uint32_t)kcnt * (uint32_t)N * 4u;
-        mbar_wait(&empty[slot], ((kb / kStages) & 1) ^ 1);
+        mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full_w[slot], bytes);
-        bulk_g2s(smem_raw + (size_t)slot * p.stage_bytes + kABytes, pr.w + (size_t)kb * kKBlock * N, bytes,
-                 &full_w[slot]);
+        bulk_g2s(smem_raw + (size_t)slot * p.stage_bytes + kABytes,
+                 pr.w + (size_t)split * p.Kpad * N + (size_t)kb * kKBlock * N, bytes, &full_w[slot]);
       }
     }
-  } else if (warp == 8) {
+    if (clustered) cluster_sync_all();  // matches the workers' statistics exchange
+  } else if (warp == kWorkerWarps) {
     // ---------------- MMA issuer -----------------------------------------------------------------
     if (lane == 0) {
       // N split into MMA-sized pieces (multiples of 16, <= 256)
@@ -168,9 +179,9 @@ linear_kernel(const LinParams p) {
       const uint32_t idesc_b = umma::idesc_tf32(kRows, n_b > 0 ? n_b : 16);
       const uint32_t lbo_w = (uint32_t)N * 16u;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % kStages;
+        const int slot = kb % p.nstages;
         const int kcnt = min(kKBlock, p.Kpad - kb * kKBlock);
-        const uint32_t par = (kb / kStages) & 1;
+        const uint32_t par = (kb / p.nstages) & 1;
         mbar_wait(&a_ready[slot], par);
         mbar_wait(&full_w[slot], par);
         umma::fence_after_thread_sync();
@@ -192,6 +203,7 @@ linear_kernel(const LinParams p) {
         if (kb == nkb - 1) umma::mma_commit(&mma_done);
       }
     }
+    if (clustered) cluster_sync_all();  // matches the workers' statistics exchange
   } else {
     // ---------------- staging warps ---------------------------------------------------------------
     const long long row0 = (long long)tile * kRows;
@@ -204,8 +216,9 @@ linear_kernel(const LinParams p) {
 
     auto issue_block = [&](int kb) {
       if (vec && kb < nkb) {
-        const int slot = kb % kStages;
-        mbar_wait(&empty[slot], ((kb / kStages) & 1) ^ 1);  // the MMAs that read this slot have finished
+        const int slot = kb % p.nstages;
+        if (lane == 0) mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);  // the MMAs that read this slot are done
+        __syncwarp();
         unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
         unsigned char *sP = sA + kTileBytes;
         const int k = kb * kKBlock + cj * 4;
@@ -221,12 +234,12 @@ linear_kernel(const LinParams p) {
       }
       umma::cp_async_commit();
     };
-    for (int i = 0; i < kPrefetch; ++i) issue_block(i);
+    for (int i = 0; i < p.prefetch; ++i) issue_block(i);
 
     for (int kb = 0; kb < nkb; ++kb) {
-      const int slot = kb % kStages;
-      issue_block(kb + kPrefetch);
-      umma::cp_async_wait<kPrefetch>();  // block kb has landed (this thread's copies)
+      const int slot = kb % p.nstages;
+      issue_block(kb + p.prefetch);
+      if (p.prefetch == 2) umma::cp_async_wait<2>(); else umma::cp_async_wait<1>();  // block kb has landed (own copies)
       unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
       if (vec) {
         // the chunks this thread copied: "+ pos", round to tf32 (round-to-nearest), in place
@@ -250,7 +263,7 @@ linear_kernel(const LinParams p) {
         }
       } else {
         // rows that are not 16-byte aligned (K = 3 or 6: xyz / box inputs of the position embedding): thread = row
-        mbar_wait(&empty[slot], ((kb / kStages) & 1) ^ 1);
+        mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);
         const long long row = row0 + tid;
         const bool valid = row < pr.rows;
         const float *xrow = pr.x + row * K;
@@ -269,7 +282,8 @@ linear_kernel(const LinParams p) {
         }
       }
       umma::fence_proxy_async_smem();
-      mbar_arrive(&a_ready[slot]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[slot]);
     }
     LIN_TS(2);
     mbar_wait(&mma_done, 0);
@@ -277,35 +291,32 @@ linear_kernel(const LinParams p) {
     __syncwarp();
     LIN_TS(3);
 
-    // ---------------- epilogue: thread = (row, column half) ------------------------------------------------
+    // ---------------- epilogue ---------------------------------------------------------------------------
     // All MMAs and weight copies are complete: the ring is reused as the output tile [128][N + 4].
-    const int q = warp & 3, half = warp >> 2;
+    // Phase 1, thread = (row, column quarter): warp w reads TMEM lanes 32 (w % 4).. (its hardware quadrant) and
+    // the 16-column chunks of quarter w / 4: bias, ReLU, dropout, rounding -> tile (or straight to the
+    // channel-major output).  Phase 2, warp = row: residual (coalesced global reads) + LayerNorm with warp-shuffle
+    // row statistics + coalesced 16-byte stores.
+    const int q = warp & 3, part = warp >> 2;
     const int r = q * 32 + lane;  // row of the tile = TMEM lane
     const long long row = row0 + r;
     const bool valid = row < pr.rows;
-    const int NH = ((N / 2 + 15) / 16) * 16;  // columns per half (multiple of 16)
-    const int cbeg = min(N, half * NH), cend = min(N, cbeg + NH);
+    const int nchunks = N >> 4;
+    const int cbeg = ((part * nchunks) / 4) << 4, cend = (((part + 1) * nchunks) / 4) << 4;
     const uint32_t trow = umma::tmem_addr(tbase, (uint32_t)(q * 32), 0);
     const int pitch = N + 4;
     float *tile_s = reinterpret_cast<float *>(smem_raw);
     float *srow = tile_s + (size_t)r * pitch;
     const int nvalid = (int)min((long long)kRows, (long long)pr.rows - row0);
     const int n4 = N >> 2;
-    if (p.ln && pr.residual) {
-      // residual tile -> shared memory, coalesced 16-byte cp.async (a warp moves one row segment at a time)
-      for (int rr = warp; rr < nvalid; rr += kWorkers / 32)
-        for (int c4 = lane; c4 < n4; c4 += 32)
-          umma::cp_async16(tile_s + (size_t)rr * pitch + c4 * 4, pr.residual + (row0 + rr) * N + c4 * 4, 16u);
-      umma::cp_async_commit();
-      umma::cp_async_wait<0>();
-      named_bar_sync_workers();
-    }
     LIN_TS(8);
-    float sum = 0.f, sumsq = 0.f;
     const bool direct_t = pr.tb > 0;  // channel-major output goes straight to global (already coalesced)
     long long bb = 0, rr0 = 0;
     if (direct_t) { bb = row / pr.tb; rr0 = row - bb * pr.tb; }
-    auto process = [&](const uint32_t (&u)[16], int c0) {
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+      uint32_t u[16];
+      umma::tmem_ld16(trow + (uint32_t)c0, u);
+      umma::tmem_ld_wait();
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int c = c0 + q4 * 4;
@@ -318,71 +329,118 @@ linear_kernel(const LinParams p) {
         if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         if (p.drop_thresh) {  // nn.Dropout on this block's output: element (row, column) of problem pi
           const uint32_t ra = (uint32_t)row * (uint32_t)kMaxProbs + (uint32_t)pi;
-          o.x = dropout_keep(p.drop_seed, ra, (uint32_t)c + 0u, p.drop_thresh) ? o.x * p.drop_scale : 0.f;
-          o.y = dropout_keep(p.drop_seed, ra, (uint32_t)c + 1u, p.drop_thresh) ? o.y * p.drop_scale : 0.f;
-          o.z = dropout_keep(p.drop_seed, ra, (uint32_t)c + 2u, p.drop_thresh) ? o.z * p.drop_scale : 0.f;
-          o.w = dropout_keep(p.drop_seed, ra, (uint32_t)c + 3u, p.drop_thresh) ? o.w * p.drop_scale : 0.f;
+          const uint32_t gc = (uint32_t)(n0 + c);
+          o.x = dropout_keep(p.drop_seed, ra, gc + 0u, p.drop_thresh) ? o.x * p.drop_scale : 0.f;
+          o.y = dropout_keep(p.drop_seed, ra, gc + 1u, p.drop_thresh) ? o.y * p.drop_scale : 0.f;
+          o.z = dropout_keep(p.drop_seed, ra, gc + 2u, p.drop_thresh) ? o.z * p.drop_scale : 0.f;
+          o.w = dropout_keep(p.drop_seed, ra, gc + 3u, p.drop_thresh) ? o.w * p.drop_scale : 0.f;
         }
         if (pr.round_out) o = tf32x4(o);
-        if (p.ln) {
-          if (pr.residual && valid) {
-            const float4 r4 = *reinterpret_cast<const float4 *>(srow + c);
-            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-          }
-          sum += (o.x + o.y) + (o.z + o.w);
-          sumsq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, sumsq))));
-        }
         if (direct_t) {
           if (valid) {
-            float *yt = pr.y + (bb * N + c) * (long long)pr.ldt + rr0;
+            float *yt = pr.y + (bb * Nf + n0 + c) * (long long)pr.ldt + rr0;
             yt[0] = o.x; yt[pr.ldt] = o.y; yt[2 * (long long)pr.ldt] = o.z; yt[3 * (long long)pr.ldt] = o.w;
           }
         } else {
           *reinterpret_cast<float4 *>(srow + c) = o;
         }
       }
-    };
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
-      uint32_t u[16];
-      umma::tmem_ld16(trow + (uint32_t)c0, u);
-      umma::tmem_ld_wait();
-      process(u, c0);
     }
     LIN_TS(9);
-    if (p.ln) {
-      // per-row (sum, sum of squares) of the two column halves; combined by the copy-out below.
-      // var = E[x^2] - mean^2 in fp32: relative error ~1e-7 (1 + mean^2/var), harmless for these activations.
-      s_part[half][r] = sum;
-      s_part2[half][r] = sumsq;
-    }
-    LIN_TS(10);
     if (!direct_t) {
-      named_bar_sync_workers();  // the tile (and the row statistics) are complete
-      // coalesced copy-out (a warp moves one row at a time), LayerNorm applied on the way
-      const float invN = 1.0f / (float)N;
-      for (int rr = warp; rr < nvalid; rr += kWorkers / 32) {
+      named_bar_sync_workers();  // the tile is complete
+      LIN_TS(10);
+      const float invN = 1.0f / (float)Nf;
+      constexpr int kMaxJ = (kMaxN / 4 + 31) / 32;  // float4 columns per lane
+      if (p.ln) {
+        // pass A (warp = 8 rows, 4 at a time so 12 residual loads are in flight): residual added in place, per-row
+        // (sum, sum of squares) of this CTA's columns -> s_stat
+        constexpr int kRB = 4;
+        for (int rb = warp * (kRows / kWorkerWarps); rb < (warp + 1) * (kRows / kWorkerWarps); rb += kRB) {
+          float4 r4[kRB][kMaxJ];
+#pragma unroll
+          for (int i = 0; i < kRB; ++i)
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j) {
+              const int c4 = lane + j * 32;
+              r4[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (pr.residual && rb + i < nvalid && c4 < n4)
+                r4[i][j] = __ldg(reinterpret_cast<const float4 *>(pr.residual + (row0 + rb + i) * Nf + n0) + c4);
+            }
+          if (rb == warp * (kRows / kWorkerWarps)) LIN_TS(13);
+#pragma unroll
+          for (int i = 0; i < kRB; ++i) {
+            float sum = 0.f, sumsq = 0.f;
+            float4 *src = reinterpret_cast<float4 *>(tile_s + (size_t)(rb + i) * pitch);
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j) {
+              const int c4 = lane + j * 32;
+              if (rb + i < nvalid && c4 < n4) {
+                float4 o = src[c4];
+                o.x += r4[i][j].x; o.y += r4[i][j].y; o.z += r4[i][j].z; o.w += r4[i][j].w;
+                if (pr.residual) src[c4] = o;
+                sum += (o.x + o.y) + (o.z + o.w);
+                sumsq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, sumsq))));
+              }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+              sum += __shfl_xor_sync(0xffffffffu, sum, d);
+              sumsq += __shfl_xor_sync(0xffffffffu, sumsq, d);
+            }
+            if (lane == 0) s_stat[rb + i] = make_float2(sum, sumsq);
+          }
+        }
+        LIN_TS(11);
+        if (clustered) cluster_sync_all(); else __syncwarp();
+        LIN_TS(12);
+      }
+      // pass B: normalise with the row statistics (own, or all S column slices' through DSMEM) and store
+      for (int rr = warp * (kRows / kWorkerWarps); rr < (warp + 1) * (kRows / kWorkerWarps) && rr < nvalid; ++rr) {
+        const float4 *src = reinterpret_cast<const float4 *>(tile_s + (size_t)rr * pitch);
+        float4 *dst = reinterpret_cast<float4 *>(pr.y + (row0 + rr) * Nf + n0);
         float mean = 0.f, rstd = 1.f;
         if (p.ln) {
-          const float m1 = (s_part[0][rr] + s_part[1][rr]) * invN;
-          const float m2 = (s_part2[0][rr] + s_part2[1][rr]) * invN;
-          mean = m1;
-          rstd = 1.0f / sqrtf(fmaxf(m2 - m1 * m1, 0.f) + p.eps);
-        }
-        const float4 *src = reinterpret_cast<const float4 *>(tile_s + (size_t)rr * pitch);
-        float4 *dst = reinterpret_cast<float4 *>(pr.y + (row0 + rr) * N);
-        for (int c4 = lane; c4 < n4; c4 += 32) {
-          float4 o = src[c4];
-          if (p.ln) {
-            const float4 g4 = *reinterpret_cast<const float4 *>(s_gamma + c4 * 4);
-            const float4 e4 = *reinterpret_cast<const float4 *>(s_beta + c4 * 4);
-            o.x = (o.x - mean) * rstd * g4.x + e4.x;
-            o.y = (o.y - mean) * rstd * g4.y + e4.y;
-            o.z = (o.z - mean) * rstd * g4.z + e4.z;
-            o.w = (o.w - mean) * rstd * g4.w + e4.w;
+          // var = E[x^2] - mean^2 in fp32: relative error ~1e-7 (1 + mean^2/var), harmless for these activations
+          float sum = 0.f, sumsq = 0.f;
+          if (clustered) {
+            if (lane < p.S) {
+              const float2 st = ld_shared_cluster_f32x2(mapa_u32(smem_u32(&s_stat[rr]), (uint32_t)lane));
+              sum = st.x; sumsq = st.y;
+            }
+#pragma unroll
+            for (int d = 2; d > 0; d >>= 1) {  // S <= 4
+              sum += __shfl_xor_sync(0xffffffffu, sum, d);
+              sumsq += __shfl_xor_sync(0xffffffffu, sumsq, d);
+            }
+            sum = __shfl_sync(0xffffffffu, sum, 0);
+            sumsq = __shfl_sync(0xffffffffu, sumsq, 0);
+          } else {
+            const float2 st = s_stat[rr];
+            sum = st.x; sumsq = st.y;
           }
-          dst[c4] = o;
+          mean = sum * invN;
+          rstd = 1.0f / sqrtf(fmaxf(sumsq * invN - mean * mean, 0.f) + p.eps);
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j) {
+          const int c4 = lane + j * 32;
+          if (c4 < n4) {
+            float4 o = src[c4];
+            if (p.ln) {
+              const float4 g4 = *reinterpret_cast<const float4 *>(s_gamma + c4 * 4);
+              const float4 e4 = *reinterpret_cast<const float4 *>(s_beta + c4 * 4);
+              o.x = (o.x - mean) * rstd * g4.x + e4.x;
+              o.y = (o.y - mean) * rstd * g4.y + e4.y;
+              o.z = (o.z - mean) * rstd * g4.z + e4.z;
+              o.w = (o.w - mean) * rstd * g4.w + e4.w;
+            }
+            dst[c4] = o;
+          }
         }
       }
+    } else if (clustered) {
+      cluster_sync_all();  // unreachable (LayerNorm never combines with channel-major output); keeps arrival counts equal
     }
     LIN_TS(16);
   }
@@ -390,19 +448,24 @@ linear_kernel(const LinParams p) {
   umma::fence_before_thread_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tbase, p.tmem_cols);
+  if (clustered) cluster_sync_all();  // nobody leaves while a peer may still read its row statistics
   LIN_TS(17);
 }
 
 // W (N, K) row-major [* scale[n]] -> blocks [kb] of float4 [kcnt/4][N] (K-major core-matrix layout,
 // chunk-major), rounded to tf32 once.  K is zero-padded to a multiple of 8.
 __global__ void pack_linear_kernel(const float *__restrict__ W, const float *__restrict__ scale, int N, int K, int Kpad,
-                                   float *__restrict__ dst) {
+                                   int NS, float *__restrict__ dst) {
+  // destination order: [column split s][k block][16-byte chunk][NS columns] float4
   const int total = N * Kpad;
+  const int per_split = Kpad * NS;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int kb = e / (kKBlock * N);
-    const int rem = e - kb * kKBlock * N;
-    const int c = rem / (4 * N);
-    const int n = (rem >> 2) % N;
+    const int sidx = e / per_split;
+    const int e1 = e - sidx * per_split;
+    const int kb = e1 / (kKBlock * NS);
+    const int rem = e1 - kb * kKBlock * NS;
+    const int c = rem / (4 * NS);
+    const int n = sidx * NS + ((rem >> 2) % NS);
     const int k = kb * kKBlock + c * 4 + (rem & 3);
     float w = 0.f;
     if (k < K) {
@@ -411,6 +474,19 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, const float *__r
     }
     dst[e] = to_tf32(w);
   }
+}
+
+// How many CTAs share the N columns of a row tile.  One SM moves ~64 B/clk to and from L2, so a 128 x 288 tile
+// (A 147 KB [+ pos], W 332 KB, out 147 KB) is bandwidth-bound on its SM; splitting N spreads the weight and
+// output traffic (and fills more of the 148 SMs: most launches of the attention stack have <= 16 row tiles).
+inline int lin_splits(int N) {
+  // Measured (scripts/lin_ts.py, benchmarks/micro_attn.py): with the staging loop as the per-tile bottleneck the
+  // split does not pay yet (3 enc + 6 dec layers: 3.78 ms split vs 3.13 ms unsplit), so it is opt-in.
+  static const int enabled = [] { const char *e = getenv("EDA_LINEAR_SPLIT"); return e ? atoi(e) : 0; }();
+  if (!enabled) return 1;
+  if (N % 48 == 0 && N / 3 >= 64) return 3;   // 288 -> 3 x 96
+  if (N % 64 == 0 && N >= 256) return N / 64 <= 4 ? N / 64 : 4;  // 256 -> 4 x 64
+  return 1;
 }
 
 // keep-mask (1.0 / 0.0) of the dropout decisions above, for the backward pass: out[a * cols + b]
@@ -460,7 +536,8 @@ int eda_linear_pack(const float *W, const float *scale, int N, int K, float *pac
   if (!lin_supported(N, K)) return EDA_ERR_UNSUPPORTED;
   if (!W || !packed) return EDA_ERR_INVALID_ARGUMENT;
   const int total = N * kpad_of(K);
-  pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, scale, N, K, kpad_of(K), packed);
+  pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, scale, N, K, kpad_of(K), N / lin_splits(N),
+                                                                         packed);
   return check_launch("pack_linear_kernel");
 }
 
@@ -491,11 +568,16 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   p.gamma = ln_gamma; p.beta = ln_beta; p.eps = ln_eps;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
-  p.tmem_cols = N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : N <= 256 ? 256u : 512u;
+  p.S = lin_splits(N);
+  p.NS = N / p.S;
+  const int NS = p.NS;
+  p.tmem_cols = NS <= 32 ? 32u : NS <= 64 ? 64u : NS <= 128 ? 128u : NS <= 256 ? 256u : 512u;
   // stage = A tile + P tile + W block, padded to 1024 bytes (SWIZZLE_128B atoms must stay 1024-aligned)
-  p.stage_bytes = (uint32_t)((kABytes + kKBlock * N * 4 + 1023) & ~1023);
-  size_t smem = (size_t)kStages * p.stage_bytes;
-  const size_t out_tile = (size_t)kRows * (N + 4) * sizeof(float);
+  p.stage_bytes = (uint32_t)((kABytes + kKBlock * NS * 4 + 1023) & ~1023);
+  p.nstages = (size_t)4 * p.stage_bytes <= 200 * 1024 ? 4 : 3;
+  p.prefetch = p.nstages - 2;
+  size_t smem = (size_t)p.nstages * p.stage_bytes;
+  const size_t out_tile = (size_t)kRows * (NS + 4) * sizeof(float);
   if (smem < out_tile) smem = out_tile;
   smem += 1024;  // alignment slack
   static size_t smem_set = 0;  // one process per GPU: the attribute is raised once per size increase
@@ -504,7 +586,25 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
                  "linear smem attr");
     smem_set = smem;
   }
-  linear_kernel<<<tiles, kThreads, smem, as_stream(stream)>>>(p);
+  if (p.ln && p.S > 1) {
+    // LayerNorm needs whole rows: the S column slices of a row tile form a thread-block cluster and exchange
+    // their per-row statistics through distributed shared memory
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * p.S));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, linear_kernel, p), "linear_kernel cluster launch");
+  } else {
+    linear_kernel<<<tiles * p.S, kThreads, smem, as_stream(stream)>>>(p);
+  }
   return check_launch("linear_kernel");
 }
 

@@ -12,4 +12,4 @@ for R in (640, 8192):
         ts = (ctypes.c_longlong * 32)()
         lib.eda_debug_timestamps(ts, 32)
         t = list(ts)
-        print(f"R={R} ln={ln}: setup {t[1]-t[0]} staging_done {t[2]-t[1]} mma_done {t[3]-t[1]} epilogue: residual {t[8]-t[3]} tmem_pass {t[9]-t[8]} ln {t[10]-t[9]} copy_out {t[16]-t[10]} | epilogue_end {t[16]-t[1]} total {t[17]-t[0]} cycles")
+        print(f"R={R} ln={ln}: setup {t[1]-t[0]} staging_done {t[2]-t[1]} mma_done {t[3]-t[1]} epilogue: tmem_pass {t[9]-t[8]} barrier {t[10]-t[9]} copy_out {t[16]-t[10]} (ln: first-batch loads issued {t[13]-t[10]}, passA {t[11]-t[10]}, sync {t[12]-t[11]}, passB {t[16]-t[12]}) | epilogue_end {t[16]-t[1]} total {t[17]-t[0]} cycles")
