@@ -151,6 +151,7 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
   }
   if (rank == 0 && tid == 0) idxs[0] = 0;
 
+  int next_mark = (progress != nullptr) ? min(every, m) : 0;  // sample count at which the next milestone is published
   for (int it = 1; it < m; ++it) {
     const int buf = it & 1;
     if (CL > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], CL * 20);
@@ -252,7 +253,8 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
       // progress milestones (eda_furthest_point_sampling_progress): idxs[0..it] of this scene are final and
       // visible device-wide before the counter moves, so a consumer released by a stream-ordered wait on the
       // counter may start on the first (it + 1) centres while the sampling continues
-      if (progress != nullptr && ((it + 1) % every == 0 || it == m - 1)) {
+      if (it + 1 == next_mark) {  // (no per-iteration division: thread 0's warp is on the critical chain)
+        next_mark = min(next_mark + every, m);
         __threadfence();
         atomicAdd(progress, 1);
       }
@@ -291,6 +293,7 @@ fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float
   float ox = p0x, oy = p0y, oz = p0z;
   if (tid == 0) idxs[0] = 0;
   __syncthreads();
+  int next_mark = (progress != nullptr) ? min(every, m) : 0;
   for (int it = 1; it < m; ++it) {
     const int buf = it & 1;
     float best = -1.0f;
@@ -317,7 +320,8 @@ fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float
     ox = xyz[(size_t)old * 3]; oy = xyz[(size_t)old * 3 + 1]; oz = xyz[(size_t)old * 3 + 2];
     if (tid == 0) {
       idxs[it] = old;
-      if (progress != nullptr && ((it + 1) % every == 0 || it == m - 1)) {
+      if (it + 1 == next_mark) {  // (no per-iteration division: thread 0's warp is on the critical chain)
+        next_mark = min(next_mark + every, m);
         __threadfence();
         atomicAdd(progress, 1);
       }
