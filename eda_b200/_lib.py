@@ -51,6 +51,15 @@ PROTOTYPES = {
     "eda_debug_timestamps_attn": (_c_int, [_vp, _c_int]),
     "eda_attention_forward": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                                        _c_float, ctypes.c_uint, _vp, _vp]),
+    "eda_linear_pack_strided": (_c_int, [_vp, ctypes.c_longlong, ctypes.c_longlong, _c_int, _c_int, _vp, _vp]),
+    "eda_attention_forward_lse": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
+                                           _c_float, ctypes.c_uint, _vp, _vp, _vp]),
+    "eda_attention_backward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
+                                        _c_int, _c_int, _c_float, _c_float, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp]),
+    "eda_wgrad": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp]),
+    "eda_layernorm_backward": (_c_int, [_vp, _vp, _vp, _c_float, ctypes.c_longlong, _c_int, _vp, _vp, _vp, _vp, _c_float,
+                                        ctypes.c_uint, _vp]),
+    "eda_relu_backward": (_c_int, [_vp, _vp, _c_float, ctypes.c_longlong, _vp, _vp]),
     "eda_selftest_umma": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_selftest_umma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
 }
@@ -60,7 +69,13 @@ PROTOTYPES = {
 class LinearProblem(ctypes.Structure):
     """struct eda_linear_problem (include/eda_b200.h)."""
     _fields_ = [("x", _vp), ("pos", _vp), ("w_packed", _vp), ("bias", _vp), ("residual", _vp), ("y", _vp),
-                ("rows", _c_int), ("y_batch_rows", _c_int), ("y_ld", _c_int), ("round_tf32", _c_int)]
+                ("rows", _c_int), ("y_batch_rows", _c_int), ("y_ld", _c_int), ("round_tf32", _c_int), ("pre_ln", _vp)]
+
+
+class WgradProblem(ctypes.Structure):
+    """struct eda_wgrad_problem (include/eda_b200.h)."""
+    _fields_ = [("dy", _vp), ("x", _vp), ("dw", _vp), ("db", _vp), ("rows", ctypes.c_longlong),
+                ("ldy", _c_int), ("ldx", _c_int), ("ldw", _c_int)]
 
 
 _lib = None

@@ -8,10 +8,16 @@ encoder_decoder_layers.py are made of:
 
 Forward = hand-written CUDA only (3 launches per mha_block, 2 per ffn_block); train-mode dropout (attention
 probabilities, block outputs, FFN hidden) is applied inside those kernels from a counter-based hash and the
-backward pass regenerates the same masks (eda_dropout_mask).  Backward (round 1) =
-recompute of the same maths with differentiable torch ops on the GPU, as for the fused SA kernel.
+backward pass regenerates the same masks from the same hash.
+
+Backward = hand-written CUDA as well (csrc/attn_bwd.cu, csrc/grad_ops.cu): LayerNorm backward, the attention core's
+flash-style backward from the saved log-sum-exp, activation gradients through the forward tcgen05 GEMM with the
+transposed weight, weight gradients by the split-row wgrad kernel — ~14 launches per attention block where autograd
+through the reference's math path issues ~45.  EDA_BACKWARD=torch selects the older recompute-with-torch-ops backward
+(kept as a cross-check for the tests).
 There is no CPU path: CPU tensors raise RuntimeError like the rest of the package.
 """
+import os
 import ctypes
 import math
 
@@ -123,6 +129,10 @@ def linear_raw(problems, K, N, relu=False, ln=None, dropout=None):
             arr[i].y_batch_rows, arr[i].y_ld = tb, ld
         arr[i].y, arr[i].rows = y.data_ptr(), R
         arr[i].round_tf32 = 1 if pr.get("round_tf32") else 0
+        pre = pr.get("pre_ln")
+        if pre is not None:
+            assert pre.is_contiguous() and pre.numel() == R * N and ln is not None
+            arr[i].pre_ln = pre.data_ptr()
         outs.append(y)
     g = b = None
     eps = 0.0
@@ -138,7 +148,7 @@ def linear_raw(problems, K, N, relu=False, ln=None, dropout=None):
     return outs
 
 
-def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H, dropout=None):
+def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H, dropout=None, lse=None):
     """q (B*Nq,E), k (B*Nk,E) projected, vt (B,E,ld) channel-major projected values (ld >= Nk, ld % 4 == 0);
     mask (B,Nk) bool or None -> ctx (B*Nq,E)."""
     lib = _lib.load()
@@ -156,14 +166,129 @@ def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H, dropout=None):
         assert m.shape == (B, Nk)
     with torch.cuda.device(q.device):
         dp, dseed = dropout if dropout is not None else (0.0, 0)
-        rc = lib.eda_attention_forward(_p(q), _p(k), _p(vt), ldv, _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), float(dp),
-                                       int(dseed), _p(ctx), _stream(q.device))
+        rc = lib.eda_attention_forward_lse(_p(q), _p(k), _p(vt), ldv, _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D),
+                                           float(dp), int(dseed), _p(ctx), _p(lse), _stream(q.device))
     _lib.check(rc, "attention_forward")
     return ctx
 
 
+
 # ---------------------------------------------------------------------------------------------------
-# differentiable restatements (backward only)
+# backward building blocks (csrc/grad_ops.cu, csrc/attn_bwd.cu)
+# ---------------------------------------------------------------------------------------------------
+def use_cuda_backward():
+    return os.environ.get("EDA_BACKWARD", "cuda") != "torch"
+
+
+def pack_weight_t(W, cache_key=None):
+    """Packs W^T for eda_linear_forward: with W (Nout, Kin) the weight of y = x W^T (any row-strided view), the
+    result drives the activation-gradient GEMM dx = dy W (K = Nout, N = Kin)."""
+    lib = _lib.load()
+    Nout, Kin = W.shape
+    assert W.stride(1) == 1
+    cache = None
+    if cache_key is not None:
+        cache = _cache_of(cache_key[0])
+        tag = (W.data_ptr(), W._version, Nout, Kin, W.stride(0), W.device)
+        hit = cache.get(cache_key[1])
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+    n = lib.eda_linear_packed_floats(Kin, Nout)
+    if n == 0:
+        raise RuntimeError(f"eda_b200.linear: unsupported transposed weight shape ({Kin},{Nout})")
+    packed = torch.empty(n, dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+        rc = lib.eda_linear_pack_strided(_p(W.detach()), 1, int(W.stride(0)), Kin, Nout, _p(packed), _stream(W.device))
+    _lib.check(rc, "linear_pack_strided")
+    if cache is not None:
+        cache[cache_key[1]] = (tag, packed)
+    return packed
+
+
+def wgrad(problems, N, K):
+    """problems: list (<= 6) of dicts dy (R,N), x (R,K), dw (N,K) view [row stride = dw.stride(0)], db (N) or None.
+    dw += dy^T x, db += column sums of dy (accumulating: the caller zero-initialises)."""
+    lib = _lib.load()
+    dev = problems[0]["dy"].device
+    arr = (_lib.WgradProblem * len(problems))()
+    keep = []
+    for i, pr in enumerate(problems):
+        dy, x, dw, db = pr["dy"], pr["x"], pr["dw"], pr.get("db")
+        assert dy.is_contiguous() and x.is_contiguous() and dy.dtype == torch.float32 and x.dtype == torch.float32
+        R = dy.numel() // N
+        assert x.numel() == R * K and dw.shape == (N, K) and dw.stride(1) == 1
+        arr[i].dy, arr[i].x, arr[i].dw = dy.data_ptr(), x.data_ptr(), dw.data_ptr()
+        arr[i].db = db.data_ptr() if db is not None else None
+        arr[i].rows, arr[i].ldy, arr[i].ldx, arr[i].ldw = R, N, K, dw.stride(0)
+        keep.append((dy, x, dw, db))
+    with torch.cuda.device(dev):
+        rc = lib.eda_wgrad(ctypes.cast(arr, ctypes.c_void_p), len(problems), N, K, _stream(dev))
+    _lib.check(rc, "wgrad")
+
+
+def layernorm_backward(dy, u, gamma, eps, dgamma, dbeta, dropout=None):
+    """dy, u (R,N).  Returns (du, dproj): du = gradient of the LayerNorm input, dproj = du with the output-dropout
+    mask of the producing GEMM re-applied (the same tensor as du without dropout)."""
+    lib = _lib.load()
+    N = u.size(-1)
+    R = u.numel() // N
+    du = torch.empty_like(u)
+    dp, dseed = dropout if dropout is not None else (0.0, 0)
+    dproj = torch.empty_like(u) if dp > 0 else du
+    with torch.cuda.device(u.device):
+        rc = lib.eda_layernorm_backward(_p(dy), _p(u), _p(gamma.detach().contiguous()), float(eps), R, N, _p(du),
+                                        _p(dproj) if dp > 0 else None, _p(dgamma), _p(dbeta), float(dp), int(dseed),
+                                        _stream(u.device))
+    _lib.check(rc, "layernorm_backward")
+    return du, dproj
+
+
+def relu_backward(dy, y, scale=1.0):
+    out = torch.empty_like(dy)
+    with torch.cuda.device(dy.device):
+        rc = _lib.load().eda_relu_backward(_p(dy), _p(y), float(scale), dy.numel(), _p(out), _stream(dy.device))
+    _lib.check(rc, "relu_backward")
+    return out
+
+
+def _transpose_last2(x):
+    B, R, C = x.shape
+    out = torch.empty((B, C, R), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().eda_transpose_last2(_p(x), B, R, C, _p(out), _stream(x.device))
+    _lib.check(rc, "transpose_last2")
+    return out
+
+
+def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, H, dropout=None):
+    """q (B*Nq,E), k (B*Nk,E), vt (B,E,ld) as attention_raw took them; dctx, c (B*Nq,E); lse (B,H,Nq).
+    Returns dq (B*Nq,E), dk (B*Nk,E), dv (B*Nk,E)."""
+    lib = _lib.load()
+    E = q.size(-1)
+    D = E // H
+    ld = vt.size(2)
+    v = _transpose_last2(vt)  # (B, ld, E): row-major values, rows >= Nk are padding and never read
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k)
+    dv = torch.empty_like(k)
+    delta = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+    m = None
+    if key_padding_mask is not None:
+        m = key_padding_mask
+        if m.dtype != torch.bool:
+            m = m != 0
+        m = m.contiguous().view(torch.uint8)
+    dp, dseed = dropout if dropout is not None else (0.0, 0)
+    with torch.cuda.device(q.device):
+        rc = lib.eda_attention_backward(_p(q), _p(k), _p(v), ld * E, _p(dctx), _p(c), _p(lse), _p(m), B, Nq, Nk, H, D,
+                                        1.0 / math.sqrt(D), float(dp), int(dseed), _p(delta), _p(dq), _p(dk), _p(dv),
+                                        _stream(q.device))
+    _lib.check(rc, "attention_backward")
+    return dq, dk, dv
+
+
+# ---------------------------------------------------------------------------------------------------
+# differentiable restatements (EDA_BACKWARD=torch cross-check only)
 # ---------------------------------------------------------------------------------------------------
 def _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H, attn_keep=None, attn_scale=1.0):
     E = q_in.size(-1)
@@ -209,19 +334,27 @@ class _MHABlockFn(torch.autograd.Function):
             dict(x=v_in, w_packed=wv, bias=ib[2 * E:], y_batch_rows=Nk, round_tf32=True),
         ], E, E)
         p_attn, seed_attn, p_out, seed_out = drop
-        c = attention_raw(q, k, v, mask, B, Nq, Nk, H, dropout=(p_attn, seed_attn) if p_attn > 0 else None)
+        train = any(ctx.needs_input_grad) and use_cuda_backward()
+        lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if train else None
+        c = attention_raw(q, k, v, mask, B, Nq, Nk, H, dropout=(p_attn, seed_attn) if p_attn > 0 else None, lse=lse)
         res = residual.contiguous() if residual is not None else None
         ln = (ln_w, ln_b, eps) if ln_w is not None else None
-        (y,) = linear_raw([dict(x=c, w_packed=wo, bias=out_b, residual=res)], E, E, ln=ln,
+        u = torch.empty((B * Nq, E), dtype=torch.float32, device=q.device) if (train and ln is not None) else None
+        (y,) = linear_raw([dict(x=c, w_packed=wo, bias=out_b, residual=res, pre_ln=u)], E, E, ln=ln,
                           dropout=(p_out, seed_out) if p_out > 0 else None)
         if ln is None and res is not None:
             y = y + res.view(-1, E)
-        ctx.save_for_backward(q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b)
+        ctx.save_for_backward(q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b,
+                              *((q, k, v, c, lse, u) if train else ()))
         ctx.meta = (H, eps, mask, drop)
+        ctx.key = key
+        ctx.cuda_bw = train
         return y.view(B, Nq, E)
 
     @staticmethod
     def backward(ctx, grad):
+        if ctx.cuda_bw:
+            return _MHABlockFn._backward_cuda(ctx, grad)
         H, eps, mask, drop = ctx.meta
         p_attn, seed_attn, p_out, seed_out = drop
         saved = ctx.saved_tensors
@@ -245,6 +378,65 @@ class _MHABlockFn(torch.autograd.Function):
             grads = torch.autograd.grad(y, wanted, grad, allow_unused=True) if wanted else []
         gmap = {id(t): g for t, g in zip(wanted, grads)}
         return (None, None, None, None, *[gmap.get(id(t)) if t is not None else None for t in ts], None)
+
+
+
+    @staticmethod
+    def _backward_cuda(ctx, grad):
+        H, eps, mask, drop = ctx.meta
+        p_attn, seed_attn, p_out, seed_out = drop
+        (q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b, q, k, vt, c, lse, u) = \
+            ctx.saved_tensors
+        key = ctx.key
+        B, Nq, E = q_in.shape
+        Nk = k_in.size(1)
+        dev = q_in.device
+        grad = grad.contiguous().view(-1, E)
+        has_ln = ln_w is not None
+        # one zeroed buffer for every parameter gradient of the block (the wgrad / LayerNorm kernels accumulate)
+        flat = torch.zeros(3 * E * E + 3 * E + E * E + E + 2 * E, dtype=torch.float32, device=dev)
+        o = 0
+        d_in_w = flat[o:o + 3 * E * E].view(3 * E, E); o += 3 * E * E
+        d_in_b = flat[o:o + 3 * E]; o += 3 * E
+        d_out_w = flat[o:o + E * E].view(E, E); o += E * E
+        d_out_b = flat[o:o + E]; o += E
+        d_ln_w = flat[o:o + E]; o += E
+        d_ln_b = flat[o:o + E]
+        # 1. LayerNorm (+ output dropout)
+        if has_ln:
+            du, dproj = layernorm_backward(grad, u, ln_w, eps, d_ln_w, d_ln_b,
+                                           dropout=(p_out, seed_out) if p_out > 0 else None)
+        else:
+            du = grad
+            dproj = grad
+            if p_out > 0:
+                dproj = grad * (dropout_mask(seed_out, p_out, B * Nq, E, 3, 0, dev) * (1.0 / (1.0 - p_out)))
+        # 2. out-projection: activation gradient (tcgen05 GEMM with the transposed weight) and weight gradient
+        (dctx,) = linear_raw([dict(x=dproj, w_packed=pack_weight_t(out_w, cache_key=(key, "ot")))], E, E)
+        wgrad([dict(dy=dproj, x=c, dw=d_out_w, db=d_out_b)], E, E)
+        # 3. attention core
+        dq, dk, dv = attention_backward_raw(q, k, vt, dctx, c, lse, mask, B, Nq, Nk, H,
+                                            dropout=(p_attn, seed_attn) if p_attn > 0 else None)
+        # 4. in-projections
+        dq_in, dk_in, dv_in = linear_raw([
+            dict(x=dq, w_packed=pack_weight_t(in_w[:E], cache_key=(key, "qt"))),
+            dict(x=dk, w_packed=pack_weight_t(in_w[E:2 * E], cache_key=(key, "kt"))),
+            dict(x=dv, w_packed=pack_weight_t(in_w[2 * E:], cache_key=(key, "vt"))),
+        ], E, E)
+        probs = [dict(dy=dq, x=q_in, dw=d_in_w[:E], db=d_in_b[:E]),
+                 dict(dy=dk, x=k_in, dw=d_in_w[E:2 * E], db=d_in_b[E:2 * E]),
+                 dict(dy=dv, x=v_in, dw=d_in_w[2 * E:], db=d_in_b[2 * E:])]
+        if q_pos is not None:
+            probs.append(dict(dy=dq, x=q_pos.contiguous(), dw=d_in_w[:E]))
+        if k_pos is not None:
+            probs.append(dict(dy=dk, x=k_pos.contiguous(), dw=d_in_w[E:2 * E]))
+        wgrad(probs, E, E)
+        dq_in = dq_in.view(B, Nq, E)
+        dk_in = dk_in.view(B, Nk, E)
+        dv_in = dv_in.view(B, Nk, E)
+        return (None, None, None, None, dq_in, dq_in if q_pos is not None else None, dk_in,
+                dk_in if k_pos is not None else None, dv_in, du.view(B, Nq, E) if residual is not None else None,
+                d_in_w, d_in_b, d_out_w, d_out_b, d_ln_w if has_ln else None, d_ln_b if has_ln else None, None)
 
 
 def mha_block(mha, q_in, k_in, v_in, q_pos=None, k_pos=None, key_padding_mask=None, residual=None, norm=None,
@@ -271,16 +463,48 @@ class _FFNBlockFn(torch.autograd.Function):
         p1 = pack_weight(w1, cache_key=(key, "w1"))
         p2 = pack_weight(w2, cache_key=(key, "w2"))
         pa, sa, pb, sb = drop
+        train = any(ctx.needs_input_grad) and use_cuda_backward()
         (hdn,) = linear_raw([dict(x=x2, w_packed=p1, bias=b1)], E, Fh, relu=True, dropout=(pa, sa) if pa > 0 else None)
-        (y,) = linear_raw([dict(x=hdn, w_packed=p2, bias=b2, residual=x2)], Fh, E, ln=(ln_w, ln_b, eps),
+        u = torch.empty_like(x2) if train else None
+        (y,) = linear_raw([dict(x=hdn, w_packed=p2, bias=b2, residual=x2, pre_ln=u)], Fh, E, ln=(ln_w, ln_b, eps),
                           dropout=(pb, sb) if pb > 0 else None)
-        ctx.save_for_backward(x, w1, b1, w2, b2, ln_w, ln_b)
+        ctx.save_for_backward(x, w1, b1, w2, b2, ln_w, ln_b, *((hdn, u) if train else ()))
         ctx.eps = eps
         ctx.drop = drop
+        ctx.key = key
+        ctx.cuda_bw = train
         return y.view(shape)
 
     @staticmethod
+    def _backward_cuda(ctx, grad):
+        x, w1, b1, w2, b2, ln_w, ln_b, hdn, u = ctx.saved_tensors
+        pa, sa, pb, sb = ctx.drop
+        key = ctx.key
+        E, Fh = w1.size(1), w1.size(0)
+        dev = x.device
+        grad = grad.contiguous().view(-1, E)
+        flat = torch.zeros(2 * E * Fh + Fh + E + 2 * E, dtype=torch.float32, device=dev)
+        o = 0
+        dw1 = flat[o:o + Fh * E].view(Fh, E); o += Fh * E
+        dw2 = flat[o:o + E * Fh].view(E, Fh); o += E * Fh
+        db1 = flat[o:o + Fh]; o += Fh
+        db2 = flat[o:o + E]; o += E
+        d_ln_w = flat[o:o + E]; o += E
+        d_ln_b = flat[o:o + E]
+        du, dproj = layernorm_backward(grad, u, ln_w, ctx.eps, d_ln_w, d_ln_b, dropout=(pb, sb) if pb > 0 else None)
+        (dh,) = linear_raw([dict(x=dproj, w_packed=pack_weight_t(w2, cache_key=(key, "w2t")))], E, Fh)
+        # hdn is the saved post-ReLU, post-dropout activation: > 0 exactly where the unit was active and kept
+        dz = relu_backward(dh, hdn, 1.0 / (1.0 - pa) if pa > 0 else 1.0)
+        wgrad([dict(dy=dproj, x=hdn, dw=dw2, db=db2)], E, Fh)
+        wgrad([dict(dy=dz, x=x.contiguous().view(-1, E), dw=dw1, db=db1)], Fh, E)
+        (dx,) = linear_raw([dict(x=dz, w_packed=pack_weight_t(w1, cache_key=(key, "w1t")))], Fh, E)
+        dx += du
+        return (None, None, dx.view(x.shape), dw1, db1, dw2, db2, d_ln_w, d_ln_b, None)
+
+    @staticmethod
     def backward(ctx, grad):
+        if ctx.cuda_bw:
+            return _FFNBlockFn._backward_cuda(ctx, grad)
         with torch.enable_grad():
             ts = [t.detach().requires_grad_(ctx.needs_input_grad[2 + i]) for i, t in enumerate(ctx.saved_tensors)]
             x, w1, b1, w2, b2, ln_w, ln_b = ts

@@ -42,6 +42,7 @@ struct AttnParams {
   const float *q, *k, *vt;    // vt: (B, H*D, ldv) channel-major
   const unsigned char *mask;  // (B, Nk), nonzero = key ignored; may be null
   float *ctx;
+  float *lse;                 // optional (B, H, Nq): log-sum-exp of the masked scores, for eda_attention_backward
   int Nq, Nk, H, ldv;
   float scale;
   uint32_t drop_thresh, drop_seed;  // dropout on the attention probabilities (nn.MultiheadAttention(dropout=p)); 0 = off
@@ -311,7 +312,9 @@ attention_kernel(const AttnParams p) {
   {
     s_x[half][r] = l;
     __syncthreads();
-    const float inv = 1.0f / (s_x[0][r] + s_x[1][r]);
+    const float ltot = s_x[0][r] + s_x[1][r];
+    const float inv = 1.0f / ltot;
+    if (p.lse && half == 0 && qvalid) p.lse[((size_t)b * p.H + h) * p.Nq + qrow] = m + logf(ltot);
     float *dst = p.ctx + ((size_t)b * p.Nq + qrow) * HD + h * D;
 #pragma unroll
     for (int i = 0; i < kOChunks; ++i) {
@@ -367,10 +370,10 @@ extern "C" int eda_debug_timestamps_attn(long long *host_out, int n) {
   return EDA_OK;
 }
 
-extern "C" int eda_attention_forward(const float *q, const float *k, const float *v, int ldv,
-                                     const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                     float scale, float dropout_p, unsigned int dropout_seed, float *ctx,
-                                     void *stream) {
+extern "C" int eda_attention_forward_lse(const float *q, const float *k, const float *v, int ldv,
+                                         const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
+                                         float scale, float dropout_p, unsigned int dropout_seed, float *ctx,
+                                         float *lse, void *stream) {
   using namespace eda;
   if (B < 0 || Nq < 0 || Nk < 1 || H < 1 || D < 1) return EDA_ERR_INVALID_ARGUMENT;
   if (H > 65535 || B > 65535) return EDA_ERR_UNSUPPORTED;
@@ -381,7 +384,7 @@ extern "C" int eda_attention_forward(const float *q, const float *k, const float
       (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15))
     return EDA_ERR_INVALID_ARGUMENT;
   AttnParams p = {};
-  p.q = q; p.k = k; p.vt = v; p.mask = key_padding_mask; p.ctx = ctx;
+  p.q = q; p.k = k; p.vt = v; p.mask = key_padding_mask; p.ctx = ctx; p.lse = lse;
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.ldv = ldv; p.scale = scale;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
@@ -392,4 +395,12 @@ extern "C" int eda_attention_forward(const float *q, const float *k, const float
     case 64: return launch_attention<64>(p, B, st);
     default: return EDA_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int eda_attention_forward(const float *q, const float *k, const float *v, int ldv,
+                                     const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
+                                     float scale, float dropout_p, unsigned int dropout_seed, float *ctx,
+                                     void *stream) {
+  return eda_attention_forward_lse(q, k, v, ldv, key_padding_mask, B, Nq, Nk, H, D, scale, dropout_p, dropout_seed, ctx,
+                                   nullptr, stream);
 }

@@ -50,6 +50,7 @@ constexpr int kPrefetch = 1;  // blocks the staging warps run ahead (the slot it
 struct LinProblem {
   const float *x, *pos, *w, *bias, *residual;
   float *y;
+  float *pre;  // optional (rows, N): the LayerNorm INPUT (residual + product), saved for the backward pass
   int rows, tile0;
   int tb, ldt;  // tb > 0: channel-major output, y[((row / tb) * N + col) * ldt + row % tb]
   int round_out;  // round the outputs to tf32 (they feed tensor-core operands of the attention kernel directly)
@@ -427,6 +428,7 @@ linear_kernel(const LinParams p) {
           const int c4 = lane + j * 32;
           if (c4 < n4) {
             float4 o = src[c4];
+            if (pr.pre) reinterpret_cast<float4 *>(pr.pre + (row0 + rr) * Nf + n0)[c4] = o;
             if (p.ln) {
               const float4 g4 = *reinterpret_cast<const float4 *>(s_gamma + c4 * 4);
               const float4 e4 = *reinterpret_cast<const float4 *>(s_beta + c4 * 4);
@@ -455,7 +457,7 @@ linear_kernel(const LinParams p) {
 // W (N, K) row-major [* scale[n]] -> blocks [kb] of float4 [kcnt/4][N] (K-major core-matrix layout,
 // chunk-major), rounded to tf32 once.  K is zero-padded to a multiple of 8.
 __global__ void pack_linear_kernel(const float *__restrict__ W, const float *__restrict__ scale, int N, int K, int Kpad,
-                                   int NS, float *__restrict__ dst) {
+                                   int NS, long long sn, long long sk, float *__restrict__ dst) {
   // destination order: [column split s][k block][16-byte chunk][NS columns] float4
   const int total = N * Kpad;
   const int per_split = Kpad * NS;
@@ -469,7 +471,7 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, const float *__r
     const int k = kb * kKBlock + c * 4 + (rem & 3);
     float w = 0.f;
     if (k < K) {
-      w = W[(size_t)n * K + k];
+      w = W[n * sn + k * sk];
       if (scale) w *= scale[n];
     }
     dst[e] = to_tf32(w);
@@ -537,7 +539,18 @@ int eda_linear_pack(const float *W, const float *scale, int N, int K, float *pac
   if (!W || !packed) return EDA_ERR_INVALID_ARGUMENT;
   const int total = N * kpad_of(K);
   pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, scale, N, K, kpad_of(K), N / lin_splits(N),
-                                                                         packed);
+                                                                         (long long)K, 1LL, packed);
+  return check_launch("pack_linear_kernel");
+}
+
+int eda_linear_pack_strided(const float *W, long long stride_n, long long stride_k, int N, int K, float *packed,
+                            void *stream) {
+  using namespace eda;
+  if (!lin_supported(N, K)) return EDA_ERR_UNSUPPORTED;
+  if (!W || !packed) return EDA_ERR_INVALID_ARGUMENT;
+  const int total = N * kpad_of(K);
+  pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, nullptr, N, K, kpad_of(K), N / lin_splits(N),
+                                                                         stride_n, stride_k, packed);
   return check_launch("pack_linear_kernel");
 }
 
@@ -558,8 +571,9 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
       return EDA_ERR_INVALID_ARGUMENT;
     if (q.y_batch_rows < 0 || (q.y_batch_rows > 0 && (q.y_ld < q.y_batch_rows || layer_norm)))
       return EDA_ERR_INVALID_ARGUMENT;
+    if (q.pre_ln && (q.y_batch_rows > 0 || (reinterpret_cast<uintptr_t>(q.pre_ln) & 15))) return EDA_ERR_INVALID_ARGUMENT;
     p.pr[i].x = q.x; p.pr[i].pos = q.pos; p.pr[i].w = q.w_packed; p.pr[i].bias = q.bias;
-    p.pr[i].residual = q.residual; p.pr[i].y = q.y; p.pr[i].rows = q.rows; p.pr[i].tile0 = tiles;
+    p.pr[i].residual = q.residual; p.pr[i].y = q.y; p.pr[i].pre = q.pre_ln; p.pr[i].rows = q.rows; p.pr[i].tile0 = tiles;
     p.pr[i].tb = q.y_batch_rows; p.pr[i].ldt = q.y_ld; p.pr[i].round_out = q.round_tf32;
     tiles += (q.rows + kRows - 1) / kRows;
   }

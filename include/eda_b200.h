@@ -198,9 +198,16 @@ typedef struct eda_linear_problem {
   int y_ld;              /* >= T; padding columns are not written */
   int round_tf32;        /* != 0: round outputs to tf32 (round-to-nearest): K and V projections, whose outputs
                             eda_attention_forward feeds to the tensor cores as they are */
+  float *pre_ln;         /* optional (rows, N): receives the LayerNorm input (residual + product), which
+                            eda_layernorm_backward needs; NULL = not stored */
 } eda_linear_problem;
 EDA_API size_t eda_linear_packed_floats(int N, int K);
 EDA_API int eda_linear_pack(const float *W, const float *scale, int N, int K, float *packed, void *stream);
+/* Same packing for a strided view: element (n, k) of the (N, K) weight is W[n * stride_n + k * stride_k].  With
+ * stride_n = 1, stride_k = ld it packs the TRANSPOSE of a row-major matrix, which turns eda_linear_forward into the
+ * activation-gradient GEMM dX = dY W of a layer y = x W^T (autograd's mm backward in the reference). */
+EDA_API int eda_linear_pack_strided(const float *W, long long stride_n, long long stride_k, int N, int K, float *packed,
+                                    void *stream);
 EDA_API int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu,
                                const float *ln_gamma, const float *ln_beta, float ln_eps, int layer_norm,
                                float dropout_p, unsigned int dropout_seed, void *stream);
@@ -210,6 +217,49 @@ EDA_API int eda_debug_timestamps_attn(long long *host_out, int n); /* same, atte
 EDA_API int eda_attention_forward(const float *q, const float *k, const float *vt, int ldv,
                                   const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
                                   float scale, float dropout_p, unsigned int dropout_seed, float *ctx, void *stream);
+/* Training variant: also writes lse (B, H, Nq), the log-sum-exp of every query's masked, scaled scores (NULL = skip). */
+EDA_API int eda_attention_forward_lse(const float *q, const float *k, const float *vt, int ldv,
+                                      const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
+                                      float scale, float dropout_p, unsigned int dropout_seed, float *ctx, float *lse,
+                                      void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Backward pass of the attention layers.  In the reference this is autograd through
+ * nn.MultiheadAttention's math path, nn.Linear and nn.LayerNorm (torch/nn/functional.py:6607-6665 as used by
+ * models/encoder_decoder_layers.py:37-124,127-186,288-407): per module ~45 library kernels and two (B*H, Nq, Nk)
+ * tensors in HBM.  Here:
+ *
+ * eda_attention_backward: q (B,Nq,H*D), k (B,Nk,H*D), v (B,Nk,H*D; scenes v_batch_stride floats apart) are the
+ *   PROJECTED inputs of eda_attention_forward_lse (v row-major here), ctx / lse its outputs, dctx the gradient of ctx.
+ *   Recomputes the probabilities from lse tile by tile and writes dq, dk, dv (same layouts; fully overwritten, no
+ *   atomics, deterministic).  delta (B,H,Nq) is scratch (rowsum(dctx * ctx)).  The dropout mask of the forward call
+ *   (dropout_p, dropout_seed) is regenerated from the same hash.  Head dims compiled: D in {32, 36}.
+ * eda_wgrad: for every problem i, dw_i (N, K; row stride ldw) += dy_i (rows, N; ldy)^T x_i (rows, K; ldx) and, when db_i
+ *   is not NULL, db_i (N) += column sums of dy_i.  ACCUMULATES (atomics): zero the outputs first.  N, K, ldy, ldx
+ *   multiples of 4, dy / x 16-byte aligned.  Up to 6 problems of one (N, K) per launch.
+ * eda_layernorm_backward: y = LayerNorm(u) * gamma + beta over the last dim N (<= 384, multiple of 4).  Writes
+ *   du (rows, N); dgamma / dbeta (N) are ACCUMULATED (may be NULL).  With dropout_p > 0 also writes
+ *   dproj = du * keep / (1 - p), the gradient of the GEMM output that eda_linear_forward(dropout_p, dropout_seed)
+ *   dropped before the residual add (single-problem launch); with dropout_p == 0 dproj is not written (it equals du).
+ * eda_relu_backward: out = dy * [y > 0] * scale, n elements (multiple of 4). */
+typedef struct eda_wgrad_problem {
+  const float *dy; /* (rows, N), row stride ldy */
+  const float *x;  /* (rows, K), row stride ldx */
+  float *dw;       /* (N, K), row stride ldw; accumulated */
+  float *db;       /* (N) accumulated, or NULL */
+  long long rows;
+  int ldy, ldx, ldw;
+} eda_wgrad_problem;
+EDA_API int eda_attention_backward(const float *q, const float *k, const float *v, long long v_batch_stride,
+                                   const float *dctx, const float *ctx, const float *lse,
+                                   const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
+                                   float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
+                                   float *dk, float *dv, void *stream);
+EDA_API int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *stream);
+EDA_API int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, float eps, long long rows, int N,
+                                   float *du, float *dproj, float *dgamma, float *dbeta, float dropout_p,
+                                   unsigned int dropout_seed, void *stream);
+EDA_API int eda_relu_backward(const float *dy, const float *y, float scale, long long n, float *out, void *stream);
 /* Train-mode dropout (nn.Dropout after attention / FFN blocks, attention-probability dropout of
  * nn.MultiheadAttention(dropout=p), encoder_decoder_layers.py:47-59,94,106,118 ...): dropout_p > 0 makes
  * eda_linear_forward zero each output element (after bias / ReLU, before the residual) and eda_attention_forward each
