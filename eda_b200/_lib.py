@@ -60,6 +60,16 @@ PROTOTYPES = {
     "eda_layernorm_backward": (_c_int, [_vp, _vp, _vp, _c_float, ctypes.c_longlong, _c_int, _vp, _vp, _vp, _vp, _c_float,
                                         ctypes.c_uint, _vp]),
     "eda_relu_backward": (_c_int, [_vp, _vp, _c_float, ctypes.c_longlong, _vp, _vp]),
+    "eda_sa_gather_rows": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
+                                    _c_int, _vp, _vp]),
+    "eda_bn_relu_apply": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _c_int, _vp, _vp]),
+    "eda_sa_pool_backward": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _c_int, _c_int, _vp, _vp, _vp]),
+    "eda_sa_pool_backward_apply": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _c_int, ctypes.c_longlong,
+                                            _c_int, _c_int, _vp]),
+    "eda_bn_relu_backward_stats": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _c_int, _vp, _vp]),
+    "eda_bn_relu_backward_apply": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _c_int, ctypes.c_longlong,
+                                            _c_int, _vp]),
+    "eda_sa_scatter_rows": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_selftest_umma": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_selftest_umma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
 }

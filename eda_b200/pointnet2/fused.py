@@ -2,11 +2,13 @@
 train-mode BatchNorm statistics passes, layout bookkeeping and the autograd boundary.
 
 Forward is entirely hand-written CUDA (pack -> [stats pass -> finalize] x3 in train mode -> fused
-gather+MLP+max-pool).  Backward (round 1): the grouped tensor is rebuilt with the unfused CUDA ops
-and differentiated by autograd — identical maths to the reference's backward
-(group_points_grad scatter, cuDNN/cuBLAS conv + BatchNorm backward); a fused backward is the next step.
+gather+MLP+max-pool).  Backward is hand-written CUDA too (csrc/sa_bwd.cu + the GEMM kernels): the grouped rows are
+rebuilt row-major, the three layers recomputed on the tcgen05 GEMM, and max-pool / ReLU / BatchNorm backward, the
+activation and weight gradients and the feature scatter run as one-pass kernels (see `_sa_backward_cuda`).
+EDA_BACKWARD=torch selects the older path (unfused CUDA ops + autograd through cuDNN), kept as a cross-check.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -55,12 +57,15 @@ def fusable(C, widths, nsample):
     return _lib.load().eda_sa_mlp_packed_floats(int(C), *[int(w) for w in widths]) > 0
 
 
-def _bn_scale_shift(lib, dev, stats, count, bn, conv_bias, C, training_update):
-    """scale/shift of one layer.  bn None: scale = None (1), shift = conv bias (or None)."""
+def _bn_scale_shift(lib, dev, stats, count, bn, conv_bias, C, training_update, want_stats=False):
+    """scale/shift of one layer.  bn None: scale = None (1), shift = conv bias (or None).  want_stats: also returns
+    the (2, C) [mean, invstd] the scale/shift were built from (BatchNorm backward needs them)."""
     if bn is None:
-        return None, (conv_bias.detach().contiguous() if conv_bias is not None else None)
+        r = None, (conv_bias.detach().contiguous() if conv_bias is not None else None)
+        return r + (None,) if want_stats else r
     scale = torch.empty(C, dtype=torch.float32, device=dev)
     shift = torch.empty(C, dtype=torch.float32, device=dev)
+    mean_invstd = torch.empty(2, C, dtype=torch.float32, device=dev) if want_stats else None
     momentum = bn.momentum
     if training_update:
         bn.num_batches_tracked += 1
@@ -68,14 +73,16 @@ def _bn_scale_shift(lib, dev, stats, count, bn, conv_bias, C, training_update):
             momentum = 1.0 / float(bn.num_batches_tracked.item())
     rc = lib.eda_bn_finalize(_p(stats), float(count), _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps),
                              float(momentum if momentum is not None else 0.0), _p(bn.running_mean),
-                             _p(bn.running_var), 1 if training_update else 0, C, _p(scale), _p(shift), None, None,
+                             _p(bn.running_var), 1 if training_update else 0, C, _p(scale), _p(shift),
+                             _p(mean_invstd[0]) if want_stats else None, _p(mean_invstd[1]) if want_stats else None,
                              _stream(dev))
     _lib.check(rc, "bn_finalize")
-    return scale, shift
+    return (scale, shift, mean_invstd) if want_stats else (scale, shift)
 
 
-def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, training):
-    """Runs the fused kernels.  layers = [(conv, bn_or_None)] * 3.  Returns out (B,M,C3) point-major."""
+def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, training, state=None):
+    """Runs the fused kernels.  layers = [(conv, bn_or_None)] * 3.  Returns out (B,M,C3) point-major.
+    state: optional list that receives, per layer, (scale, shift, [mean, invstd]) for the backward pass."""
     lib = _lib.load()
     dev = xyz.device
     B, N, _ = xyz.shape
@@ -115,6 +122,9 @@ def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, tr
         with torch.cuda.device(dev):
             out = torch.empty((B, M, widths[2]), dtype=torch.float32, device=dev)
             run(0, out, None)
+            if state is not None:
+                for l, (conv, bn) in enumerate(layers):
+                    state.append(_bn_scale_shift(lib, dev, None, 0.0, bn, conv.bias, widths[l], False, want_stats=True))
         return out
     with torch.cuda.device(dev):
         for l, (conv, bn) in enumerate(layers):
@@ -124,9 +134,13 @@ def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, tr
                 stats = torch.empty(2 * widths[l], dtype=torch.float32, device=dev)
                 pack(l + 1)
                 run(l + 1, None, stats)
-                scales[l], shifts[l] = _bn_scale_shift(lib, dev, stats, count, bn, conv.bias, widths[l], True)
+                scales[l], shifts[l], mi = _bn_scale_shift(lib, dev, stats, count, bn, conv.bias, widths[l], True,
+                                                           want_stats=True)
             else:
-                scales[l], shifts[l] = _bn_scale_shift(lib, dev, None, 0.0, bn, conv.bias, widths[l], False)
+                scales[l], shifts[l], mi = _bn_scale_shift(lib, dev, None, 0.0, bn, conv.bias, widths[l], False,
+                                                           want_stats=True)
+            if state is not None:
+                state.append((scales[l], shifts[l], mi))
         out = torch.empty((B, M, widths[2]), dtype=torch.float32, device=dev)
         pack(3)
         run(0, out, None)
@@ -169,7 +183,10 @@ class FusedSAFunction(torch.autograd.Function):
         # BN buffers as they are BEFORE this forward (eval-mode backward needs the ones that were used)
         ctx.running = [(bn.running_mean.clone(), bn.running_var.clone()) if (bn is not None and not training) else None
                        for _, bn in layers]
-        out_pm = sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, module.radius, module.normalize_xyz, training)
+        ctx.cuda_bw = (any(ctx.needs_input_grad) and all(has_bn) and os.environ.get("EDA_BACKWARD", "cuda") != "torch")
+        ctx.state = [] if ctx.cuda_bw else None
+        out_pm = sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, module.radius, module.normalize_xyz, training,
+                                state=ctx.state)
         out = transpose_last2(out_pm)
         ctx.save_for_backward(xyz, new_xyz, features, idx, *params)
         ctx.meta = (has_bn, float(module.radius), bool(module.normalize_xyz), training,
@@ -179,6 +196,8 @@ class FusedSAFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out, _grad_pm=None):
+        if ctx.cuda_bw:
+            return _sa_backward_cuda(ctx, grad_out)
         xyz, new_xyz, features, idx, *params = ctx.saved_tensors
         has_bn, radius, normalize_xyz, training, eps = ctx.meta
         with torch.enable_grad():
@@ -191,6 +210,101 @@ class FusedSAFunction(torch.autograd.Function):
         gf = gmap.get(id(f)) if f is not None else None
         gps = [gmap.get(id(p)) if p is not None else None for p in ps]
         return (None, None, None, gf, None, *gps)
+
+
+def _sa_backward_cuda(ctx, grad_out):
+    """Backward of one fused SA stage on the CUDA kernels.  Per layer l (rows R = B*M*S, row-major activations):
+         recompute   x0 = gather, z_l = a_{l-1} W_l^T (tcgen05 GEMM), a_l = relu(z_l scale_l + shift_l)
+         layer 3     arg-max over the S rows of a centre + ReLU gate -> dy3 (one row per centre and channel)
+         BatchNorm   dz_l = scale_l (dy_l - mean(dy_l) - zhat_l mean(dy_l zhat_l)); d beta = sum dy, d gamma = sum dy zhat
+         GEMMs       dW_l = dz_l^T a_{l-1} (eda_wgrad), da_{l-1} = dz_l W_l (tcgen05 GEMM, transposed packed weight)
+         features    d features[idx] += dx0[:, :C]"""
+    from .. import attn_ops as ops
+
+    lib = _lib.load()
+    xyz, new_xyz, features, idx, *params = ctx.saved_tensors
+    has_bn, radius, normalize_xyz, training, eps = ctx.meta
+    dev = xyz.device
+    stream = _stream(dev)
+    B, N, _ = xyz.shape
+    M, S = idx.size(1), idx.size(2)
+    C = 0 if features is None else features.size(1)
+    # params: per layer conv.weight, conv.bias, bn.weight, bn.bias (every layer has a BatchNorm on this path)
+    Ws = [params[4 * l].detach().reshape(params[4 * l].size(0), -1) for l in range(3)]
+    widths = [w.size(0) for w in Ws]
+    K0pad = ((C + 3 + 15) // 16) * 16
+    R = B * M * S
+    feat_pm = None if features is None else point_major(features.detach())
+    feat_stride = 0 if feat_pm is None else feat_pm.stride(1)
+    new_xyz = new_xyz.contiguous()
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    def chk(rc, what):
+        _lib.check(rc, what)
+
+    def gemm(x, w_packed, K, Nout):
+        (y,) = ops.linear_raw([dict(x=x, w_packed=w_packed)], K, Nout)
+        return y
+
+    with torch.cuda.device(dev):
+        # ---- recompute the forward, row-major ----------------------------------------------------------------
+        x0 = torch.empty((R, K0pad), **f32)
+        chk(lib.eda_sa_gather_rows(_p(xyz), _p(new_xyz), _p(feat_pm), feat_stride, _p(idx), B, N, M, S, C, K0pad,
+                                   float(radius), 1 if normalize_xyz else 0, _p(x0), stream), "sa_gather_rows")
+        # layer-1 weight in the gathered column order [features | xyz | pad] (reference order: [xyz | features])
+        W1p = torch.zeros((widths[0], K0pad), **f32)
+        W1p[:, :C] = Ws[0][:, 3:]
+        W1p[:, C:C + 3] = Ws[0][:, :3]
+        Wl = [W1p, Ws[1].contiguous(), Ws[2].contiguous()]
+        Kin = [K0pad, widths[0], widths[1]]
+        z, a = [None] * 3, [x0, None, None]
+        for l in range(3):
+            z[l] = gemm(a[l], ops.pack_weight(Wl[l]), Kin[l], widths[l])
+            if l < 2:
+                scale, shift, _ = ctx.state[l]
+                a[l + 1] = torch.empty_like(z[l])
+                chk(lib.eda_bn_relu_apply(_p(z[l]), _p(scale), _p(shift), R, widths[l], _p(a[l + 1]), stream),
+                    "bn_relu_apply")
+        # ---- layer 3: max-pool + ReLU + BatchNorm backward -----------------------------------------------------
+        g_pm = transpose_last2(grad_out.contiguous())  # (B, M, C3)
+        stats = [torch.zeros(2 * widths[l], **f32) for l in range(3)]
+        dWl = [torch.zeros_like(Wl[l]) for l in range(3)]
+        scale, shift, mi = ctx.state[2]
+        amax = torch.empty((B * M, widths[2]), dtype=torch.int32, device=dev)
+        chk(lib.eda_sa_pool_backward(_p(z[2]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), _p(g_pm), B * M, S, widths[2],
+                                     _p(amax), _p(stats[2]), stream), "sa_pool_backward")
+        chk(lib.eda_sa_pool_backward_apply(_p(z[2]), _p(amax), _p(g_pm), _p(scale), _p(mi[0]), _p(mi[1]), _p(stats[2]),
+                                           float(R), 1 if training else 0, B * M, S, widths[2], stream),
+            "sa_pool_backward_apply")
+        dz = z[2]  # overwritten in place
+        for l in (2, 1, 0):
+            ops.wgrad([dict(dy=dz, x=a[l], dw=dWl[l])], widths[l], Kin[l])
+            if l == 0:
+                break
+            da = gemm(dz, ops.pack_weight_t(Wl[l]), widths[l], Kin[l])
+            scale, shift, mi = ctx.state[l - 1]
+            chk(lib.eda_bn_relu_backward_stats(_p(da), _p(z[l - 1]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), R,
+                                               widths[l - 1], _p(stats[l - 1]), stream), "bn_relu_backward_stats")
+            chk(lib.eda_bn_relu_backward_apply(_p(da), _p(z[l - 1]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]),
+                                               _p(stats[l - 1]), float(R), 1 if training else 0, R, widths[l - 1], stream),
+                "bn_relu_backward_apply")
+            dz = da
+            z[l] = a[l] = None  # release
+        gf = None
+        if features is not None and ctx.needs_input_grad[3]:
+            dx0 = gemm(dz, ops.pack_weight_t(W1p), widths[0], K0pad)
+            dfeat_pm = torch.zeros((B, N, C), **f32)
+            chk(lib.eda_sa_scatter_rows(_p(dx0), _p(idx), B, N, M, S, C, K0pad, _p(dfeat_pm), stream), "sa_scatter_rows")
+            gf = transpose_last2(dfeat_pm)
+    gps = []
+    for l in range(3):
+        w = params[4 * l]
+        if l == 0:
+            dW = torch.cat([dWl[0][:, C:C + 3], dWl[0][:, :C]], dim=1)
+        else:
+            dW = dWl[l]
+        gps += [dW.reshape(w.shape), None, stats[l][widths[l]:], stats[l][:widths[l]]]
+    return (None, None, None, gf, None, *gps)
 
 
 def sa_params(layers):

@@ -273,6 +273,44 @@ EDA_API int eda_dropout_mask(unsigned int seed, float p, long long rows, int col
                              unsigned int a_add, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Backward pass of the fused set-abstraction stage (eda_sa_mlp_forward).  In the reference: autograd through
+ * QueryAndGroup / SharedMLP / max_pool2d (pointnet2/pointnet2_utils.py:209-257,317-376, pytorch_utils.py:11-36,
+ * pointnet2_modules.py:251-267) = cuDNN convolution / BatchNorm backward on (B,C,npoint,nsample) tensors + the atomic
+ * scatter of group_points_grad (group_points_gpu.cu:48-80).  Here the grouped rows are row-major (row = (b, centre,
+ * sample), column = channel): every layer's GEMM runs on eda_linear_forward / eda_wgrad and these entry points are the
+ * memory-bound stages in between (one pass over HBM each).  scale / shift are the folded BatchNorm terms
+ * (y = z * scale + shift), mean / invstd the statistics they were built from, stats = [sum(dy) (C), sum(dy * zhat) (C)]
+ * (ACCUMULATED: zero first; they are also the gradients of the BatchNorm bias / weight), count = rows the batch
+ * statistics were taken over, batch_stats = 0 for eval-mode (running-statistics) BatchNorm.
+ *   eda_sa_gather_rows          x0 (B*M*S, K0pad) = [features[idx] (C) | (xyz[idx] - new_xyz) [/ radius] (3) | 0]
+ *   eda_bn_relu_apply           out = relu(z * scale[c] + shift[c]),  z (rows, C)
+ *   eda_sa_pool_backward        per (centre, channel): first arg-max row of y3 over the S samples -> amax (centres, C)
+ *                               (-1 where the max is <= 0: the ReLU kills it), stats of layer 3
+ *   eda_sa_pool_backward_apply  z3 <- dz3 = scale (dy3 - mean(dy3) - zhat3 mean(dy3 zhat3)),  dy3 = grad_out at amax
+ *   eda_bn_relu_backward_stats  stats of dy = da * [z * scale + shift > 0]
+ *   eda_bn_relu_backward_apply  da <- dz = scale (dy - mean(dy) - zhat mean(dy zhat))
+ *   eda_sa_scatter_rows         dfeat (B, N, C) point-major += dx0[:, :C] scattered by idx (red.global.add) */
+EDA_API int eda_sa_gather_rows(const float *xyz, const float *new_xyz, const float *feat, int feat_stride,
+                               const int *idx, int B, int N, int M, int S, int C, int K0pad, float radius,
+                               int normalize_xyz, float *x0, void *stream);
+EDA_API int eda_bn_relu_apply(const float *z, const float *scale, const float *shift, long long rows, int C, float *out,
+                              void *stream);
+EDA_API int eda_sa_pool_backward(const float *z3, const float *scale, const float *shift, const float *mean,
+                                 const float *invstd, const float *grad_out, long long centres, int S, int C, int *amax,
+                                 float *stats, void *stream);
+EDA_API int eda_sa_pool_backward_apply(float *z3, const int *amax, const float *grad_out, const float *scale,
+                                       const float *mean, const float *invstd, const float *stats, double count,
+                                       int batch_stats, long long centres, int S, int C, void *stream);
+EDA_API int eda_bn_relu_backward_stats(const float *da, const float *z, const float *scale, const float *shift,
+                                       const float *mean, const float *invstd, long long rows, int C, float *stats,
+                                       void *stream);
+EDA_API int eda_bn_relu_backward_apply(float *da, const float *z, const float *scale, const float *shift,
+                                       const float *mean, const float *invstd, const float *stats, double count,
+                                       int batch_stats, long long rows, int C, void *stream);
+EDA_API int eda_sa_scatter_rows(const float *dx0, const int *idx, int B, int N, int M, int S, int C, int K0pad,
+                                float *dfeat, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05/TMEM building blocks the fused kernels rely on (no reference
  * counterpart).  D[128,N] = A[128,K] * W[N,K]^T with kind::tf32, fp32 accumulate, one CTA.
  * mode 0: A from shared memory; mode 1: A from tensor memory; mode 2: A from shared memory, B staged

@@ -125,11 +125,23 @@ def test_cuda_sa_module_matches_reference_python(path, fuse):
         assert_close_tf32(out.detach().cpu(), want)
     else:
         torch.testing.assert_close(out.detach().cpu(), want, rtol=1e-4, atol=1e-4)
-    # backward (round 1: recomputed through the unfused CUDA ops in fp32 -> reference-grade gradients)
+    # backward.  Unfused: the reference's op sequence in fp32 -> element-wise agreement.  Fused: the CUDA backward
+    # (csrc/sa_bwd.cu) recomputes the layers with tf32 GEMM operands like the forward kernel, so a max-pool arg-max or
+    # ReLU gate whose candidates are within ~1e-3 of each other may resolve differently from the fp32 reference and
+    # move a whole gradient entry (tests/test_backward.py pins every kernel of the chain exactly on shared
+    # pre-activations) -> relative Frobenius error per tensor, bound = the measured flip noise.
     out.backward(_t(z["grad_out"]).cuda())
-    torch.testing.assert_close(feats.grad.cpu(), _t(z["grad_features"]), rtol=2e-3, atol=2e-4)
-    for k, p in m.named_parameters():
-        torch.testing.assert_close(p.grad.cpu(), _t(z["grad." + k]), rtol=2e-3, atol=2e-3, msg=lambda s: f"{k}: {s}")
+    if fuse:
+        def rel(a, b):
+            return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-20)).item()
+
+        assert rel(feats.grad.cpu(), _t(z["grad_features"])) <= 0.1
+        for k, p in m.named_parameters():
+            assert rel(p.grad.cpu(), _t(z["grad." + k])) <= 0.1, k
+    else:
+        torch.testing.assert_close(feats.grad.cpu(), _t(z["grad_features"]), rtol=2e-3, atol=2e-4)
+        for k, p in m.named_parameters():
+            torch.testing.assert_close(p.grad.cpu(), _t(z["grad." + k]), rtol=2e-3, atol=2e-3, msg=lambda s: f"{k}: {s}")
     if training:
         sd = m.state_dict()
         for k in z.files:
