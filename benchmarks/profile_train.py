@@ -94,6 +94,9 @@ def main():
                      "cpu_us": e.cpu_time_total})
     ranges = [r_ for r_ in rows if r_["name"] in ("fwd", "bwd", "bw_sa", "bw_mha", "bw_ffn", "bw_linear")]
     kernels = sorted(rows, key=lambda r_: -r_["self_device_us"])[:45]
+    from torch.autograd import DeviceType
+    res["device_busy_ms_total"] = sum(e.self_device_time_total for e in ka
+                                      if getattr(e, "device_type", None) == DeviceType.CUDA) / 1000.0
     res["ranges"] = ranges
     res["top_self_device"] = kernels
     print(json.dumps(res, indent=1))

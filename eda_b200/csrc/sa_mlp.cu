@@ -49,7 +49,7 @@ struct SaParams {
   const float *packed;   // pre-packed weights (eda_sa_mlp_pack)
   const float *shift[3]; // per-layer additive term after the (scale-folded) conv; null = 0
   float *out;            // (B,M,C3) zero-initialised, stats_layer == 0
-  float *stats;          // [2][C_l] zero-initialised (sum, sum of squares), stats_layer > 0
+  double *stats;         // [2][C_l] zero-initialised (sum, sum of squares; fp64 so that var = E[z^2] - E[z]^2 over ~1e6 rows keeps its digits), stats_layer > 0
   long long total_rows;  // B*M*S
   int N, M, S, log2S, C, feat_stride;
   int K0pad, Cout[3];
@@ -236,7 +236,7 @@ sa_mlp_kernel(const SaParams p) {
       umma::tmem_st_wait();
     };
     // per-channel sum / sum of squares of the raw conv output over this tile's valid rows
-    auto take_stats = [&](uint32_t taddr, int ncols, float *sum, float *sumsq, bool valid) {
+    auto take_stats = [&](uint32_t taddr, int ncols, double *sum, double *sumsq, bool valid) {
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t u[16];
         umma::tmem_ld16(taddr + (uint32_t)c0, u);
@@ -253,8 +253,8 @@ sa_mlp_kernel(const SaParams p) {
         const float a = s1[0] + __shfl_xor_sync(kFull, s1[0], 16);
         const float q = s2[0] + __shfl_xor_sync(kFull, s2[0], 16);
         if (lane < 16) {
-          atomicAdd(sum + c0 + lane, a);
-          atomicAdd(sumsq + c0 + lane, q);
+          atomicAdd(sum + c0 + lane, (double)a);
+          atomicAdd(sumsq + c0 + lane, (double)q);
         }
       }
     };
@@ -440,7 +440,7 @@ __global__ void pack_layer_kernel(const float *__restrict__ W, const float *__re
 // eps 1e-5, momentum 0.1 set at models/bdetr.py:341-345): normalise with the biased variance, update
 // running_var with the unbiased one.  Also used with precomputed running stats (count <= 0): then
 // stats is ignored and running_mean/var are read.
-__global__ void bn_finalize_kernel(const float *__restrict__ stats, double count, const float *__restrict__ gamma,
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, double count, const float *__restrict__ gamma,
                                    const float *__restrict__ beta, float eps, float momentum,
                                    float *__restrict__ running_mean, float *__restrict__ running_var, int update,
                                    int C, float *__restrict__ scale, float *__restrict__ shift,
@@ -449,8 +449,8 @@ __global__ void bn_finalize_kernel(const float *__restrict__ stats, double count
   if (c >= C) return;
   double mean, var;
   if (count > 0) {
-    mean = (double)stats[c] / count;
-    var = (double)stats[C + c] / count - mean * mean;
+    mean = stats[c] / count;
+    var = stats[C + c] / count - mean * mean;
     if (var < 0) var = 0;
     if (update && running_mean && running_var) {
       const double unbiased = count > 1 ? var * count / (count - 1) : var;
@@ -537,7 +537,7 @@ static int sa_mlp_forward_impl(const float *xyz, const float *new_xyz, const int
                                int feat_stride, const int *idx, const float *packed, const float *shift1,
                                const float *shift2, const float *shift3, int B, int N, int M, int Mtot, int m0, int S,
                                int C, int C1, int C2, int C3, float radius, int normalize_xyz, int stats_layer,
-                               int zero_fill, float *out, float *stats, void *stream) {
+                               int zero_fill, float *out, double *stats, void *stream) {
   using namespace eda;
   if (B < 0 || N <= 0 || M < 0 || S <= 0 || m0 < 0 || m0 + M > Mtot) return EDA_ERR_INVALID_ARGUMENT;
   if (!dims_supported(C, C1, C2, C3) || stats_layer < 0 || stats_layer > 3) return EDA_ERR_UNSUPPORTED;
@@ -566,7 +566,7 @@ static int sa_mlp_forward_impl(const float *xyz, const float *new_xyz, const int
     if (stats_layer == 0)
       EDA_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * Mtot * C3 * sizeof(float), st), "sa out memset");
     else
-      EDA_CUDA_TRY(cudaMemsetAsync(stats, 0, (size_t)2 * Cl * sizeof(float), st), "sa stats memset");
+      EDA_CUDA_TRY(cudaMemsetAsync(stats, 0, (size_t)2 * Cl * sizeof(double), st), "sa stats memset");
   }
 
   const size_t smem = (size_t)kRing * kSlotBytes + 3 * kMaxC * sizeof(float);
@@ -587,7 +587,7 @@ static int sa_mlp_forward_impl(const float *xyz, const float *new_xyz, const int
 int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const float *feat, int feat_stride, const int *idx,
                        const float *packed, const float *shift1, const float *shift2, const float *shift3, int B,
                        int N, int M, int S, int C, int C1, int C2, int C3, float radius, int normalize_xyz,
-                       int stats_layer, float *out, float *stats, void *stream) {
+                       int stats_layer, float *out, double *stats, void *stream) {
   if (!new_xyz && (long long)B * M * S > 0) return EDA_ERR_INVALID_ARGUMENT;
   return sa_mlp_forward_impl(xyz, new_xyz, nullptr, feat, feat_stride, idx, packed, shift1, shift2, shift3, B, N, M, M, 0,
                              S, C, C1, C2, C3, radius, normalize_xyz, stats_layer, 1, out, stats, stream);
@@ -602,7 +602,7 @@ int eda_sa_mlp_forward_range(const float *xyz, const int *centre_idx, const floa
                              Mtot, m0, S, C, C1, C2, C3, radius, normalize_xyz, 0, 0, out, nullptr, stream);
 }
 
-int eda_bn_finalize(const float *stats, double count, const float *gamma, const float *beta, float eps,
+int eda_bn_finalize(const double *stats, double count, const float *gamma, const float *beta, float eps,
                     float momentum, float *running_mean, float *running_var, int update_running, int C,
                     float *scale, float *shift, float *save_mean, float *save_invstd, void *stream) {
   using namespace eda;

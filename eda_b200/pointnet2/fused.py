@@ -131,7 +131,7 @@ def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, tr
             batch_stats = training and bn is not None
             if batch_stats:
                 # train-mode BatchNorm: batch statistics of layer l's conv output, layers < l already final
-                stats = torch.empty(2 * widths[l], dtype=torch.float32, device=dev)
+                stats = torch.empty(2 * widths[l], dtype=torch.float64, device=dev)  # fp64 sums (see csrc/sa_mlp.cu)
                 pack(l + 1)
                 run(l + 1, None, stats)
                 scales[l], shifts[l], mi = _bn_scale_shift(lib, dev, stats, count, bn, conv.bias, widths[l], True,

@@ -136,7 +136,8 @@ EDA_API int eda_three_interpolate_grad(const float *grad_out, const int *idx, co
  *   conv1'(x) + shift1)) + shift2)) + shift3)   (zero-filled by the callee).
  *   stats_layer == l in 1..3: layers < l as above, layer l's conv output is only reduced to
  *   stats[0:C_l] = sum, stats[C_l:2C_l] = sum of squares over all B*M*S rows (zero-filled by the
- *   callee) — the batch statistics train-mode BatchNorm2d needs.
+ *   callee) — the batch statistics train-mode BatchNorm2d needs.  The sums are fp64 (atomicAdd on double): over
+ *   ~1e6 rows, var = E[z^2] - E[z]^2 from fp32 sums loses up to 1e-2 relative when |mean| >> std.
  * eda_bn_finalize: (sum, sumsq, count) + gamma/beta/eps -> scale = gamma/sqrt(var+eps),
  *   shift = beta - mean*scale; optionally updates running_mean/var with `momentum` (unbiased variance),
  *   as nn.BatchNorm2d does in training.  count <= 0: use running_mean/var instead (eval mode).
@@ -149,7 +150,7 @@ EDA_API int eda_sa_mlp_pack(const float *W1, const float *W2, const float *W3, c
 EDA_API int eda_sa_mlp_forward(const float *xyz, const float *new_xyz, const float *feat, int feat_stride,
                                const int *idx, const float *packed, const float *shift1, const float *shift2,
                                const float *shift3, int B, int N, int M, int S, int C, int C1, int C2, int C3,
-                               float radius, int normalize_xyz, int stats_layer, float *out, float *stats,
+                               float radius, int normalize_xyz, int stats_layer, float *out, double *stats,
                                void *stream);
 /* eda_sa_mlp_forward (stats_layer 0) for centres m0 .. m0+mc-1 only, centres given by FPS index; `out`
  * (B,Mtot,C3) must have been zero-filled by the caller (once, before the first range). */
@@ -157,7 +158,7 @@ EDA_API int eda_sa_mlp_forward_range(const float *xyz, const int *centre_idx, co
                                      const int *idx, const float *packed, const float *shift1, const float *shift2,
                                      const float *shift3, int B, int N, int Mtot, int m0, int mc, int S, int C, int C1,
                                      int C2, int C3, float radius, int normalize_xyz, float *out, void *stream);
-EDA_API int eda_bn_finalize(const float *stats, double count, const float *gamma, const float *beta, float eps,
+EDA_API int eda_bn_finalize(const double *stats, double count, const float *gamma, const float *beta, float eps,
                             float momentum, float *running_mean, float *running_var, int update_running, int C,
                             float *scale, float *shift, float *save_mean, float *save_invstd, void *stream);
 EDA_API int eda_transpose_last2(const float *in, int B, int R, int C, float *out, void *stream);
