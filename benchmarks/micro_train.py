@@ -134,7 +134,7 @@ def main():
         loss = loss_of(model(*args))
         loss.backward()
         fg.all_reduce_mean()
-        return loss
+        return loss.detach()  # no reference to the autograd graph survives the step (CUDA-graph capture needs that)
 
     res = {"B_per_gpu": B, "world": world, "N": N, "gpu": torch.cuda.get_device_name(local),
            "trainable_params": sum(p.numel() for p in fg.params), "grad_bytes": fg.nbytes}
@@ -144,6 +144,25 @@ def main():
     res["ours_scenes_per_s"] = B * world / (res["ours_fwd_bwd"]["min_ms"] * 1e-3)
     with torch.no_grad():
         res["ours_fwd_only_train_mode"] = timeit(lambda: model(*args), 2, 5, world)
+    eager_grads = fg.flat.clone()
+    # the same step as ONE CUDA graph (eda_b200/graphs.py GraphedTrainStep); the all-reduce stays outside the graph
+    try:
+        from eda_b200.graphs import GraphedTrainStep
+
+        gstep = GraphedTrainStep(model, loss_of, list(args), fg)
+
+        def graphed():
+            loss = gstep(*args)
+            fg.all_reduce_mean()
+            return loss
+
+        res["graphed_loss"] = graphed().item()
+        res["graphed_vs_eager_grad_rel_diff"] = ((fg.flat - eager_grads).norm() / eager_grads.norm()).item()
+        res["ours_graphed_fwd_bwd"] = timeit(graphed, 3, 10, world)
+        res["ours_graphed_scenes_per_s"] = B * world / (res["ours_graphed_fwd_bwd"]["min_ms"] * 1e-3)
+    except Exception as e:  # noqa: BLE001
+        res["graphed_error"] = repr(e)[:500]
+        step()
 
     if world == 1:
         try:
@@ -161,7 +180,7 @@ def main():
                 fg.zero()
                 loss = loss_of(reference_forward(model, ref_ext, *args))
                 loss.backward()
-                return loss
+                return loss.detach()
 
             res["ref_loss"] = ref_step().item()
             rel = {}
@@ -174,6 +193,8 @@ def main():
             res["ref_fwd_bwd"] = timeit(ref_step, 1, 3, 1)
             res["ref_scenes_per_s"] = B / (res["ref_fwd_bwd"]["min_ms"] * 1e-3)
             res["speedup_fwd_bwd"] = res["ref_fwd_bwd"]["min_ms"] / res["ours_fwd_bwd"]["min_ms"]
+            if "ours_graphed_fwd_bwd" in res:
+                res["speedup_fwd_bwd_graphed"] = res["ref_fwd_bwd"]["min_ms"] / res["ours_graphed_fwd_bwd"]["min_ms"]
     if rank == 0:
         print(json.dumps(res, indent=1))
     if world > 1:

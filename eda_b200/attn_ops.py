@@ -43,6 +43,12 @@ def _require_cuda(t, name="input"):
 # ---------------------------------------------------------------------------------------------------
 # packed weights
 # ---------------------------------------------------------------------------------------------------
+# Packed-weight caches are keyed on the parameter's (data_ptr, _version): right for eager execution, wrong inside a
+# CUDA graph of a TRAINING step (the graph must re-pack after every optimizer step).  graphs.GraphedTrainStep turns
+# the caches off while it warms up and captures, so the pack kernels become part of the graph.
+PACK_CACHE = True
+
+
 def _cache_of(owner):
     """The packed-weight cache lives ON the owning module, so it dies with it (a process-wide dict keyed by
     id() / data_ptr() could hand a new module the packed weights of a dead one whose memory it reuses)."""
@@ -60,7 +66,7 @@ def pack_weight(W, scale=None, cache_key=None):
     lib = _lib.load()
     N, K = W.shape
     cache = None
-    if cache_key is not None and scale is None:
+    if cache_key is not None and scale is None and PACK_CACHE:
         cache = _cache_of(cache_key[0])
         tag = (W.data_ptr(), W._version, N, K, W.device)
         hit = cache.get(cache_key[1])
@@ -187,7 +193,7 @@ def pack_weight_t(W, cache_key=None):
     Nout, Kin = W.shape
     assert W.stride(1) == 1
     cache = None
-    if cache_key is not None:
+    if cache_key is not None and PACK_CACHE:
         cache = _cache_of(cache_key[0])
         tag = (W.data_ptr(), W._version, Nout, Kin, W.stride(0), W.device)
         hit = cache.get(cache_key[1])

@@ -47,3 +47,70 @@ class GraphedCallable:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.static_outputs
+
+
+class GraphedTrainStep:
+    """One training step (zero grads -> forward -> loss -> backward) recorded as ONE CUDA graph.
+
+        fg = ddp.FlatGradients(model)
+        step = GraphedTrainStep(model, loss_fn, example_inputs, fg)
+        loss = step(*inputs)          # cudaGraphLaunch; gradients are in fg.flat (views: param.grad)
+        fg.all_reduce_mean(); optimizer.step()
+
+    Eagerly the step is ~900 kernel launches of 5-50 us each issued from Python through ctypes / autograd and is bound
+    by that host work; replayed, only the device time remains.  The weight-pack kernels are captured too (the
+    packed-weight caches are switched off during warm-up and capture), so replays after an optimizer step use the
+    updated parameters; BatchNorm running statistics and `num_batches_tracked` are updated by captured device ops.
+    Restrictions: fixed shapes; parameters, gradients (FlatGradients) and inputs must stay at their addresses; dropout
+    seeds are drawn on the host at capture time, so a graph recorded with dropout p > 0 would repeat the same masks
+    every replay — the constructor refuses that configuration."""
+
+    def __init__(self, model, loss_fn, example_inputs, flat_grads, warmup=3):
+        from . import attn_ops
+
+        if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
+            raise RuntimeError("GraphedTrainStep needs CUDA tensor inputs")
+        for m in model.modules():
+            p = getattr(m, "p", None) if isinstance(m, torch.nn.Dropout) else getattr(m, "dropout", None) \
+                if isinstance(m, torch.nn.MultiheadAttention) else None
+            if m.training and isinstance(p, float) and p > 0:
+                raise RuntimeError("GraphedTrainStep: dropout > 0 in training mode cannot be captured "
+                                   "(host-side seeds would be frozen into the graph)")
+        if not flat_grads.check_views():
+            raise RuntimeError("GraphedTrainStep: param.grad must alias the FlatGradients buffer")
+        self.device = example_inputs[0].device
+        self.static_inputs = [t.clone() for t in example_inputs]
+        self.flat_grads = flat_grads
+
+        def step():
+            flat_grads.zero()
+            loss = loss_fn(model(*self.static_inputs))
+            loss.backward()
+            return loss.detach()
+
+        saved = attn_ops.PACK_CACHE
+        attn_ops.PACK_CACHE = False
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    step()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = step()
+        finally:
+            attn_ops.PACK_CACHE = saved
+
+    def __call__(self, *inputs):
+        if len(inputs) != len(self.static_inputs):
+            raise RuntimeError("GraphedTrainStep: wrong number of inputs")
+        for dst, src in zip(self.static_inputs, inputs):
+            if dst.shape != src.shape or dst.dtype != src.dtype:
+                raise RuntimeError("GraphedTrainStep: input shape/dtype differs from the captured one")
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

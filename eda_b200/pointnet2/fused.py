@@ -387,7 +387,8 @@ def eval_packed(module, layers, C, widths, dev):
         if bn is not None:
             tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
     key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (C, str(dev))
-    hit = module.__dict__.get("_eda_sa_eval_cache")
+    from .. import attn_ops
+    hit = module.__dict__.get("_eda_sa_eval_cache") if attn_ops.PACK_CACHE else None
     if hit is not None and hit[0] == key:
         return hit[1], hit[2]
     nfl = lib.eda_sa_mlp_packed_floats(C, *widths)
