@@ -63,7 +63,7 @@ def main():
             loss = mt.loss_of(model(*args))
         with record_function("bwd"):
             loss.backward()
-        return loss
+        return loss.detach()
 
     for _ in range(3):
         step()
@@ -77,6 +77,7 @@ def main():
     loss.backward()
     ev[2].record()
     torch.cuda.synchronize()
+    del loss
     res = {"fwd_ms": ev[0].elapsed_time(ev[1]), "bwd_ms": ev[1].elapsed_time(ev[2])}
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
@@ -99,6 +100,33 @@ def main():
                                       if getattr(e, "device_type", None) == DeviceType.CUDA) / 1000.0
     res["ranges"] = ranges
     res["top_self_device"] = kernels
+    # ---- the same step as one CUDA graph: per-kernel device time of a replay (no host gaps) ----
+    try:
+        from eda_b200.graphs import GraphedTrainStep
+
+        gstep = GraphedTrainStep(model, mt.loss_of, list(args), fg)
+        for _ in range(3):
+            gstep(*args)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gstep(*args)
+        e1.record()
+        torch.cuda.synchronize()
+        res["graphed_ms"] = e0.elapsed_time(e1)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof2:
+            gstep(*args)
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof2.events():
+            if ev.device_type == DeviceType.CUDA:
+                a = agg.setdefault(ev.name[:90], [0, 0.0])
+                a[0] += 1
+                a[1] += ev.device_time
+        res["graphed_kernel_sum_ms"] = sum(v[1] for v in agg.values()) / 1000.0
+        res["graphed_kernels"] = sorted(([k, v[0], round(v[1] / 1000.0, 3)] for k, v in agg.items()), key=lambda r_: -r_[2])[:40]
+    except Exception as e:  # noqa: BLE001
+        res["graphed_error"] = repr(e)[:400]
     print(json.dumps(res, indent=1))
     if out_path:
         with open(out_path, "w") as f:

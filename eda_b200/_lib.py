@@ -60,6 +60,8 @@ PROTOTYPES = {
     "eda_layernorm_backward": (_c_int, [_vp, _vp, _vp, _c_float, ctypes.c_longlong, _c_int, _vp, _vp, _vp, _vp, _c_float,
                                         ctypes.c_uint, _vp]),
     "eda_relu_backward": (_c_int, [_vp, _vp, _c_float, ctypes.c_longlong, _vp, _vp]),
+    "eda_rows_gemm": (_c_int, [_vp, _c_int, _vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _c_int,
+                               _c_int, _vp, _c_int, _vp]),
     "eda_sa_gather_rows": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                                     _c_int, _vp, _vp]),
     "eda_bn_relu_apply": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _c_int, _vp, _vp]),
@@ -85,7 +87,7 @@ class LinearProblem(ctypes.Structure):
 class WgradProblem(ctypes.Structure):
     """struct eda_wgrad_problem (include/eda_b200.h)."""
     _fields_ = [("dy", _vp), ("x", _vp), ("dw", _vp), ("db", _vp), ("rows", ctypes.c_longlong),
-                ("ldy", _c_int), ("ldx", _c_int), ("ldw", _c_int)]
+                ("ldy", _c_int), ("ldx", _c_int), ("ldw", _c_int), ("x_scale", _vp), ("x_shift", _vp)]
 
 
 _lib = None

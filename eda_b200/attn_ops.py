@@ -212,7 +212,8 @@ def pack_weight_t(W, cache_key=None):
 
 
 def wgrad(problems, N, K):
-    """problems: list (<= 6) of dicts dy (R,N), x (R,K), dw (N,K) view [row stride = dw.stride(0)], db (N) or None.
+    """problems: list (<= 6) of dicts dy (R,N), x (R,K), dw (N,K) view [row stride = dw.stride(0)], db (N) or None,
+    optional x_scale / x_shift (K): x is consumed as relu(x * x_scale + x_shift).
     dw += dy^T x, db += column sums of dy (accumulating: the caller zero-initialises)."""
     lib = _lib.load()
     dev = problems[0]["dy"].device
@@ -226,7 +227,10 @@ def wgrad(problems, N, K):
         arr[i].dy, arr[i].x, arr[i].dw = dy.data_ptr(), x.data_ptr(), dw.data_ptr()
         arr[i].db = db.data_ptr() if db is not None else None
         arr[i].rows, arr[i].ldy, arr[i].ldx, arr[i].ldw = R, N, K, dw.stride(0)
-        keep.append((dy, x, dw, db))
+        xs, xh = pr.get("x_scale"), pr.get("x_shift")
+        arr[i].x_scale = xs.data_ptr() if xs is not None else None
+        arr[i].x_shift = xh.data_ptr() if xh is not None else None
+        keep.append((dy, x, dw, db, xs, xh))
     with torch.cuda.device(dev):
         rc = lib.eda_wgrad(ctypes.cast(arr, ctypes.c_void_p), len(problems), N, K, _stream(dev))
     _lib.check(rc, "wgrad")
@@ -247,6 +251,25 @@ def layernorm_backward(dy, u, gamma, eps, dgamma, dbeta, dropout=None):
                                         _stream(u.device))
     _lib.check(rc, "layernorm_backward")
     return du, dproj
+
+
+def rows_gemm(x, W, transpose=False, in_scale=None, in_shift=None):
+    """y = f(x) W^T (transpose=False, W (N,K)) or f(x) W (transpose=True, W (K,N): the activation gradient of a layer
+    y = a W^T), f = relu(x * in_scale + in_shift) when given.  x (R,K) contiguous; W any 2-D strided view."""
+    lib = _lib.load()
+    R, K = x.shape
+    if transpose:
+        assert W.size(0) == K
+        N, sn, sk = W.size(1), W.stride(1), W.stride(0)
+    else:
+        assert W.size(1) == K
+        N, sn, sk = W.size(0), W.stride(0), W.stride(1)
+    y = torch.empty((R, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.eda_rows_gemm(_p(x), K, _p(in_scale), _p(in_shift), _p(W), int(sn), int(sk), R, K, N, _p(y), N,
+                               _stream(x.device))
+    _lib.check(rc, "rows_gemm")
+    return y
 
 
 def relu_backward(dy, y, scale=1.0):

@@ -53,6 +53,7 @@ constexpr int kWgThreads = 128;
 
 struct WgProblem {
   const float *dy, *x;
+  const float *x_scale, *x_shift;  // optional: x is consumed as relu(x * x_scale[k] + x_shift[k])
   float *dw, *db;
   long long rows;
   int ldy, ldx, ldw;
@@ -103,6 +104,15 @@ wgrad_kernel(const WgParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
   float bsum = 0.f;
+  // optional prologue on X (folded BatchNorm + ReLU of the producing layer), per column of this thread's B fragments
+  const bool pro = pr.x_scale != nullptr;
+  float xs[4], xh[4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int k = k0 + wn + nt * 8 + g;
+    xs[nt] = (pro && k < p.K) ? __ldg(pr.x_scale + k) : 1.f;
+    xh[nt] = (pro && k < p.K) ? __ldg(pr.x_shift + k) : 0.f;
+  }
 
   issue(c_lo, 0);
   for (long long c = c_lo; c < c_hi; ++c) {
@@ -130,8 +140,13 @@ wgrad_kernel(const WgParams p) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int n = wn + nt * 8 + g;
-        b[nt][0] = f2tf32(x0[n]);
-        b[nt][1] = f2tf32(x1[n]);
+        float v0 = x0[n], v1 = x1[n];
+        if (pro) {
+          v0 = fmaxf(fmaf(v0, xs[nt], xh[nt]), 0.f);
+          v1 = fmaxf(fmaf(v1, xs[nt], xh[nt]), 0.f);
+        }
+        b[nt][0] = f2tf32(v0);
+        b[nt][1] = f2tf32(v1);
       }
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -304,6 +319,8 @@ int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *st
     if (q.ldy < N || q.ldx < K || q.ldw < K || (q.ldy & 3) || (q.ldx & 3) || !aligned16(q.dy) || !aligned16(q.x))
       return EDA_ERR_INVALID_ARGUMENT;
     p.pr[i].dy = q.dy; p.pr[i].x = q.x; p.pr[i].dw = q.dw; p.pr[i].db = q.db; p.pr[i].rows = q.rows;
+    p.pr[i].x_scale = q.x_scale; p.pr[i].x_shift = q.x_shift;
+    if ((q.x_scale == nullptr) != (q.x_shift == nullptr)) return EDA_ERR_INVALID_ARGUMENT;
     p.pr[i].ldy = q.ldy; p.pr[i].ldx = q.ldx; p.pr[i].ldw = q.ldw;
     if (q.rows > max_rows) max_rows = q.rows;
   }

@@ -1,0 +1,182 @@
+// Row-streaming GEMM for the set-abstraction backward pass (sm_100a):
+//
+//     Y[R x N] = f(X)[R x K] W'[N x K]^T,   f(x) = x   or   relu(x * in_scale[k] + in_shift[k])
+//
+// R is 10^5 - 10^6 grouped points, K and N are the MLP widths (16 ... 272): every operand row is touched once, so
+// the kernel is bound by HBM (4 (K + N) bytes per row), not by the tensor pipe, and what matters is that rows stream
+// at full bandwidth: persistent CTAs (one per SM), the weight slice (<= 128 output channels) converted to tf32 once
+// into shared memory, X tiles of 128 rows x 32 channels in a 3-stage cp.async ring that runs across tile
+// boundaries, warp-level mma.sync.m16n8k8 tf32 with fp32 accumulators (warp = 16 rows x up to 128 columns), results
+// written as full 32-byte sectors.  The optional prologue f applies the previous layer's folded BatchNorm + ReLU while
+// the A fragments are formed, so the post-activation tensor never exists in HBM; W' is addressed through two strides,
+// so W^T (activation gradients, dX = dY W) needs no transposed copy.
+#include "common.cuh"
+
+namespace eda {
+namespace {
+
+constexpr int kRgRows = 128, kRgThreads = 256, kRgKc = 32, kRgPx = kRgKc + 4, kRgStages = 3, kRgNc = 128;
+constexpr int kRgMaxK = 288;
+
+struct RowsGemmParams {
+  const float *x, *in_scale, *in_shift, *w;
+  float *y;
+  long long rows, w_sn, w_sk;
+  int ldx, ldy, K, N, ntiles;
+};
+
+__device__ __forceinline__ uint32_t rg_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void rg_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void rg_cp16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+
+template <bool kPrologue>
+__global__ void __launch_bounds__(kRgThreads, 1)
+rows_gemm_kernel(const RowsGemmParams p) {
+  extern __shared__ __align__(16) unsigned char rg_smem[];
+  const int K = p.K, PW = K + 4;  // (g * PW + t) % 32 = 4 g + t: conflict-free B fragments (K % 8 == 0)
+  const int n0 = blockIdx.y * kRgNc;
+  const int Nc = min(kRgNc, p.N - n0);         // multiple of 8
+  uint32_t *sW = reinterpret_cast<uint32_t *>(rg_smem);                    // [Nc][PW] tf32
+  float *sX = reinterpret_cast<float *>(sW + (size_t)kRgNc * PW);          // [stages][128][36]
+  float *sSc = sX + kRgStages * kRgRows * kRgPx;                            // [K] in_scale, [K] in_shift
+  float *sSh = sSc + kRgMaxK;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  const int nkc = (K + kRgKc - 1) / kRgKc;
+  const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long total = (long long)my_tiles * nkc;  // (tile, k-chunk) items of this CTA, in order
+
+  auto issue = [&](long long item) {
+    if (item < total) {
+      const int ti = (int)(item / nkc), kc = (int)(item - (long long)ti * nkc);
+      const long long row0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * kRgRows;
+      float *dst = sX + (size_t)(item % kRgStages) * kRgRows * kRgPx;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int id = i * kRgThreads + tid;
+        const int r = id >> 3, c4 = (id & 7) << 2;
+        const long long row = row0 + r;
+        const int k = kc * kRgKc + c4;
+        const bool in = row < p.rows && k < K;
+        rg_cp16(dst + r * kRgPx + c4, in ? p.x + row * p.ldx + k : p.x, in ? 16u : 0u);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  issue(1);
+
+  // weights of this column slice -> shared memory (tf32), prologue vectors
+  for (int i = tid; i < Nc * K; i += kRgThreads) {
+    const int n = i / K, k = i - n * K;
+    sW[n * PW + k] = rg_tf32(__ldg(p.w + (n0 + n) * p.w_sn + k * p.w_sk));
+  }
+  if (kPrologue)
+    for (int i = tid; i < K; i += kRgThreads) {
+      sSc[i] = __ldg(p.in_scale + i);
+      sSh[i] = __ldg(p.in_shift + i);
+    }
+
+  constexpr int kMaxNT = kRgNc / 8;
+  const int nnt = Nc >> 3;
+  float acc[kMaxNT][4];
+  const int r0 = warp * 16;
+  for (long long item = 0; item < total; ++item) {
+    const int ti = (int)(item / nkc), kc = (int)(item - (long long)ti * nkc);
+    issue(item + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncthreads();  // chunk `item` has landed for every thread (first iteration: also the weights)
+    if (kc == 0) {
+#pragma unroll
+      for (int j = 0; j < kMaxNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    }
+    const float *xs = sX + (size_t)(item % kRgStages) * kRgRows * kRgPx;
+    const int kcnt = min(kRgKc, K - kc * kRgKc);
+    for (int ks = 0; ks < kcnt / 8; ++ks) {
+      const int kl = ks * 8 + t, kg = kc * kRgKc + kl;
+      float a0 = xs[(r0 + g) * kRgPx + kl], a1 = xs[(r0 + g + 8) * kRgPx + kl];
+      float a2 = xs[(r0 + g) * kRgPx + kl + 4], a3 = xs[(r0 + g + 8) * kRgPx + kl + 4];
+      if (kPrologue) {
+        const float s0 = sSc[kg], h0 = sSh[kg], s1 = sSc[kg + 4], h1 = sSh[kg + 4];
+        a0 = fmaxf(fmaf(a0, s0, h0), 0.f); a1 = fmaxf(fmaf(a1, s0, h0), 0.f);
+        a2 = fmaxf(fmaf(a2, s1, h1), 0.f); a3 = fmaxf(fmaf(a3, s1, h1), 0.f);
+      }
+      const uint32_t a[4] = {rg_tf32(a0), rg_tf32(a1), rg_tf32(a2), rg_tf32(a3)};
+      const uint32_t *wr = sW + g * PW + kg;
+#pragma unroll
+      for (int j = 0; j < kMaxNT; ++j)
+        if (j < nnt) rg_mma(acc[j], a, wr[j * 8 * PW], wr[j * 8 * PW + 4]);
+    }
+    if (kc == nkc - 1) {
+      const long long row0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * kRgRows;
+      const long long ra = row0 + r0 + g, rb = ra + 8;
+#pragma unroll
+      for (int j = 0; j < kMaxNT; ++j) {
+        if (j < nnt) {
+          const int n = n0 + j * 8 + 2 * t;
+          if (ra < p.rows) *reinterpret_cast<float2 *>(p.y + ra * p.ldy + n) = make_float2(acc[j][0], acc[j][1]);
+          if (rb < p.rows) *reinterpret_cast<float2 *>(p.y + rb * p.ldy + n) = make_float2(acc[j][2], acc[j][3]);
+        }
+      }
+    }
+    __syncthreads();  // the stage read here is refilled by the next iteration's prefetch
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+}  // namespace
+}  // namespace eda
+
+extern "C" int eda_rows_gemm(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
+                             long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y, int ldy,
+                             void *stream) {
+  using namespace eda;
+  if (rows < 0 || K < 8 || N < 8) return EDA_ERR_INVALID_ARGUMENT;
+  if ((K & 7) || (N & 7) || K > kRgMaxK) return EDA_ERR_UNSUPPORTED;
+  if (rows == 0) return EDA_OK;
+  if (!x || !w || !y || ldx < K || ldy < N || (ldx & 3) || (ldy & 1) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(y) & 7) || ((in_scale == nullptr) != (in_shift == nullptr)))
+    return EDA_ERR_INVALID_ARGUMENT;
+  const long long ntiles = (rows + kRgRows - 1) / kRgRows;
+  if (ntiles > 0x7fffffffLL) return EDA_ERR_UNSUPPORTED;
+  RowsGemmParams p = {};
+  p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.y = y; p.rows = rows; p.w_sn = w_stride_n;
+  p.w_sk = w_stride_k; p.ldx = ldx; p.ldy = ldy; p.K = K; p.N = N; p.ntiles = (int)ntiles;
+  const size_t smem = (size_t)kRgNc * (K + 4) * 4 + (size_t)kRgStages * kRgRows * kRgPx * 4 + 2 * kRgMaxK * 4;
+  static size_t smem_set[2] = {0, 0};
+  const int which = in_scale ? 1 : 0;
+  if (smem > smem_set[which]) {
+    if (which)
+      EDA_CUDA_TRY(cudaFuncSetAttribute(rows_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "rows_gemm smem attr");
+    else
+      EDA_CUDA_TRY(cudaFuncSetAttribute(rows_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "rows_gemm smem attr");
+    smem_set[which] = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ny = (N + kRgNc - 1) / kRgNc;
+  long long gx = sms / ny;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  dim3 grid((unsigned)gx, (unsigned)ny);
+  if (which)
+    rows_gemm_kernel<true><<<grid, kRgThreads, smem, as_stream(stream)>>>(p);
+  else
+    rows_gemm_kernel<false><<<grid, kRgThreads, smem, as_stream(stream)>>>(p);
+  return check_launch("rows_gemm_kernel");
+}

@@ -123,6 +123,7 @@ sa_mlp_kernel(const SaParams p) {
   float *s_shift = reinterpret_cast<float *>(smem_raw + kRing * kSlotBytes);  // [3][kMaxC]
   __shared__ __align__(8) uint64_t full_bar[kRing], empty_bar[kRing], mma_done;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_stat[4][2][kMaxC];  // per compute warp: this CTA's partial (sum, sum of squares) of the statistics pass
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nlayers_run = p.stats_layer == 0 ? 3 : p.stats_layer;
@@ -141,6 +142,7 @@ sa_mlp_kernel(const SaParams p) {
     const int l = i / kMaxC, c = i % kMaxC;
     s_shift[i] = (p.shift[l] != nullptr && c < p.Cout[l]) ? __ldg(p.shift[l] + c) : 0.f;
   }
+  for (int i = tid; i < 4 * 2 * kMaxC; i += kThreads) (&s_stat[0][0][0])[i] = 0.f;
   umma::fence_before_thread_sync();
   __syncthreads();
   umma::fence_after_thread_sync();
@@ -236,7 +238,11 @@ sa_mlp_kernel(const SaParams p) {
       umma::tmem_st_wait();
     };
     // per-channel sum / sum of squares of the raw conv output over this tile's valid rows
-    auto take_stats = [&](uint32_t taddr, int ncols, double *sum, double *sumsq, bool valid) {
+    // (fp32 partials per warp in shared memory, single writer per slot, summed in a fixed order — a CTA sees a few
+    // thousand rows — then ONE fp64 atomic per channel and CTA at the end: per-tile atomics on the same 2 C addresses
+    // serialise in L2, and fp32 atomics in arbitrary order make the statistics differ from run to run by ~1e-7, which
+    // tf32 rounding of the activations amplifies to ~1e-3 on single outputs)
+    auto take_stats = [&](uint32_t taddr, int ncols, float *sum, float *sumsq, bool valid) {
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t u[16];
         umma::tmem_ld16(taddr + (uint32_t)c0, u);
@@ -253,8 +259,8 @@ sa_mlp_kernel(const SaParams p) {
         const float a = s1[0] + __shfl_xor_sync(kFull, s1[0], 16);
         const float q = s2[0] + __shfl_xor_sync(kFull, s2[0], 16);
         if (lane < 16) {
-          atomicAdd(sum + c0 + lane, (double)a);
-          atomicAdd(sumsq + c0 + lane, (double)q);
+          sum[c0 + lane] += a;
+          sumsq[c0 + lane] += q;
         }
       }
     };
@@ -325,7 +331,7 @@ sa_mlp_kernel(const SaParams p) {
       wait_mma_done();
 
       if (p.stats_layer == 1) {
-        take_stats(t_r1, p.Cout[0], p.stats, p.stats + p.Cout[0], valid);
+        take_stats(t_r1, p.Cout[0], s_stat[warp][0], s_stat[warp][1], valid);
       } else {
         // ================= layer 2: A1 = relu(D1 + shift1) in region 1, D2 -> region 2 ===========
         relu_inplace(t_r1, p.Cout[0], s_shift);
@@ -333,7 +339,7 @@ sa_mlp_kernel(const SaParams p) {
         if (tid == 0) issue_blocks(128u, 0u, 0, p.Cout[0], p.Cout[1], true);
         wait_mma_done();
         if (p.stats_layer == 2) {
-          take_stats(t_r2, p.Cout[1], p.stats, p.stats + p.Cout[1], valid);
+          take_stats(t_r2, p.Cout[1], s_stat[warp][0], s_stat[warp][1], valid);
         } else {
           // ================= layer 3: A2 in region 2, D3 halves -> region 1 ======================
           relu_inplace(t_r2, p.Cout[1], s_shift + kMaxC);
@@ -345,7 +351,7 @@ sa_mlp_kernel(const SaParams p) {
             if (tid == 0) issue_blocks(0u, 128u, 0, p.Cout[1], nblk, true);
             wait_mma_done();
             if (p.stats_layer == 3) {
-              take_stats(t_r1, nblk, p.stats + h * 128, p.stats + C3 + h * 128, valid);
+              take_stats(t_r1, nblk, s_stat[warp][0] + h * 128, s_stat[warp][1] + h * 128, valid);
             } else {
               // shift, max over the S rows of each centre, ReLU via integer max against the zeroed output.
               // S >= 16 and a power of two: a centre's rows are one aligned 16-lane segment, one
@@ -377,6 +383,14 @@ sa_mlp_kernel(const SaParams p) {
       }
       // every TMEM read of this tile is done before the next tile's stores / MMAs overwrite it
       phase_sync();
+    }
+    if (p.stats_layer > 0) {
+      named_bar_sync_compute();  // all shared-memory partials are in
+      const int Cl = p.Cout[p.stats_layer - 1];
+      for (int c = tid; c < Cl; c += kComputeThreads) {
+        atomicAdd(p.stats + c, ((double)s_stat[0][0][c] + (double)s_stat[1][0][c]) + ((double)s_stat[2][0][c] + (double)s_stat[3][0][c]));
+        atomicAdd(p.stats + Cl + c, ((double)s_stat[0][1][c] + (double)s_stat[1][1][c]) + ((double)s_stat[2][1][c] + (double)s_stat[3][1][c]));
+      }
     }
   }
 

@@ -213,11 +213,12 @@ class FusedSAFunction(torch.autograd.Function):
 
 
 def _sa_backward_cuda(ctx, grad_out):
-    """Backward of one fused SA stage on the CUDA kernels.  Per layer l (rows R = B*M*S, row-major activations):
-         recompute   x0 = gather, z_l = a_{l-1} W_l^T (tcgen05 GEMM), a_l = relu(z_l scale_l + shift_l)
+    """Backward of one fused SA stage on the CUDA kernels.  Rows R = B*M*S, row-major pre-activations z_l (R, C_l):
+         recompute   x0 = gather;  z_l = relu(bn(z_{l-1})) W_l^T  — eda_rows_gemm, the previous layer's folded BatchNorm +
+                     ReLU applied as its prologue, so the post-activation tensors never exist in HBM
          layer 3     arg-max over the S rows of a centre + ReLU gate -> dy3 (one row per centre and channel)
          BatchNorm   dz_l = scale_l (dy_l - mean(dy_l) - zhat_l mean(dy_l zhat_l)); d beta = sum dy, d gamma = sum dy zhat
-         GEMMs       dW_l = dz_l^T a_{l-1} (eda_wgrad), da_{l-1} = dz_l W_l (tcgen05 GEMM, transposed packed weight)
+         GEMMs       dW_l = dz_l^T relu(bn(z_{l-1})) (eda_wgrad, same prologue), da_{l-1} = dz_l W_l (eda_rows_gemm, W^T by strides)
          features    d features[idx] += dx0[:, :C]"""
     from .. import attn_ops as ops
 
@@ -242,10 +243,6 @@ def _sa_backward_cuda(ctx, grad_out):
     def chk(rc, what):
         _lib.check(rc, what)
 
-    def gemm(x, w_packed, K, Nout):
-        (y,) = ops.linear_raw([dict(x=x, w_packed=w_packed)], K, Nout)
-        return y
-
     with torch.cuda.device(dev):
         # ---- recompute the forward, row-major ----------------------------------------------------------------
         x0 = torch.empty((R, K0pad), **f32)
@@ -255,20 +252,20 @@ def _sa_backward_cuda(ctx, grad_out):
         W1p = torch.zeros((widths[0], K0pad), **f32)
         W1p[:, :C] = Ws[0][:, 3:]
         W1p[:, C:C + 3] = Ws[0][:, :3]
-        Wl = [W1p, Ws[1].contiguous(), Ws[2].contiguous()]
+        Wl = [W1p, Ws[1], Ws[2]]
         Kin = [K0pad, widths[0], widths[1]]
-        z, a = [None] * 3, [x0, None, None]
+        # input of layer l as (tensor, scale, shift): layer 1 reads x0 as it is, layers 2 / 3 read relu(bn(z_{l-1}))
+        z = [None] * 3
+        src = [(x0, None, None)]
         for l in range(3):
-            z[l] = gemm(a[l], ops.pack_weight(Wl[l]), Kin[l], widths[l])
+            xin, sc, sh = src[l]
+            z[l] = ops.rows_gemm(xin, Wl[l], in_scale=sc, in_shift=sh)
             if l < 2:
-                scale, shift, _ = ctx.state[l]
-                a[l + 1] = torch.empty_like(z[l])
-                chk(lib.eda_bn_relu_apply(_p(z[l]), _p(scale), _p(shift), R, widths[l], _p(a[l + 1]), stream),
-                    "bn_relu_apply")
+                src.append((z[l], ctx.state[l][0], ctx.state[l][1]))
         # ---- layer 3: max-pool + ReLU + BatchNorm backward -----------------------------------------------------
         g_pm = transpose_last2(grad_out.contiguous())  # (B, M, C3)
         stats = [torch.zeros(2 * widths[l], **f32) for l in range(3)]
-        dWl = [torch.zeros_like(Wl[l]) for l in range(3)]
+        dWl = [torch.zeros((widths[l], Kin[l]), **f32) for l in range(3)]
         scale, shift, mi = ctx.state[2]
         amax = torch.empty((B * M, widths[2]), dtype=torch.int32, device=dev)
         chk(lib.eda_sa_pool_backward(_p(z[2]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), _p(g_pm), B * M, S, widths[2],
@@ -277,11 +274,13 @@ def _sa_backward_cuda(ctx, grad_out):
                                            float(R), 1 if training else 0, B * M, S, widths[2], stream),
             "sa_pool_backward_apply")
         dz = z[2]  # overwritten in place
+        z[2] = None
         for l in (2, 1, 0):
-            ops.wgrad([dict(dy=dz, x=a[l], dw=dWl[l])], widths[l], Kin[l])
+            xin, sc, sh = src[l]
+            ops.wgrad([dict(dy=dz, x=xin, dw=dWl[l], x_scale=sc, x_shift=sh)], widths[l], Kin[l])
             if l == 0:
                 break
-            da = gemm(dz, ops.pack_weight_t(Wl[l]), widths[l], Kin[l])
+            da = ops.rows_gemm(dz, Wl[l], transpose=True)
             scale, shift, mi = ctx.state[l - 1]
             chk(lib.eda_bn_relu_backward_stats(_p(da), _p(z[l - 1]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), R,
                                                widths[l - 1], _p(stats[l - 1]), stream), "bn_relu_backward_stats")
@@ -289,10 +288,9 @@ def _sa_backward_cuda(ctx, grad_out):
                                                _p(stats[l - 1]), float(R), 1 if training else 0, R, widths[l - 1], stream),
                 "bn_relu_backward_apply")
             dz = da
-            z[l] = a[l] = None  # release
         gf = None
         if features is not None and ctx.needs_input_grad[3]:
-            dx0 = gemm(dz, ops.pack_weight_t(W1p), widths[0], K0pad)
+            dx0 = ops.rows_gemm(dz, W1p, transpose=True)
             dfeat_pm = torch.zeros((B, N, C), **f32)
             chk(lib.eda_sa_scatter_rows(_p(dx0), _p(idx), B, N, M, S, C, K0pad, _p(dfeat_pm), stream), "sa_scatter_rows")
             gf = transpose_last2(dfeat_pm)

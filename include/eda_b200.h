@@ -250,6 +250,8 @@ typedef struct eda_wgrad_problem {
   float *db;       /* (N) accumulated, or NULL */
   long long rows;
   int ldy, ldx, ldw;
+  const float *x_scale; /* optional (K): x is consumed as relu(x * x_scale[k] + x_shift[k]) — the folded   */
+  const float *x_shift; /* BatchNorm + ReLU of the layer that produced it (both NULL: x as it is)          */
 } eda_wgrad_problem;
 EDA_API int eda_attention_backward(const float *q, const float *k, const float *v, long long v_batch_stride,
                                    const float *dctx, const float *ctx, const float *lse,
@@ -291,6 +293,13 @@ EDA_API int eda_dropout_mask(unsigned int seed, float p, long long rows, int col
  *   eda_bn_relu_backward_stats  stats of dy = da * [z * scale + shift > 0]
  *   eda_bn_relu_backward_apply  da <- dz = scale (dy - mean(dy) - zhat mean(dy zhat))
  *   eda_sa_scatter_rows         dfeat (B, N, C) point-major += dx0[:, :C] scattered by idx (red.global.add) */
+/* eda_rows_gemm: y (rows, N; row stride ldy) = f(x) (rows, K; ldx) W'^T with W'[n][k] = w[n * w_stride_n + k * w_stride_k]
+ * (so a row-major (N, K) weight is (K, 1), and its use as dX = dY W is (1, ld)) and f(x) = x, or
+ * relu(x * in_scale[k] + in_shift[k]) when in_scale / in_shift are given.  K, N multiples of 8, K <= 288; tf32 operands,
+ * fp32 accumulation.  Persistent row-streaming kernel for the 10^5 - 10^6-row GEMMs of the SA backward pass. */
+EDA_API int eda_rows_gemm(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
+                          long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y, int ldy,
+                          void *stream);
 EDA_API int eda_sa_gather_rows(const float *xyz, const float *new_xyz, const float *feat, int feat_stride,
                                const int *idx, int B, int N, int M, int S, int C, int K0pad, float radius,
                                int normalize_xyz, float *x0, void *stream);

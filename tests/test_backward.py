@@ -385,3 +385,37 @@ def test_sa_pool_bn_relu_backward_kernels(training, S, C):
     a = torch.empty_like(z)
     assert lib.eda_bn_relu_apply(_vp(z), _vp(scale), _vp(shift), R, C, _vp(a), _stream()) == 0
     torch.testing.assert_close(a, torch.relu(z * scale + shift), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("R,K,N,prologue,transpose", [(1000, 16, 64, False, False), (70000, 64, 64, True, False),
+                                                      (5000, 144, 128, False, False), (3000, 128, 256, True, False),
+                                                      (129, 272, 128, False, False), (4000, 256, 128, False, True),
+                                                      (2000, 128, 272, False, True), (1, 64, 8, True, False)])
+def test_rows_gemm_kernel(R, K, N, prologue, transpose):
+    from eda_b200 import attn_ops as ops
+
+    g = torch.Generator().manual_seed(R + K + N)
+    x = torch.randn(R, K, generator=g).cuda()
+    W = (torch.randn(K, N, generator=g) if transpose else torch.randn(N, K, generator=g)).cuda() / math.sqrt(K)
+    sc = (1 + 0.3 * torch.randn(K, generator=g)).cuda() if prologue else None
+    sh = (0.2 * torch.randn(K, generator=g)).cuda() if prologue else None
+    y = ops.rows_gemm(x, W, transpose=transpose, in_scale=sc, in_shift=sh)
+    xd = x.double()
+    if prologue:
+        xd = torch.relu(xd * sc.double() + sh.double())
+    ref = xd @ (W.double() if transpose else W.double().t())
+    assert y.shape == ref.shape and rel(y, ref) <= 2e-3
+    torch.testing.assert_close(y.double(), ref, rtol=2e-3, atol=5e-3)
+
+
+def test_wgrad_kernel_with_bn_relu_prologue():
+    from eda_b200 import attn_ops as ops
+
+    g = torch.Generator().manual_seed(5)
+    R, N, K = 30000, 128, 64
+    dy, x = torch.randn(R, N, generator=g).cuda(), torch.randn(R, K, generator=g).cuda()
+    sc, sh = (1 + 0.3 * torch.randn(K, generator=g)).cuda(), (0.2 * torch.randn(K, generator=g)).cuda()
+    dw = torch.zeros(N, K, device="cuda")
+    ops.wgrad([dict(dy=dy, x=x, dw=dw, x_scale=sc, x_shift=sh)], N, K)
+    ref = dy.double().t() @ torch.relu(x.double() * sc.double() + sh.double())
+    assert rel(dw, ref) <= 5e-3
