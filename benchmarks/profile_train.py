@@ -63,6 +63,7 @@ def main():
             loss = mt.loss_of(model(*args))
         with record_function("bwd"):
             loss.backward()
+            fg.sync()
         return loss.detach()
 
     for _ in range(3):
@@ -75,6 +76,7 @@ def main():
     loss = mt.loss_of(model(*args))
     ev[1].record()
     loss.backward()
+    fg.sync()
     ev[2].record()
     torch.cuda.synchronize()
     del loss

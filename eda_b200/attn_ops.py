@@ -211,6 +211,52 @@ def pack_weight_t(W, cache_key=None):
     return packed
 
 
+# Fused gradient accumulation (opt-in, switched on by ddp.FlatGradients): when a parameter already owns a gradient
+# buffer (param.grad, e.g. a view of the flat all-reduce bucket), the weight-gradient kernels accumulate straight into
+# it and the autograd Function returns None for that parameter — no per-block zeroed scratch, no AccumulateGrad add
+# kernel.  Because nothing downstream in the backward pass reads those buffers, the wgrad launches then run on a side
+# stream, off the critical path (most kernels of the attention backward occupy < 64 of the 148 SMs); join_wgrad()
+# makes the current stream wait for them (FlatGradients.all_reduce_mean / GraphedTrainStep call it once per step).
+FUSED_WGRAD = False
+_wgrad_streams = {}
+
+
+def _wgrad_side(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _wgrad_streams.get(key)
+    if st is None:
+        st = _wgrad_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def join_wgrad():
+    """The current stream waits for every weight-gradient kernel issued on the side streams so far."""
+    for key, st in _wgrad_streams.items():
+        torch.cuda.current_stream(torch.device("cuda", key)).wait_stream(st)
+
+
+def _grad_buffers(params):
+    """Per parameter: its existing gradient buffer when fused accumulation applies, else None."""
+    out = []
+    for p in params:
+        g = getattr(p, "grad", None) if (FUSED_WGRAD and p is not None) else None
+        out.append(g if (g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.shape == p.shape) else None)
+    return out
+
+
+def wgrad_side(problems, N, K):
+    """eda_wgrad on the side stream, ordered after everything issued on the current stream so far.  Only for
+    problems whose outputs are fused-accumulation buffers (see FUSED_WGRAD)."""
+    dev = problems[0]["dy"].device
+    cur, side = torch.cuda.current_stream(dev), _wgrad_side(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        wgrad(problems, N, K)
+    for pr in problems:  # inputs were allocated on `cur`: keep them alive until the side-stream kernel has run
+        pr["dy"].record_stream(side)
+        pr["x"].record_stream(side)
+
+
 def wgrad(problems, N, K):
     """problems: list (<= 6) of dicts dy (R,N), x (R,K), dw (N,K) view [row stride = dw.stride(0)], db (N) or None,
     optional x_scale / x_shift (K): x is consumed as relu(x * x_scale + x_shift).
@@ -378,6 +424,7 @@ class _MHABlockFn(torch.autograd.Function):
         ctx.meta = (H, eps, mask, drop)
         ctx.key = key
         ctx.cuda_bw = train
+        ctx.gbufs = _grad_buffers((in_w, in_b, out_w, out_b, ln_w, ln_b)) if train else None
         return y.view(B, Nq, E)
 
     @staticmethod
@@ -422,15 +469,22 @@ class _MHABlockFn(torch.autograd.Function):
         dev = q_in.device
         grad = grad.contiguous().view(-1, E)
         has_ln = ln_w is not None
-        # one zeroed buffer for every parameter gradient of the block (the wgrad / LayerNorm kernels accumulate)
-        flat = torch.zeros(3 * E * E + 3 * E + E * E + E + 2 * E, dtype=torch.float32, device=dev)
-        o = 0
-        d_in_w = flat[o:o + 3 * E * E].view(3 * E, E); o += 3 * E * E
-        d_in_b = flat[o:o + 3 * E]; o += 3 * E
-        d_out_w = flat[o:o + E * E].view(E, E); o += E * E
-        d_out_b = flat[o:o + E]; o += E
-        d_ln_w = flat[o:o + E]; o += E
-        d_ln_b = flat[o:o + E]
+        # gradient buffers: the parameters' own (fused accumulation) or one zeroed scratch for the whole block
+        g_in_w, g_in_b, g_out_w, g_out_b, g_ln_w, g_ln_b = ctx.gbufs
+        fused = all(g is not None for g in (g_in_w, g_in_b, g_out_w, g_out_b)) and \
+            (not has_ln or (g_ln_w is not None and g_ln_b is not None))
+        if fused:
+            d_in_w, d_in_b, d_out_w, d_out_b, d_ln_w, d_ln_b = g_in_w, g_in_b, g_out_w, g_out_b, g_ln_w, g_ln_b
+        else:
+            flat = torch.zeros(3 * E * E + 3 * E + E * E + E + 2 * E, dtype=torch.float32, device=dev)
+            o = 0
+            d_in_w = flat[o:o + 3 * E * E].view(3 * E, E); o += 3 * E * E
+            d_in_b = flat[o:o + 3 * E]; o += 3 * E
+            d_out_w = flat[o:o + E * E].view(E, E); o += E * E
+            d_out_b = flat[o:o + E]; o += E
+            d_ln_w = flat[o:o + E]; o += E
+            d_ln_b = flat[o:o + E]
+        run_wgrad = wgrad_side if fused else wgrad
         # 1. LayerNorm (+ output dropout)
         if has_ln:
             du, dproj = layernorm_backward(grad, u, ln_w, eps, d_ln_w, d_ln_b,
@@ -442,7 +496,7 @@ class _MHABlockFn(torch.autograd.Function):
                 dproj = grad * (dropout_mask(seed_out, p_out, B * Nq, E, 3, 0, dev) * (1.0 / (1.0 - p_out)))
         # 2. out-projection: activation gradient (tcgen05 GEMM with the transposed weight) and weight gradient
         (dctx,) = linear_raw([dict(x=dproj, w_packed=pack_weight_t(out_w, cache_key=(key, "ot")))], E, E)
-        wgrad([dict(dy=dproj, x=c, dw=d_out_w, db=d_out_b)], E, E)
+        run_wgrad([dict(dy=dproj, x=c, dw=d_out_w, db=d_out_b)], E, E)
         # 3. attention core
         dq, dk, dv = attention_backward_raw(q, k, vt, dctx, c, lse, mask, B, Nq, Nk, H,
                                             dropout=(p_attn, seed_attn) if p_attn > 0 else None)
@@ -459,13 +513,14 @@ class _MHABlockFn(torch.autograd.Function):
             probs.append(dict(dy=dq, x=q_pos.contiguous(), dw=d_in_w[:E]))
         if k_pos is not None:
             probs.append(dict(dy=dk, x=k_pos.contiguous(), dw=d_in_w[E:2 * E]))
-        wgrad(probs, E, E)
+        run_wgrad(probs, E, E)
         dq_in = dq_in.view(B, Nq, E)
         dk_in = dk_in.view(B, Nk, E)
         dv_in = dv_in.view(B, Nk, E)
         return (None, None, None, None, dq_in, dq_in if q_pos is not None else None, dk_in,
                 dk_in if k_pos is not None else None, dv_in, du.view(B, Nq, E) if residual is not None else None,
-                d_in_w, d_in_b, d_out_w, d_out_b, d_ln_w if has_ln else None, d_ln_b if has_ln else None, None)
+                *((None,) * 6 if fused else (d_in_w, d_in_b, d_out_w, d_out_b, d_ln_w if has_ln else None,
+                                             d_ln_b if has_ln else None)), None)
 
 
 def mha_block(mha, q_in, k_in, v_in, q_pos=None, k_pos=None, key_padding_mask=None, residual=None, norm=None,
@@ -502,6 +557,7 @@ class _FFNBlockFn(torch.autograd.Function):
         ctx.drop = drop
         ctx.key = key
         ctx.cuda_bw = train
+        ctx.gbufs = _grad_buffers((w1, b1, w2, b2, ln_w, ln_b)) if train else None
         return y.view(shape)
 
     @staticmethod
@@ -512,22 +568,29 @@ class _FFNBlockFn(torch.autograd.Function):
         E, Fh = w1.size(1), w1.size(0)
         dev = x.device
         grad = grad.contiguous().view(-1, E)
-        flat = torch.zeros(2 * E * Fh + Fh + E + 2 * E, dtype=torch.float32, device=dev)
-        o = 0
-        dw1 = flat[o:o + Fh * E].view(Fh, E); o += Fh * E
-        dw2 = flat[o:o + E * Fh].view(E, Fh); o += E * Fh
-        db1 = flat[o:o + Fh]; o += Fh
-        db2 = flat[o:o + E]; o += E
-        d_ln_w = flat[o:o + E]; o += E
-        d_ln_b = flat[o:o + E]
+        fused = all(g is not None for g in ctx.gbufs)
+        if fused:
+            dw1, db1, dw2, db2, d_ln_w, d_ln_b = ctx.gbufs
+        else:
+            flat = torch.zeros(2 * E * Fh + Fh + E + 2 * E, dtype=torch.float32, device=dev)
+            o = 0
+            dw1 = flat[o:o + Fh * E].view(Fh, E); o += Fh * E
+            dw2 = flat[o:o + E * Fh].view(E, Fh); o += E * Fh
+            db1 = flat[o:o + Fh]; o += Fh
+            db2 = flat[o:o + E]; o += E
+            d_ln_w = flat[o:o + E]; o += E
+            d_ln_b = flat[o:o + E]
+        run_wgrad = wgrad_side if fused else wgrad
         du, dproj = layernorm_backward(grad, u, ln_w, ctx.eps, d_ln_w, d_ln_b, dropout=(pb, sb) if pb > 0 else None)
         (dh,) = linear_raw([dict(x=dproj, w_packed=pack_weight_t(w2, cache_key=(key, "w2t")))], E, Fh)
         # hdn is the saved post-ReLU, post-dropout activation: > 0 exactly where the unit was active and kept
         dz = relu_backward(dh, hdn, 1.0 / (1.0 - pa) if pa > 0 else 1.0)
-        wgrad([dict(dy=dproj, x=hdn, dw=dw2, db=db2)], E, Fh)
-        wgrad([dict(dy=dz, x=x.contiguous().view(-1, E), dw=dw1, db=db1)], Fh, E)
+        run_wgrad([dict(dy=dproj, x=hdn, dw=dw2, db=db2)], E, Fh)
+        run_wgrad([dict(dy=dz, x=x.contiguous().view(-1, E), dw=dw1, db=db1)], Fh, E)
         (dx,) = linear_raw([dict(x=dz, w_packed=pack_weight_t(w1, cache_key=(key, "w1t")))], Fh, E)
         dx += du
+        if fused:
+            return (None, None, dx.view(x.shape), None, None, None, None, None, None, None)
         return (None, None, dx.view(x.shape), dw1, db1, dw2, db2, d_ln_w, d_ln_b, None)
 
     @staticmethod

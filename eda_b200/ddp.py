@@ -38,7 +38,10 @@ class FlatGradients:
         optimizer.step(); fg.zero()
     """
 
-    def __init__(self, module):
+    def __init__(self, module, fused_weight_grads=True):
+        """fused_weight_grads: let the attention-layer backward accumulate weight gradients straight into these
+        buffers from a side stream (attn_ops.FUSED_WGRAD) instead of returning them to autograd; `sync()` (called by
+        `all_reduce_mean`) orders the current stream after those kernels."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise RuntimeError("FlatGradients: module has no trainable parameters")
@@ -52,6 +55,9 @@ class FlatGradients:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             off += n
+        if fused_weight_grads and dev.type == "cuda":
+            from . import attn_ops
+            attn_ops.FUSED_WGRAD = True
 
     @property
     def nbytes(self):
@@ -59,6 +65,12 @@ class FlatGradients:
 
     def zero(self):
         self.flat.zero_()
+
+    def sync(self):
+        """Gradients are complete on the current stream after this (joins the side-stream weight-gradient kernels)."""
+        if self.flat.is_cuda:
+            from . import attn_ops
+            attn_ops.join_wgrad()
 
     def check_views(self):
         """True while every param.grad is still a view into the flat buffer (an optimizer's
@@ -73,6 +85,7 @@ class FlatGradients:
 
     def all_reduce_mean(self, async_op=False):
         """Sum over ranks then divide by the world size.  Returns the work handle when async_op."""
+        self.sync()
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
         world = dist.get_world_size()

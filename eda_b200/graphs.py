@@ -86,6 +86,7 @@ class GraphedTrainStep:
             flat_grads.zero()
             loss = loss_fn(model(*self.static_inputs))
             loss.backward()
+            flat_grads.sync()  # side-stream weight-gradient kernels rejoin the (capturing) stream
             return loss.detach()
 
         saved = attn_ops.PACK_CACHE

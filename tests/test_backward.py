@@ -419,3 +419,37 @@ def test_wgrad_kernel_with_bn_relu_prologue():
     ops.wgrad([dict(dy=dy, x=x, dw=dw, x_scale=sc, x_shift=sh)], N, K)
     ref = dy.double().t() @ torch.relu(x.double() * sc.double() + sh.double())
     assert rel(dw, ref) <= 5e-3
+
+
+def test_fused_weight_grad_accumulation_matches_autograd_path():
+    """ddp.FlatGradients lets the wgrad kernels accumulate into param.grad from a side stream (attn_ops.FUSED_WGRAD);
+    after fg.sync() the gradients equal the ones the plain autograd path returns, also when accumulated twice."""
+    from eda_b200 import attn_ops as ops, ddp, encoder_decoder_layers as edl
+
+    m = edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.0, "relu", self_position_embedding="loc_learned", butd=True)
+    ac.fill_params(m, seed=5).cuda().eval()
+    inp = {k: v.cuda() for k, v in ac.make_inputs("dec_layer").items()}
+    w = torch.randn(inp["query"].shape, generator=torch.Generator().manual_seed(0)).cuda()
+
+    def run():
+        out = m(inp["query"], inp["vis"], inp["text"], inp["query_pos"], None, inp["text_mask"],
+                detected_feats=inp["det"], detected_mask=inp["det_mask"])
+        (out * w).sum().backward()
+
+    for prm in m.parameters():
+        prm.grad = None
+    assert not ops.FUSED_WGRAD
+    run()
+    want = {n: prm.grad.clone() for n, prm in m.named_parameters()}
+    try:
+        fg = ddp.FlatGradients(m)
+        assert ops.FUSED_WGRAD and fg.check_views()
+        run()
+        run()
+        fg.sync()
+        torch.cuda.synchronize()
+        assert fg.check_views()
+        for n, prm in m.named_parameters():
+            assert rel(prm.grad, 2 * want[n]) <= 1e-4, n
+    finally:
+        ops.FUSED_WGRAD = False
