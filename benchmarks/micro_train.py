@@ -31,22 +31,7 @@ from eda_b200.pointnet2 import pointnet2_utils  # noqa: E402
 from oracle import attention_oracle as ao  # noqa: E402  (baseline leg only)
 
 
-class HotPath(torch.nn.Module):
-    def __init__(self):
-        super().__init__()
-        self.backbone = Pointnet2Backbone(input_feature_dim=3, width=1)
-        self.encoder = edl.BiEncoder(edl.BiEncoderLayer(ac.E, 0.0, "relu", ac.HEADS, ac.FF, True, True, True), 3)
-        self.decoder = torch.nn.ModuleList(
-            [edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.0, "relu", "loc_learned", True) for _ in range(6)])
-
-    def forward(self, pc, pos, text, text_mask, det, det_mask, query, qpos):
-        ep = self.backbone(pc)
-        vis = ep["fp2_features"].transpose(1, 2).contiguous()
-        v, t = self.encoder(vis, pos, None, text, text_mask, {}, detected_feats=det, detected_mask=det_mask)
-        q = query
-        for d in self.decoder:
-            q = d(q, v, t, qpos, None, text_mask, detected_feats=det, detected_mask=det_mask)
-        return q, v, t
+from eda_b200.hotpath import HotPath  # noqa: E402
 
 
 def reference_forward(model, ref_ext, pc, pos, text, text_mask, det, det_mask, query, qpos):
