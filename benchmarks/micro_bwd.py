@@ -51,10 +51,11 @@ def main():
         c = ops.attention_raw(q, k, vt, None, B, Nq, Nk, H, lse=lse)
         e = {}
         e["attn_fwd"] = timeit(lambda: ops.attention_raw(q, k, vt, None, B, Nq, Nk, H, lse=lse))
-        e["attn_bwd(2 launches + transpose)"] = timeit(
-            lambda: ops.attention_backward_raw(q, k, vt, dctx, c, lse, None, B, Nq, Nk, H))
         flops = 4.0 * Nq * Nk * 36 * H * B
-        e["attn_bwd_TFLOPs(7 products)"] = round(3.5 * flops / (e["attn_bwd(2 launches + transpose)"] * 1e-6) / 1e12, 1)
+        for impl in ("tc", "mma"):
+            key = f"attn_bwd_{impl} (2 launches + layout copies)"
+            e[key] = timeit(lambda: ops.attention_backward_raw(q, k, vt, dctx, c, lse, None, B, Nq, Nk, H, impl=impl))
+            e[f"attn_bwd_{impl}_TFLOPs(7 products)"] = round(3.5 * flops / (e[key] * 1e-6) / 1e12, 1)
         res["attention"][f"{Nq}x{Nk}"] = e
     for R in (640, 1056, 2048, 8192):
         x, dy = r(R, E), r(R, E)

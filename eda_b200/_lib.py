@@ -56,6 +56,9 @@ PROTOTYPES = {
                                            _c_float, ctypes.c_uint, _vp, _vp, _vp]),
     "eda_attention_backward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
                                         _c_int, _c_int, _c_float, _c_float, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp]),
+    "eda_attention_backward_tc": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp,
+                                           _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, ctypes.c_uint,
+                                           _vp, _vp, _vp, _vp, _vp]),
     "eda_wgrad": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp]),
     "eda_layernorm_backward": (_c_int, [_vp, _vp, _vp, _c_float, ctypes.c_longlong, _c_int, _vp, _vp, _vp, _vp, _c_float,
                                         ctypes.c_uint, _vp]),

@@ -335,10 +335,22 @@ def _transpose_last2(x):
     return out
 
 
-def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, H, dropout=None):
+def _channel_major(x, B, N, E):
+    """(B*N, E) -> (B, E, ld) with ld = N rounded up to 4 (padding columns stay uninitialised: never read)."""
+    ld = (N + 3) & ~3
+    if ld == N:
+        return _transpose_last2(x.view(B, N, E)), ld
+    out = torch.empty((B, E, ld), dtype=torch.float32, device=x.device)
+    out[:, :, :N].copy_(x.view(B, N, E).transpose(1, 2))
+    return out, ld
+
+
+def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, H, dropout=None, impl=None):
     """q (B*Nq,E), k (B*Nk,E), vt (B,E,ld) as attention_raw took them; dctx, c (B*Nq,E); lse (B,H,Nq).
-    Returns dq (B*Nq,E), dk (B*Nk,E), dv (B*Nk,E)."""
+    Returns dq (B*Nq,E), dk (B*Nk,E), dv (B*Nk,E).  impl: "tc" (tcgen05 kernel, default) or "mma" (warp-level
+    mma.sync kernel, the cross-check); EDA_ATTN_BWD overrides the default."""
     lib = _lib.load()
+    impl = impl or os.environ.get("EDA_ATTN_BWD", "tc")
     E = q.size(-1)
     D = E // H
     ld = vt.size(2)
@@ -354,6 +366,16 @@ def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, 
             m = m != 0
         m = m.contiguous().view(torch.uint8)
     dp, dseed = dropout if dropout is not None else (0.0, 0)
+    if impl == "tc":
+        kt, ldk = _channel_major(k, B, Nk, E)
+        qt, ldq = _channel_major(q, B, Nq, E)
+        dot, _ = _channel_major(dctx, B, Nq, E)
+        with torch.cuda.device(q.device):
+            rc = lib.eda_attention_backward_tc(_p(q), _p(k), _p(v), ld * E, _p(kt), ldk, _p(qt), _p(dot), ldq, _p(dctx),
+                                               _p(c), _p(lse), _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), float(dp),
+                                               int(dseed), _p(delta), _p(dq), _p(dk), _p(dv), _stream(q.device))
+        _lib.check(rc, "attention_backward_tc")
+        return dq, dk, dv
     with torch.cuda.device(q.device):
         rc = lib.eda_attention_backward(_p(q), _p(k), _p(v), ld * E, _p(dctx), _p(c), _p(lse), _p(m), B, Nq, Nk, H, D,
                                         1.0 / math.sqrt(D), float(dp), int(dseed), _p(delta), _p(dq), _p(dk), _p(dv),

@@ -185,6 +185,11 @@ class FusedSAFunction(torch.autograd.Function):
                        for _, bn in layers]
         ctx.cuda_bw = (any(ctx.needs_input_grad) and all(has_bn) and os.environ.get("EDA_BACKWARD", "cuda") != "torch")
         ctx.state = [] if ctx.cuda_bw else None
+        if ctx.cuda_bw:
+            from .. import attn_ops
+            # conv weights of layers 2 / 3 whose gradient buffers exist: their wgrad kernels accumulate straight
+            # into them from the side stream (attn_ops.FUSED_WGRAD); layer 1 needs a column permutation, so it stays
+            ctx.gbufs = attn_ops._grad_buffers((params[4], params[8]))
         out_pm = sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, module.radius, module.normalize_xyz, training,
                                 state=ctx.state)
         out = transpose_last2(out_pm)
@@ -275,9 +280,14 @@ def _sa_backward_cuda(ctx, grad_out):
             "sa_pool_backward_apply")
         dz = z[2]  # overwritten in place
         z[2] = None
+        fused_w = [None, ctx.gbufs[0], ctx.gbufs[1]]
         for l in (2, 1, 0):
             xin, sc, sh = src[l]
-            ops.wgrad([dict(dy=dz, x=xin, dw=dWl[l], x_scale=sc, x_shift=sh)], widths[l], Kin[l])
+            if fused_w[l] is not None:
+                ops.wgrad_side([dict(dy=dz, x=xin, dw=fused_w[l].view(widths[l], Kin[l]), x_scale=sc, x_shift=sh)],
+                               widths[l], Kin[l])
+            else:
+                ops.wgrad([dict(dy=dz, x=xin, dw=dWl[l], x_scale=sc, x_shift=sh)], widths[l], Kin[l])
             if l == 0:
                 break
             da = ops.rows_gemm(dz, Wl[l], transpose=True)
@@ -301,7 +311,7 @@ def _sa_backward_cuda(ctx, grad_out):
             dW = torch.cat([dWl[0][:, C:C + 3], dWl[0][:, :C]], dim=1)
         else:
             dW = dWl[l]
-        gps += [dW.reshape(w.shape), None, stats[l][widths[l]:], stats[l][:widths[l]]]
+        gps += [None if fused_w[l] is not None else dW.reshape(w.shape), None, stats[l][widths[l]:], stats[l][:widths[l]]]
     return (None, None, None, gf, None, *gps)
 
 

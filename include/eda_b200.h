@@ -258,6 +258,16 @@ EDA_API int eda_attention_backward(const float *q, const float *k, const float *
                                    const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
                                    float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
                                    float *dk, float *dv, void *stream);
+/* Same result on the tcgen05 tensor cores (TMEM-resident score tiles; csrc/attn_bwd_tc.cu).  Additionally takes
+ * channel-major copies kt (B, H*D, ldk) of k and qt, dctx_t (B, H*D, ldq) of q and dctx (ld >= N, multiple of 4; padding
+ * columns are never read): the second products dq += dS k, dk += dS^T q, dv += P^T dctx want four consecutive column
+ * indices of one channel per 16-byte operand unit. */
+EDA_API int eda_attention_backward_tc(const float *q, const float *k, const float *v, long long v_batch_stride,
+                                      const float *kt, int ldk, const float *qt, const float *dctx_t, int ldq,
+                                      const float *dctx, const float *ctx, const float *lse,
+                                      const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
+                                      float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
+                                      float *dk, float *dv, void *stream);
 EDA_API int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *stream);
 EDA_API int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, float eps, long long rows, int N,
                                    float *du, float *dproj, float *dgamma, float *dbeta, float dropout_p,

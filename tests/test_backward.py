@@ -78,9 +78,10 @@ def test_layernorm_backward_kernel(R, N, p):
         assert dproj is du
 
 
+@pytest.mark.parametrize("impl", ["tc", "mma"])
 @pytest.mark.parametrize("B,Nq,Nk,masked,p", [(2, 80, 80, True, 0.0), (2, 256, 132, True, 0.1), (2, 200, 1024, False, 0.0),
                                               (1, 1024, 1024, False, 0.1), (3, 7, 5, True, 0.0), (2, 129, 257, True, 0.1)])
-def test_attention_backward_kernel(B, Nq, Nk, masked, p):
+def test_attention_backward_kernel(B, Nq, Nk, masked, p, impl):
     from eda_b200 import attn_ops as ops
 
     H, D = 8, 36
@@ -98,7 +99,7 @@ def test_attention_backward_kernel(B, Nq, Nk, masked, p):
     lse = torch.empty(B, H, Nq, device="cuda")
     c = ops.attention_raw(q.view(-1, E), k.view(-1, E), vt, mask, B, Nq, Nk, H, dropout=drop, lse=lse)
     dq, dk, dv = ops.attention_backward_raw(q.view(-1, E), k.view(-1, E), vt, dctx.view(-1, E), c, lse, mask, B, Nq, Nk, H,
-                                            dropout=drop)
+                                            dropout=drop, impl=impl)
     # fp64 autograd of the same maths with the same keep-mask
     qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
     s = (qd.view(B, Nq, H, D).transpose(1, 2) / math.sqrt(D)) @ kd.view(B, Nk, H, D).transpose(1, 2).transpose(-1, -2)
