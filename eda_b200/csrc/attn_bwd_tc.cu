@@ -1,6 +1,12 @@
 // Backward of the attention core on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
 //
-// Same maths as csrc/attn_bwd.cu (which stays as the warp-level mma.sync cross-check):
+// Measured (profiles/r1_ncu_attention_backward_tc.json, Nq = Nk = 1024, B = 8): 158 + 219 us, tcgen05 pipe 15 % active —
+// with one CTA per SM the phases of a column block (staging wait, 10 MMAs, element-wise over 2 x 64 values per thread,
+// 16-32 MMAs) run back to back, so the warp-level kernel of csrc/attn_bwd.cu (74 + 90 us, three CTAs per SM) is the
+// default and this one is selected with EDA_ATTN_BWD=tc.  Next step: 64-column blocks (176 / 224 TMEM columns) so two
+// CTAs per SM overlap each other's element-wise and MMA phases, as the forward kernel does.
+//
+// Same maths as csrc/attn_bwd.cu:
 //     P  = exp(scale q k^T + mask - lse)      dP = dctx v^T       dS = P o (dP' - delta)
 //     dq = scale dS k      dk = scale dS^T q      dv = P'^T dctx             (' = dropout keep / (1 - p) re-applied)
 // as TWO launches of one kernel template, built from the blocks the forward kernel (csrc/attention.cu) established
@@ -249,13 +255,20 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
     // ---- element-wise: this thread's 64 columns of its row, 16 at a time -----------------------------------------------
     const float *st = sStat + buf * 2 * kCB + half * 64;
     const int ncol = max(0, min(64, ncp - half * 64));
+    // all 2 x 64 values of this thread in flight at once (one wait): two warps per scheduler cannot hide a TMEM round
+    // trip per 16-column chunk
+    uint32_t s[4][16], d[4][16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (i * 16 < ncol) {
-        uint32_t s[16], d[16];
-        umma::tmem_ld16(tS + (uint32_t)(i * 16), s);
-        umma::tmem_ld16(tP + (uint32_t)(i * 16), d);
-        umma::tmem_ld_wait();
+        umma::tmem_ld16(tS + (uint32_t)(i * 16), s[i]);
+        umma::tmem_ld16(tP + (uint32_t)(i * 16), d[i]);
+      }
+    }
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i * 16 < ncol) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int cl = i * 16 + e;  // column within this thread's half
@@ -269,8 +282,8 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
             dl = row_delta;
             madd = st[cl];
           }
-          float pe = ex2_approx(fmaf(__uint_as_float(s[e]), sl2, madd) - l2);
-          float dpe = __uint_as_float(d[e]);
+          float pe = ex2_approx(fmaf(__uint_as_float(s[i][e]), sl2, madd) - l2);
+          float dpe = __uint_as_float(d[i][e]);
           float pd = pe;
           if (kDrop) {
             const int col = c0 + half * 64 + cl;
@@ -281,14 +294,14 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
           }
           const float ds = pe * (dpe - dl);
           if (kKeyRows) {
-            s[e] = __float_as_uint(to_tf32(pd));   // P' over S^T
-            d[e] = __float_as_uint(to_tf32(ds));   // dS^T over dP^T
+            s[i][e] = __float_as_uint(to_tf32(pd));   // P' over S^T
+            d[i][e] = __float_as_uint(to_tf32(ds));   // dS^T over dP^T
           } else {
-            s[e] = __float_as_uint(to_tf32(ds));   // dS over S
+            s[i][e] = __float_as_uint(to_tf32(ds));   // dS over S
           }
         }
-        umma::tmem_st16(tS + (uint32_t)(i * 16), s);
-        if (kKeyRows) umma::tmem_st16(tP + (uint32_t)(i * 16), d);
+        umma::tmem_st16(tS + (uint32_t)(i * 16), s[i]);
+        if (kKeyRows) umma::tmem_st16(tP + (uint32_t)(i * 16), d[i]);
       }
     }
     umma::tmem_st_wait();
