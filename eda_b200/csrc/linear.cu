@@ -165,8 +165,15 @@ linear_kernel(const LinParams p) {
         const uint32_t bytes = (uint32_t)kcnt * (uint32_t)N * 4u;
         mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full_w[slot], bytes);
-        bulk_g2s(smem_raw + (size_t)slot * p.stage_bytes + kABytes,
-                 pr.w + (size_t)split * p.Kpad * N + (size_t)kb * kKBlock * N, bytes, &full_w[slot]);
+        unsigned char *wdst = smem_raw + (size_t)slot * p.stage_bytes + kABytes;
+        const float *wsrc = pr.w + (size_t)kb * kKBlock * Nf;  // packed: [k block][16-byte chunk][Nf columns] float4
+        if (p.S == 1) {
+          bulk_g2s(wdst, wsrc, bytes, &full_w[slot]);
+        } else {
+          // this slice's NS columns of every chunk row: contiguous pieces of NS * 16 bytes
+          for (int c = 0; c < kcnt / 4; ++c)
+            bulk_g2s(wdst + (size_t)c * N * 16, wsrc + ((size_t)c * Nf + n0) * 4, (uint32_t)N * 16u, &full_w[slot]);
+        }
       }
     }
     if (clustered) cluster_sync_all();  // matches the workers' statistics exchange
@@ -396,19 +403,27 @@ linear_kernel(const LinParams p) {
         if (clustered) cluster_sync_all(); else __syncwarp();
         LIN_TS(12);
       }
-      // pass B: normalise with the row statistics (own, or all S column slices' through DSMEM) and store
-      for (int rr = warp * (kRows / kWorkerWarps); rr < (warp + 1) * (kRows / kWorkerWarps) && rr < nvalid; ++rr) {
-        const float4 *src = reinterpret_cast<const float4 *>(tile_s + (size_t)rr * pitch);
-        float4 *dst = reinterpret_cast<float4 *>(pr.y + (row0 + rr) * Nf + n0);
-        float mean = 0.f, rstd = 1.f;
-        if (p.ln) {
-          // var = E[x^2] - mean^2 in fp32: relative error ~1e-7 (1 + mean^2/var), harmless for these activations
-          float sum = 0.f, sumsq = 0.f;
+      // pass B: normalise with the row statistics (own, or all S column slices' through DSMEM) and store.
+      // The statistics of all of this warp's rows are fetched first: a remote shared-memory read costs ~1k cycles and
+      // eight of them in a row (one per loop iteration) were most of this pass.
+      constexpr int kRowsPerWarp = kRows / kWorkerWarps;
+      float w_mean[kRowsPerWarp], w_rstd[kRowsPerWarp];
+      if (p.ln) {
+        float2 st[kRowsPerWarp];
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; ++i) {
+          const int rr = warp * kRowsPerWarp + i;
+          st[i] = make_float2(0.f, 0.f);
           if (clustered) {
-            if (lane < p.S) {
-              const float2 st = ld_shared_cluster_f32x2(mapa_u32(smem_u32(&s_stat[rr]), (uint32_t)lane));
-              sum = st.x; sumsq = st.y;
-            }
+            if (lane < p.S) st[i] = ld_shared_cluster_f32x2(mapa_u32(smem_u32(&s_stat[rr]), (uint32_t)lane));
+          } else {
+            st[i] = s_stat[rr];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; ++i) {
+          float sum = st[i].x, sumsq = st[i].y;
+          if (clustered) {
 #pragma unroll
             for (int d = 2; d > 0; d >>= 1) {  // S <= 4
               sum += __shfl_xor_sync(0xffffffffu, sum, d);
@@ -416,13 +431,19 @@ linear_kernel(const LinParams p) {
             }
             sum = __shfl_sync(0xffffffffu, sum, 0);
             sumsq = __shfl_sync(0xffffffffu, sumsq, 0);
-          } else {
-            const float2 st = s_stat[rr];
-            sum = st.x; sumsq = st.y;
           }
-          mean = sum * invN;
-          rstd = 1.0f / sqrtf(fmaxf(sumsq * invN - mean * mean, 0.f) + p.eps);
+          // var = E[x^2] - mean^2 in fp32: relative error ~1e-7 (1 + mean^2/var), harmless for these activations
+          w_mean[i] = sum * invN;
+          w_rstd[i] = 1.0f / sqrtf(fmaxf(sumsq * invN - w_mean[i] * w_mean[i], 0.f) + p.eps);
         }
+      }
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int rr = warp * kRowsPerWarp + i;
+        if (rr >= nvalid) break;
+        const float4 *src = reinterpret_cast<const float4 *>(tile_s + (size_t)rr * pitch);
+        float4 *dst = reinterpret_cast<float4 *>(pr.y + (row0 + rr) * Nf + n0);
+        const float mean = p.ln ? w_mean[i] : 0.f, rstd = p.ln ? w_rstd[i] : 1.f;
 #pragma unroll
         for (int j = 0; j < kMaxJ; ++j) {
           const int c4 = lane + j * 32;
@@ -478,16 +499,21 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, const float *__r
   }
 }
 
-// How many CTAs share the N columns of a row tile.  One SM moves ~64 B/clk to and from L2, so a 128 x 288 tile
-// (A 147 KB [+ pos], W 332 KB, out 147 KB) is bandwidth-bound on its SM; splitting N spreads the weight and
-// output traffic (and fills more of the 148 SMs: most launches of the attention stack have <= 16 row tiles).
-inline int lin_splits(int N) {
-  // Measured (scripts/lin_ts.py, benchmarks/micro_attn.py): with the staging loop as the per-tile bottleneck the
-  // split does not pay yet (3 enc + 6 dec layers: 3.78 ms split vs 3.13 ms unsplit), so it is opt-in.
-  static const int enabled = [] { const char *e = getenv("EDA_LINEAR_SPLIT"); return e ? atoi(e) : 0; }();
-  if (!enabled) return 1;
-  if (N % 48 == 0 && N / 3 >= 64) return 3;   // 288 -> 3 x 96
-  if (N % 64 == 0 && N >= 256) return N / 64 <= 4 ? N / 64 : 4;  // 256 -> 4 x 64
+// How many CTAs share the N columns of a row tile.  A 128 x 288 x 288 tile moves A 147 KB [+ pos], W 332 KB, residual and
+// output 147 KB each through ONE SM, which sustains ~30 B/clk to and from L2 (scripts/lin_ts.py: K loop 14k cycles,
+// residual pass 8k, store pass 5.5k of a 36k-cycle tile), so a launch with few row tiles is bound by per-SM bandwidth
+// while most of the chip idles.  Splitting N over S CTAs divides the weight / residual / output traffic per SM by S (the
+// A tile is re-staged by every slice).  It only pays while all tiles x S CTAs are resident at once, so S is chosen per
+// launch from the tile count; the packed weight layout does not depend on it (a slice's columns of one 16-byte chunk row
+// are contiguous: kcnt / 4 bulk copies per k block instead of one).
+// EDA_LINEAR_SPLIT=0 disables splitting, =1 forces the widest split regardless of the tile count (tests).
+inline int lin_splits(int N, int tiles, int sms) {
+  static const int mode = [] { const char *e = getenv("EDA_LINEAR_SPLIT"); return e ? atoi(e) : -1; }();
+  if (mode == 0) return 1;
+  for (int S = 4; S >= 2; --S) {
+    if (N % S || (N / S) % 16 || N / S < 48) continue;
+    if (mode == 1 || (long long)tiles * S <= sms) return S;
+  }
   return 1;
 }
 
@@ -538,7 +564,7 @@ int eda_linear_pack(const float *W, const float *scale, int N, int K, float *pac
   if (!lin_supported(N, K)) return EDA_ERR_UNSUPPORTED;
   if (!W || !packed) return EDA_ERR_INVALID_ARGUMENT;
   const int total = N * kpad_of(K);
-  pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, scale, N, K, kpad_of(K), N / lin_splits(N),
+  pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, scale, N, K, kpad_of(K), N,
                                                                          (long long)K, 1LL, packed);
   return check_launch("pack_linear_kernel");
 }
@@ -549,7 +575,7 @@ int eda_linear_pack_strided(const float *W, long long stride_n, long long stride
   if (!lin_supported(N, K)) return EDA_ERR_UNSUPPORTED;
   if (!W || !packed) return EDA_ERR_INVALID_ARGUMENT;
   const int total = N * kpad_of(K);
-  pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, nullptr, N, K, kpad_of(K), N / lin_splits(N),
+  pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, nullptr, N, K, kpad_of(K), N,
                                                                          stride_n, stride_k, packed);
   return check_launch("pack_linear_kernel");
 }
@@ -582,7 +608,10 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   p.gamma = ln_gamma; p.beta = ln_beta; p.eps = ln_eps;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
-  p.S = lin_splits(N);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  p.S = lin_splits(N, tiles, sms);
   p.NS = N / p.S;
   const int NS = p.NS;
   p.tmem_cols = NS <= 32 ? 32u : NS <= 64 ? 64u : NS <= 128 ? 128u : NS <= 256 ? 256u : 512u;
