@@ -219,6 +219,7 @@ def pack_weight_t(W, cache_key=None):
 # makes the current stream wait for them (FlatGradients.all_reduce_mean / GraphedTrainStep call it once per step).
 FUSED_WGRAD = False
 _wgrad_streams = {}
+_wgrad_pending = set()  # devices whose side stream has work the current stream has not waited for yet
 
 
 def _wgrad_side(dev):
@@ -231,8 +232,11 @@ def _wgrad_side(dev):
 
 def join_wgrad():
     """The current stream waits for every weight-gradient kernel issued on the side streams so far."""
-    for key, st in _wgrad_streams.items():
-        torch.cuda.current_stream(torch.device("cuda", key)).wait_stream(st)
+    # only streams with un-joined work: waiting on an idle side stream would, during CUDA-graph capture, make the
+    # capturing stream depend on a stream that is not part of the capture
+    for key in list(_wgrad_pending):
+        torch.cuda.current_stream(torch.device("cuda", key)).wait_stream(_wgrad_streams[key])
+    _wgrad_pending.clear()
 
 
 def _grad_buffers(params):
@@ -250,6 +254,7 @@ def wgrad_side(problems, N, K):
     dev = problems[0]["dy"].device
     cur, side = torch.cuda.current_stream(dev), _wgrad_side(dev)
     side.wait_stream(cur)
+    _wgrad_pending.add(dev.index if dev.index is not None else torch.cuda.current_device())
     with torch.cuda.stream(side):
         wgrad(problems, N, K)
     for pr in problems:  # inputs were allocated on `cur`: keep them alive until the side-stream kernel has run

@@ -8,6 +8,8 @@ static thread_local char g_last_err[256] = "";
 void set_last_cuda_error(cudaError_t e, const char *where) {
   snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+static const uint32_t *g_dropout_epoch = nullptr;
+const uint32_t *dropout_epoch_ptr() { return __atomic_load_n(&g_dropout_epoch, __ATOMIC_RELAXED); }
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 }  // namespace eda
@@ -17,6 +19,11 @@ extern "C" {
 unsigned long long eda_launch_count(void) { return __atomic_load_n(&eda::g_launches, __ATOMIC_RELAXED); }
 
 int eda_version(void) { return 100; }
+
+int eda_dropout_set_epoch(const unsigned int *device_word) {
+  __atomic_store_n(&eda::g_dropout_epoch, reinterpret_cast<const uint32_t *>(device_word), __ATOMIC_RELAXED);
+  return EDA_OK;
+}
 
 const char *eda_error_string(int code) {
   switch (code) {

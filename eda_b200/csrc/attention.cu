@@ -46,6 +46,7 @@ struct AttnParams {
   int Nq, Nk, H, ldv;
   float scale;
   uint32_t drop_thresh, drop_seed;  // dropout on the attention probabilities (nn.MultiheadAttention(dropout=p)); 0 = off
+  const uint32_t *seed_epoch;       // optional device word added to drop_seed (eda_dropout_set_epoch)
   float drop_scale;
 };
 
@@ -175,6 +176,7 @@ attention_kernel(const AttnParams p) {
   // O columns owned by this thread (16-column chunks dealt alternately to the two halves)
   constexpr int kOChunks = Dn / 16;
 
+  const uint32_t dseed = kDrop ? effective_seed(p.drop_seed, p.seed_epoch) : 0u;
   float m = -INFINITY, l = 0.f;  // l: this thread's share of the row sum (same running max in both halves)
   uint32_t phase = 0;
   constexpr float kLog2e = 1.4426950408889634f;
@@ -262,7 +264,7 @@ attention_kernel(const AttnParams p) {
           sum += pe;  // the softmax denominator is taken BEFORE dropout, as in F.multi_head_attention_forward
           if (kDrop) {
             const uint32_t ra = (uint32_t)((b * p.H + h) * p.Nq + qrow);
-            pe = dropout_keep(p.drop_seed, ra, (uint32_t)(k0 + half * 64 + i * 16 + e), p.drop_thresh) ? pe * p.drop_scale : 0.f;
+            pe = dropout_keep(dseed, ra, (uint32_t)(k0 + half * 64 + i * 16 + e), p.drop_thresh) ? pe * p.drop_scale : 0.f;
           }
           s[i][e] = __float_as_uint(to_tf32(pe));
         }
@@ -388,6 +390,7 @@ extern "C" int eda_attention_forward_lse(const float *q, const float *k, const f
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.ldv = ldv; p.scale = scale;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
+  p.seed_epoch = dropout_epoch_ptr();
   cudaStream_t st = as_stream(stream);
   switch (D) {  // head dims the compiled template set covers (EDA: 288 / 8 = 36)
     case 32: return launch_attention<32>(p, B, st);

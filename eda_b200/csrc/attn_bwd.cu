@@ -37,6 +37,7 @@ struct AttnBwdParams {
   int Nq, Nk, H;
   float scale;
   uint32_t drop_thresh, drop_seed;
+  const uint32_t *seed_epoch;  // optional device word added to drop_seed (eda_dropout_set_epoch)
   float drop_scale;
 };
 
@@ -177,6 +178,7 @@ attention_backward_kernel(const AttnBwdParams p) {
     for (int e = 0; e < 4; ++e) { o1[i][e] = 0.f; o2[i][e] = 0.f; }
 
   const float sl2 = p.scale * kLog2e;
+  const uint32_t dseed = kDrop ? effective_seed(p.drop_seed, p.seed_epoch) : 0u;
   for (int blk = 0; blk < nblocks; ++blk) {
     const int buf = blk & 1;
     if (blk + 1 < nblocks) {
@@ -223,7 +225,7 @@ attention_backward_kernel(const AttnBwdParams p) {
         if (kDrop) {
           const int qi = kKeyRows ? c0 + cl : (second ? rB : rA);
           const int ki = kKeyRows ? (second ? rB : rA) : c0 + cl;
-          const bool keep = dropout_keep(p.drop_seed, (uint32_t)(stat_base + qi), (uint32_t)ki, p.drop_thresh);
+          const bool keep = dropout_keep(dseed, (uint32_t)(stat_base + qi), (uint32_t)ki, p.drop_thresh);
           dpe = keep ? dpe * p.drop_scale : 0.f;
           pf[j][e] = f2tf32(keep ? pe * p.drop_scale : 0.f);
         } else {
@@ -303,6 +305,7 @@ extern "C" int eda_attention_backward(const float *q, const float *k, const floa
   p.q = q; p.k = k; p.v = v; p.dctx = dctx; p.ctx = ctx; p.lse = lse; p.mask = key_padding_mask; p.delta = delta;
   p.dq = dq; p.dk = dk; p.dv = dv; p.v_batch_stride = v_batch_stride; p.Nq = Nq; p.Nk = Nk; p.H = H; p.scale = scale;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
+  p.seed_epoch = dropout_epoch_ptr();
   cudaStream_t st = as_stream(stream);
   switch (D) {
     case 32: return launch_attention_backward<32>(p, B, st);

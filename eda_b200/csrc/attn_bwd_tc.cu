@@ -40,6 +40,7 @@ struct AttnBwdTcParams {
   int Nq, Nk, H, ldk, ldq;
   float scale;
   uint32_t drop_thresh, drop_seed;
+  const uint32_t *seed_epoch;  // optional device word added to drop_seed (eda_dropout_set_epoch)
   float drop_scale;
 };
 
@@ -212,6 +213,7 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
     row_delta = s_delta[r];
   }
   const float sl2 = p.scale * kLog2e;
+  const uint32_t dseed = kDrop ? effective_seed(p.drop_seed, p.seed_epoch) : 0u;
   uint32_t phase = 0;
 
   for (int blk = 0; blk < nblocks; ++blk) {
@@ -288,7 +290,7 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
           if (kDrop) {
             const int col = c0 + half * 64 + cl;
             const int qi = kKeyRows ? col : row, ki = kKeyRows ? row : col;
-            const bool keep = dropout_keep(p.drop_seed, (uint32_t)(stat_base + qi), (uint32_t)ki, p.drop_thresh);
+            const bool keep = dropout_keep(dseed, (uint32_t)(stat_base + qi), (uint32_t)ki, p.drop_thresh);
             dpe = keep ? dpe * p.drop_scale : 0.f;
             pd = keep ? pe * p.drop_scale : 0.f;
           }
@@ -422,6 +424,7 @@ extern "C" int eda_attention_backward_tc(const float *q, const float *k, const f
   p.mask = key_padding_mask; p.delta = delta; p.dq = dq; p.dk = dk; p.dv = dv; p.v_batch_stride = v_batch_stride;
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.ldk = ldk; p.ldq = ldq; p.scale = scale;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
+  p.seed_epoch = dropout_epoch_ptr();
   cudaStream_t st = as_stream(stream);
   switch (D) {
     case 32: return launch_both<32>(p, B, st);

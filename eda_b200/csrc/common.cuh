@@ -141,6 +141,13 @@ inline uint32_t dropout_thresh(float p) {
   return t >= 16777216.0 ? 16777216u : (uint32_t)(t + 0.5);
 }
 
+// Optional device word added to every dropout seed at kernel run time (eda_dropout_set_epoch): lets a CUDA graph of a
+// training step draw fresh masks on every replay although the per-call seeds are frozen into the graph.
+const uint32_t *dropout_epoch_ptr();
+__device__ __forceinline__ uint32_t effective_seed(uint32_t seed, const uint32_t *epoch) {
+  return epoch ? seed + __ldg(epoch) : seed;
+}
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace eda

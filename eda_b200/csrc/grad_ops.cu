@@ -185,10 +185,11 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_backward_kernel(const float *__restrict__ dy, const float *__restrict__ u, const float *__restrict__ gamma,
                           float eps, long long rows, int N, float *__restrict__ du, float *__restrict__ dproj,
                           float *__restrict__ dgamma, float *__restrict__ dbeta, uint32_t drop_thresh,
-                          uint32_t drop_seed, float drop_scale) {
+                          uint32_t drop_seed_base, float drop_scale, const uint32_t *seed_epoch) {
   __shared__ float s_acc[2][kLnMaxN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n4 = N >> 2;
+  const uint32_t drop_seed = dproj ? effective_seed(drop_seed_base, seed_epoch) : 0u;
   for (int i = tid; i < 2 * kLnMaxN; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
   __syncthreads();
   float4 g4[kLnJ], ag[kLnJ], ab[kLnJ];
@@ -358,7 +359,7 @@ int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, 
   const uint32_t thresh = dropout_thresh(dropout_p);
   layernorm_backward_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(
       dy, u, gamma, eps, rows, N, du, thresh ? dproj : nullptr, dgamma, dbeta, thresh, dropout_seed,
-      1.0f / (1.0f - dropout_p));
+      1.0f / (1.0f - dropout_p), dropout_epoch_ptr());
   return check_launch("layernorm_backward_kernel");
 }
 

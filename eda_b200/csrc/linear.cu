@@ -65,6 +65,7 @@ struct LinParams {
   uint32_t tmem_cols, stage_bytes;
   int nstages, prefetch;  // ring depth in use and how many blocks the staging warps run ahead (nstages - 2)
   uint32_t drop_thresh, drop_seed;  // output dropout (after bias / ReLU, before residual): thresh 0 = off
+  const uint32_t *seed_epoch;       // optional device word added to drop_seed (eda_dropout_set_epoch)
   float drop_scale;                 // 1 / (1 - p)
 };
 
@@ -318,6 +319,7 @@ linear_kernel(const LinParams p) {
     const int nvalid = (int)min((long long)kRows, (long long)pr.rows - row0);
     const int n4 = N >> 2;
     LIN_TS(8);
+    const uint32_t dseed = p.drop_thresh ? effective_seed(p.drop_seed, p.seed_epoch) : 0u;
     const bool direct_t = pr.tb > 0;  // channel-major output goes straight to global (already coalesced)
     long long bb = 0, rr0 = 0;
     if (direct_t) { bb = row / pr.tb; rr0 = row - bb * pr.tb; }
@@ -338,10 +340,10 @@ linear_kernel(const LinParams p) {
         if (p.drop_thresh) {  // nn.Dropout on this block's output: element (row, column) of problem pi
           const uint32_t ra = (uint32_t)row * (uint32_t)kMaxProbs + (uint32_t)pi;
           const uint32_t gc = (uint32_t)(n0 + c);
-          o.x = dropout_keep(p.drop_seed, ra, gc + 0u, p.drop_thresh) ? o.x * p.drop_scale : 0.f;
-          o.y = dropout_keep(p.drop_seed, ra, gc + 1u, p.drop_thresh) ? o.y * p.drop_scale : 0.f;
-          o.z = dropout_keep(p.drop_seed, ra, gc + 2u, p.drop_thresh) ? o.z * p.drop_scale : 0.f;
-          o.w = dropout_keep(p.drop_seed, ra, gc + 3u, p.drop_thresh) ? o.w * p.drop_scale : 0.f;
+          o.x = dropout_keep(dseed, ra, gc + 0u, p.drop_thresh) ? o.x * p.drop_scale : 0.f;
+          o.y = dropout_keep(dseed, ra, gc + 1u, p.drop_thresh) ? o.y * p.drop_scale : 0.f;
+          o.z = dropout_keep(dseed, ra, gc + 2u, p.drop_thresh) ? o.z * p.drop_scale : 0.f;
+          o.w = dropout_keep(dseed, ra, gc + 3u, p.drop_thresh) ? o.w * p.drop_scale : 0.f;
         }
         if (pr.round_out) o = tf32x4(o);
         if (direct_t) {
@@ -518,8 +520,9 @@ inline int lin_splits(int N, int tiles, int sms) {
 }
 
 // keep-mask (1.0 / 0.0) of the dropout decisions above, for the backward pass: out[a * cols + b]
-__global__ void dropout_mask_kernel(uint32_t seed, uint32_t thresh, long long rows, int cols, uint32_t a_mul, uint32_t a_add,
-                                    float *__restrict__ out) {
+__global__ void dropout_mask_kernel(uint32_t seed_base, uint32_t thresh, long long rows, int cols, uint32_t a_mul, uint32_t a_add,
+                                    float *__restrict__ out, const uint32_t *seed_epoch) {
+  const uint32_t seed = effective_seed(seed_base, seed_epoch);
   const long long total = rows * cols;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long a = e / cols;
@@ -550,7 +553,8 @@ int eda_dropout_mask(unsigned int seed, float p, long long rows, int cols, unsig
   if (!out) return EDA_ERR_INVALID_ARGUMENT;
   const long long total = rows * cols;
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  dropout_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(seed, dropout_thresh(p), rows, cols, a_mul, a_add, out);
+  dropout_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(seed, dropout_thresh(p), rows, cols, a_mul, a_add, out,
+                                                           dropout_epoch_ptr());
   return check_launch("dropout_mask_kernel");
 }
 
@@ -608,6 +612,7 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   p.gamma = ln_gamma; p.beta = ln_beta; p.eps = ln_eps;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
+  p.seed_epoch = dropout_epoch_ptr();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -11,7 +11,11 @@ Inference only: packed attention weights are cached across calls (attn_ops.pack_
 recorded before an optimizer step would keep using the old packed copy.  Re-capture after changing
 weights.  Shapes are fixed at capture time (static input buffers, like any CUDA graph).
 """
+import ctypes
+
 import torch
+
+from . import _lib
 
 
 class GraphedCallable:
@@ -61,28 +65,34 @@ class GraphedTrainStep:
     by that host work; replayed, only the device time remains.  The weight-pack kernels are captured too (the
     packed-weight caches are switched off during warm-up and capture), so replays after an optimizer step use the
     updated parameters; BatchNorm running statistics and `num_batches_tracked` are updated by captured device ops.
-    Restrictions: fixed shapes; parameters, gradients (FlatGradients) and inputs must stay at their addresses; dropout
-    seeds are drawn on the host at capture time, so a graph recorded with dropout p > 0 would repeat the same masks
-    every replay — the constructor refuses that configuration."""
+    Restrictions: fixed shapes; parameters, gradients (FlatGradients) and inputs must stay at their addresses.  Dropout
+    (the reference's default 0.1) is supported: the host-drawn seeds are frozen into the graph, and a device epoch word
+    that the graph increments once per replay is added to them by the kernels (`self.dropout_epoch`)."""
 
     def __init__(self, model, loss_fn, example_inputs, flat_grads, warmup=3):
         from . import attn_ops
 
         if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
             raise RuntimeError("GraphedTrainStep needs CUDA tensor inputs")
+        # Dropout: the per-call seeds are drawn on the host while the step is recorded and are frozen into the graph.
+        # A device "epoch" word that the graph itself increments at the start of every replay is added to every seed by
+        # the kernels (eda_dropout_set_epoch), so each replay draws fresh masks — the same ones in its forward and backward.
+        has_dropout = False
         for m in model.modules():
             p = getattr(m, "p", None) if isinstance(m, torch.nn.Dropout) else getattr(m, "dropout", None) \
                 if isinstance(m, torch.nn.MultiheadAttention) else None
-            if m.training and isinstance(p, float) and p > 0:
-                raise RuntimeError("GraphedTrainStep: dropout > 0 in training mode cannot be captured "
-                                   "(host-side seeds would be frozen into the graph)")
+            has_dropout |= bool(m.training and isinstance(p, float) and p > 0)
         if not flat_grads.check_views():
             raise RuntimeError("GraphedTrainStep: param.grad must alias the FlatGradients buffer")
         self.device = example_inputs[0].device
         self.static_inputs = [t.clone() for t in example_inputs]
         self.flat_grads = flat_grads
+        self.dropout_epoch = torch.zeros(1, dtype=torch.int32, device=self.device) if has_dropout else None
+        epoch = self.dropout_epoch
 
         def step():
+            if epoch is not None:
+                epoch.add_(1)
             flat_grads.zero()
             loss = loss_fn(model(*self.static_inputs))
             loss.backward()
@@ -91,6 +101,9 @@ class GraphedTrainStep:
 
         saved = attn_ops.PACK_CACHE
         attn_ops.PACK_CACHE = False
+        lib = _lib.load()
+        if epoch is not None:
+            lib.eda_dropout_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
         try:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -104,6 +117,7 @@ class GraphedTrainStep:
                 self.loss = step()
         finally:
             attn_ops.PACK_CACHE = saved
+            lib.eda_dropout_set_epoch(None)  # eager launches after this are unaffected; the graph keeps the baked pointer
 
     def __call__(self, *inputs):
         if len(inputs) != len(self.static_inputs):

@@ -284,6 +284,12 @@ EDA_API int eda_relu_backward(const float *dy, const float *y, float scale, long
  * attention: a_mul = 1, a_add = 0, rows = B*H*Nq (row (b*H + h)*Nq + q), cols = Nk. */
 EDA_API int eda_dropout_mask(unsigned int seed, float p, long long rows, int cols, unsigned int a_mul,
                              unsigned int a_add, float *out, void *stream);
+/* Optional dropout epoch: a device word whose value every dropout-applying kernel of this library (forward and
+ * backward) adds to its dropout_seed when it RUNS.  A CUDA graph of a training step freezes the host-drawn seeds; with
+ * an epoch word that a captured device op increments once per step, every replay still draws fresh masks, identical in
+ * that step's forward and backward.  Process-wide setting (the one piece of library state besides the error string and
+ * the launch counter); NULL = off (default).  The word must stay allocated while kernels launched under it run. */
+EDA_API int eda_dropout_set_epoch(const unsigned int *device_word);
 
 /* ---------------------------------------------------------------------------------------
  * Backward pass of the fused set-abstraction stage (eda_sa_mlp_forward).  In the reference: autograd through

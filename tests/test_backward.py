@@ -454,3 +454,50 @@ def test_fused_weight_grad_accumulation_matches_autograd_path():
             assert rel(prm.grad, 2 * want[n]) <= 1e-4, n
     finally:
         ops.FUSED_WGRAD = False
+
+
+def test_graphed_train_step_with_dropout_draws_fresh_masks_and_correct_gradients():
+    """A training step with the reference's default dropout 0.1 as ONE CUDA graph: the device epoch word makes every
+    replay draw new masks (losses differ from replay to replay), forward and backward of a replay see the same masks
+    (the CUDA backward agrees with the torch cross-check backward captured with the same seeds), and eager launches
+    after the capture are unaffected."""
+    from eda_b200 import attn_ops as ops, ddp, encoder_decoder_layers as edl
+    from eda_b200.graphs import GraphedTrainStep
+
+    inp = {k: v.cuda() for k, v in ac.make_inputs("dec_layer").items()}
+    args = [inp["query"], inp["vis"], inp["text"], inp["query_pos"], inp["det"]]
+    tmask, dmask = inp["text_mask"], inp["det_mask"]
+
+    def build():
+        m = edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.1, "relu", self_position_embedding="loc_learned", butd=True)
+        return ac.fill_params(m, seed=5).cuda().train()
+
+    def loss_fn(out):
+        return out.pow(2).mean()
+
+    grads, losses = {}, {}
+    try:
+        for mode in ("cuda", "torch"):
+            m = build()
+
+            def fwd(query, vis, text, qpos, det, m=m):
+                return m(query, vis, text, qpos, None, tmask, detected_feats=det, detected_mask=dmask)
+
+            wrapper = torch.nn.Module()
+            wrapper.m = m
+            wrapper.forward = fwd
+            fg = ddp.FlatGradients(m)
+            torch.manual_seed(11)
+            step = _block_grads(mode, lambda: GraphedTrainStep(wrapper, loss_fn, args, fg))
+            assert step.dropout_epoch is not None
+            l1 = step(*args).item()
+            g1 = fg.flat.clone()
+            l2 = step(*args).item()
+            torch.cuda.synchronize()
+            assert l1 != l2 and not torch.equal(g1, fg.flat), "replays must draw different dropout masks"
+            assert int(step.dropout_epoch.item()) == 3 + 2  # 3 warm-up steps + 2 replays
+            grads[mode], losses[mode] = g1, l1
+        assert abs(losses["cuda"] - losses["torch"]) <= 1e-5 * abs(losses["torch"])
+        assert rel(grads["cuda"], grads["torch"]) <= 2e-2
+    finally:
+        ops.FUSED_WGRAD = False
