@@ -19,6 +19,8 @@ PROTOTYPES = {
     "eda_last_cuda_error": (ctypes.c_char_p, []),
     "eda_launch_count": (ctypes.c_ulonglong, []),
     "eda_fps_scratch_bytes": (_sz, [_c_int, _c_int, _c_int]),
+    "eda_fps_identity_check": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "eda_furthest_point_sampling_ex": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp]),
     "eda_furthest_point_sampling": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "eda_furthest_point_sampling_progress": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     "eda_stream_wait_value32": (_c_int, [_vp, _vp, _c_int]),

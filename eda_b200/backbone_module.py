@@ -11,11 +11,11 @@ Results are identical to running the stages back to back.
 import torch
 import torch.nn as nn
 
-from .pointnet2 import fused, pointnet2_utils
+from .pointnet2 import _ext, fused, pointnet2_utils
 from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
 
 
-def fps_chain(xyz, npoints, side, timing_events=None, pipeline_every=0):
+def fps_chain(xyz, npoints, side, timing_events=None, pipeline_every=0, identity_shortcut=True):
     """Runs FPS(xyz, npoints[0]) -> FPS(of that subset, npoints[1]) -> ... on the CUDA stream `side`
     (it first waits for the current stream).  Returns [(inds, event)] per stage; a consumer on another
     stream waits for the event before using inds.  `timing_events` = (start, end) CUDA events recorded on
@@ -33,9 +33,15 @@ def fps_chain(xyz, npoints, side, timing_events=None, pipeline_every=0):
             handle = None
             every = pipeline_every[i] if isinstance(pipeline_every, (list, tuple)) and i < len(pipeline_every) \
                 else (pipeline_every if (i == 0 and isinstance(pipeline_every, int)) else 0)
+            # stages after the first sample from a set that is already in FPS order: unless a step is decided by a tie
+            # the answer is 0..npoint-1.  A parallel check verifies that per scene (exact arithmetic, ~20 us) and the
+            # sampler skips its serial loop for verified scenes, bit-exact either way.
+            flags = _ext.fps_identity_flags(cur, npoint) if (i > 0 and identity_shortcut) else None
             if every and every > 0:
-                handle = fused.launch_pipelined_fps(cur, npoint, every, side)
+                handle = fused.launch_pipelined_fps(cur, npoint, every, side, not_identity=flags)
                 inds = handle.inds
+            elif flags is not None:
+                inds = _ext.furthest_point_sampling(cur, npoint, not_identity=flags)
             else:
                 inds = pointnet2_utils.furthest_point_sample(cur, npoint)
             if i == 0 and timing_events is not None:

@@ -87,11 +87,27 @@ struct Layout {
   }
 };
 
+// One CTA writes idxs = 0 .. m-1 and publishes every progress milestone the full kernel would have.
+__device__ __forceinline__ void fps_write_identity(int *__restrict__ idxs, int m, int *__restrict__ progress, int every) {
+  for (int i = threadIdx.x; i < m; i += blockDim.x) idxs[i] = i;
+  if (progress != nullptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(progress, (m + every - 1) / every);
+  }
+}
+
 template <int P2, int CL, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, int *__restrict__ idxs_all,
-                   int *__restrict__ progress, int every) {
+                   int *__restrict__ progress, int every, const int *__restrict__ not_identity) {
   constexpr int P = 2 * P2;
+  // Verified shortcut (eda_fps_identity_check): the answer for this scene is 0, 1, ..., m-1.  Uniform over the
+  // cluster, taken before any barrier exists.
+  if (not_identity != nullptr && __ldg(not_identity + blockIdx.x / CL) == 0) {
+    if (((CL > 1) ? cluster_ctarank() : 0u) == 0u) fps_write_identity(idxs_all + (size_t)(blockIdx.x / CL) * m, m, progress, every);
+    return;
+  }
   constexpr int kWarps = T / 32;
   extern __shared__ __align__(16) float s_xyz[];  // [P][T][3] copy of this CTA's points, then [P][T] ~codes
   unsigned *s_code = reinterpret_cast<unsigned *>(s_xyz + (size_t)P * T * 3);
@@ -269,9 +285,13 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
 constexpr int kGThreads = 1024;
 __global__ void __launch_bounds__(kGThreads, 1)
 fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float *__restrict__ temp_all,
-                  int *__restrict__ idxs_all, int *__restrict__ progress, int every) {
+                  int *__restrict__ idxs_all, int *__restrict__ progress, int every, const int *__restrict__ not_identity) {
   __shared__ Key s_warp[2][kGThreads / 32];
   const int scene = blockIdx.x;
+  if (not_identity != nullptr && __ldg(not_identity + scene) == 0) {
+    fps_write_identity(idxs_all + (size_t)scene * m, m, progress, every);
+    return;
+  }
   const float *__restrict__ xyz = xyz_all + (size_t)scene * N * 3;
   float *__restrict__ temp = temp_all + (size_t)scene * N;
   int *__restrict__ idxs = idxs_all + (size_t)scene * m;
@@ -405,6 +425,7 @@ FpsPlan plan_fps(int B, int N, int lb) {
 
 template <int P2, int CL, int T>
 int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int *idxs, int *progress, int every,
+                   const int *not_identity,
                    cudaStream_t st) {
   auto kern = fps_cluster_kernel<P2, CL, T>;
   const size_t smem = (size_t)2 * P2 * T * 4 * sizeof(float);
@@ -423,40 +444,109 @@ int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, lay, idxs, progress, every), "fps_cluster_kernel launch");
+  EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, lay, idxs, progress, every, not_identity), "fps_cluster_kernel launch");
   return check_launch("fps_cluster_kernel");
 }
 
 template <int CL, int T>
 int dispatch_p(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, int *progress, int every,
+               const int *not_identity,
                cudaStream_t st) {
   if constexpr (T == 1024) {
     switch (pl.p2) {
-      case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-      case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-      case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+      case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+      case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+      case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
     }
     return EDA_ERR_UNSUPPORTED;
   }
   switch (pl.p2) {
-    case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-    case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-    case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-    case 6: return launch_cluster<6, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-    case 8: return launch_cluster<8, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-    case 10: return launch_cluster<10, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
-    case 13: return launch_cluster<13, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, st);
+    case 1: return launch_cluster<1, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+    case 2: return launch_cluster<2, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+    case 4: return launch_cluster<4, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+    case 6: return launch_cluster<6, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+    case 8: return launch_cluster<8, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+    case 10: return launch_cluster<10, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
+    case 13: return launch_cluster<13, CL, T>(xyz, B, N, m, pl.lay, idxs, progress, every, not_identity, st);
   }
   return EDA_ERR_UNSUPPORTED;
 }
 
 template <int CL>
 int dispatch_t(const FpsPlan &pl, const float *xyz, int B, int N, int m, int *idxs, int *progress, int every,
+               const int *not_identity,
                cudaStream_t st) {
-  if (pl.t == 256) return dispatch_p<CL, 256>(pl, xyz, B, N, m, idxs, progress, every, st);
-  if (pl.t == 512) return dispatch_p<CL, 512>(pl, xyz, B, N, m, idxs, progress, every, st);
-  if (pl.t == 1024) return dispatch_p<CL, 1024>(pl, xyz, B, N, m, idxs, progress, every, st);
+  if (pl.t == 256) return dispatch_p<CL, 256>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
+  if (pl.t == 512) return dispatch_p<CL, 512>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
+  if (pl.t == 1024) return dispatch_p<CL, 1024>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
   return EDA_ERR_UNSUPPORTED;
+}
+
+
+
+// ---- identity verification for FPS of an FPS-ordered set -----------------------------------------------------------
+// The backbone samples 2048 -> 1024 -> 512 -> 256 from sets that are already in FPS order: without
+// exact ties the answer is 0, 1, ..., m-1, and 1791 strictly serial iterations (0.63 ms at B = 8) reproduce it.  The
+// answer IS the identity iff at every step i < m point i is the strict maximiser of the running minimum, i.e.
+//     d_i := min_{k<i} |p_i - p_k|^2  >  min_{k<i} |p_j - p_k|^2   for every j != i          (and p_i is not skipped)
+// (strict, so the reference's thread-layout tie-break never decides; j < i gives d_i > 0).  That condition is
+// embarrassingly parallel: pass 1 computes d_i (thread = i), pass 2 checks every j against d_1 .. d_{min(j,m)-1}
+// (thread = j, one running minimum), both with the reference's exact distance arithmetic.  A scene that fails any
+// comparison (ties, duplicates, skipped points, NaNs) sets its flag and the sampler runs the full algorithm for it.
+constexpr int kIdThreads = 256;
+
+__global__ void __launch_bounds__(kIdThreads)
+fps_identity_pass1_kernel(const float *__restrict__ xyz_all, int n, int m, float *__restrict__ dsel_all,
+                          int *__restrict__ not_identity) {
+  extern __shared__ float s_pts[];  // [min(n, m)][3]: only points k < m are ever reference points
+  const int scene = blockIdx.y;
+  const float *xyz = xyz_all + (size_t)scene * n * 3;
+  const int np = min(n, m);
+  for (int i = threadIdx.x; i < np * 3; i += kIdThreads) s_pts[i] = __ldg(xyz + i);
+  __syncthreads();
+  const int i = blockIdx.x * kIdThreads + threadIdx.x;
+  if (i >= m) return;
+  if (i >= n) {  // more samples than points: never the identity
+    atomicExch(not_identity + scene, 1);
+    return;
+  }
+  const float x = s_pts[i * 3], y = s_pts[i * 3 + 1], z = s_pts[i * 3 + 2];
+  float run = 1e10f;  // the reference's initial running minimum (sampling.cpp:78-80)
+  for (int k = 0; k < i; ++k) {
+    const float d = sq3(__fadd_rn(x, -s_pts[k * 3]), __fadd_rn(y, -s_pts[k * 3 + 1]), __fadd_rn(z, -s_pts[k * 3 + 2]));
+    run = fminf(run, d);
+  }
+  dsel_all[(size_t)scene * m + i] = run;
+  if (i > 0) {
+    const bool skipped = (double)sq3(x, y, z) <= 1e-3;  // sampling_gpu.cu:105-106
+    if (skipped || !(run > 0.f)) atomicExch(not_identity + scene, 1);
+  }
+}
+
+__global__ void __launch_bounds__(kIdThreads)
+fps_identity_pass2_kernel(const float *__restrict__ xyz_all, int n, int m, const float *__restrict__ dsel_all,
+                          int *__restrict__ not_identity) {
+  extern __shared__ float s_pts[];  // [min(n, m)][3] reference points, then [m] d_i
+  const int scene = blockIdx.y;
+  const float *xyz = xyz_all + (size_t)scene * n * 3;
+  const int np = min(n, m);
+  float *s_d = s_pts + (size_t)np * 3;
+  for (int i = threadIdx.x; i < np * 3; i += kIdThreads) s_pts[i] = __ldg(xyz + i);
+  for (int i = threadIdx.x; i < np; i += kIdThreads) s_d[i] = __ldg(dsel_all + (size_t)scene * m + i);
+  __syncthreads();
+  const int j = blockIdx.x * kIdThreads + threadIdx.x;
+  if (j >= n) return;
+  const float x = __ldg(xyz + j * 3), y = __ldg(xyz + j * 3 + 1), z = __ldg(xyz + j * 3 + 2);
+  // j competes with i = 1 .. min(j, m) - 1 (for i >= j it is the candidate itself or already selected)
+  const int last = min(j, np) - 1;
+  float run = 1e10f;
+  bool bad = false;
+  for (int k = 0; k < last; ++k) {
+    const float d = sq3(__fadd_rn(x, -s_pts[k * 3]), __fadd_rn(y, -s_pts[k * 3 + 1]), __fadd_rn(z, -s_pts[k * 3 + 2]));
+    run = fminf(run, d);               // = min_{k' <= k} |p_j - p_k'|^2 : j's running minimum when step k + 1 is decided
+    bad |= !(run < s_d[k + 1]);
+  }
+  if (bad) atomicExch(not_identity + scene, 1);
 }
 
 }  // namespace
@@ -472,6 +562,7 @@ size_t eda_fps_scratch_bytes(int B, int N, int m) {
 }
 
 static int fps_impl(const float *xyz, int B, int N, int m, void *scratch, int *idxs, int *progress, int every,
+                    const int *not_identity,
                     void *stream) {
   using namespace eda;
   if (B < 0 || N < 0 || m < 0) return EDA_ERR_INVALID_ARGUMENT;
@@ -483,26 +574,56 @@ static int fps_impl(const float *xyz, int B, int N, int m, void *scratch, int *i
   const int lb = ref_log2_block(N);
   const FpsPlan pl = plan_fps(B, N, lb);
   switch (pl.cl) {
-    case 1: return dispatch_t<1>(pl, xyz, B, N, m, idxs, progress, every, st);
-    case 2: return dispatch_t<2>(pl, xyz, B, N, m, idxs, progress, every, st);
-    case 4: return dispatch_t<4>(pl, xyz, B, N, m, idxs, progress, every, st);
-    case 8: return dispatch_t<8>(pl, xyz, B, N, m, idxs, progress, every, st);
-    case 16: return dispatch_t<16>(pl, xyz, B, N, m, idxs, progress, every, st);
+    case 1: return dispatch_t<1>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
+    case 2: return dispatch_t<2>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
+    case 4: return dispatch_t<4>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
+    case 8: return dispatch_t<8>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
+    case 16: return dispatch_t<16>(pl, xyz, B, N, m, idxs, progress, every, not_identity, st);
     default: break;
   }
   if (!scratch) return EDA_ERR_INVALID_ARGUMENT;
-  fps_global_kernel<<<B, kGThreads, 0, st>>>(xyz, N, m, lb, (float *)scratch, idxs, progress, every);
+  fps_global_kernel<<<B, kGThreads, 0, st>>>(xyz, N, m, lb, (float *)scratch, idxs, progress, every, not_identity);
   return check_launch("fps_global_kernel");
 }
 
 int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, void *scratch, int *idxs, void *stream) {
-  return fps_impl(xyz, B, N, m, scratch, idxs, nullptr, 0, stream);
+  return fps_impl(xyz, B, N, m, scratch, idxs, nullptr, 0, nullptr, stream);
+}
+
+int eda_furthest_point_sampling_ex(const float *xyz, int B, int N, int m, void *scratch, int *idxs, int *progress,
+                                   int every, const int *not_identity, void *stream) {
+  return fps_impl(xyz, B, N, m, scratch, idxs, progress, progress ? every : 0, not_identity, stream);
+}
+
+int eda_fps_identity_check(const float *xyz, int B, int n, int m, float *dsel, int *not_identity, void *stream) {
+  using namespace eda;
+  if (B < 0 || n < 0 || m < 0) return EDA_ERR_INVALID_ARGUMENT;
+  if (B == 0 || m == 0) return EDA_OK;
+  if (!xyz || !dsel || !not_identity || n == 0) return EDA_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return EDA_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  EDA_CUDA_TRY(cudaMemsetAsync(not_identity, 0, (size_t)B * sizeof(int), st), "identity flag memset");
+  const int np = n < m ? n : m;
+  const size_t smem1 = (size_t)np * 3 * sizeof(float), smem2 = (size_t)np * 4 * sizeof(float);
+  if (smem2 > 200 * 1024) return EDA_ERR_UNSUPPORTED;
+  static size_t smem_set = 0;
+  if (smem2 > 48 * 1024 && smem2 > smem_set) {
+    EDA_CUDA_TRY(cudaFuncSetAttribute(fps_identity_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
+                 "identity smem attr");
+    EDA_CUDA_TRY(cudaFuncSetAttribute(fps_identity_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
+                 "identity smem attr");
+    smem_set = smem2;
+  }
+  dim3 g1((unsigned)((m + kIdThreads - 1) / kIdThreads), (unsigned)B), g2((unsigned)((n + kIdThreads - 1) / kIdThreads), (unsigned)B);
+  fps_identity_pass1_kernel<<<g1, kIdThreads, smem1, st>>>(xyz, n, m, dsel, not_identity);
+  fps_identity_pass2_kernel<<<g2, kIdThreads, smem2, st>>>(xyz, n, m, dsel, not_identity);
+  return check_launch("fps_identity_kernels", 2);
 }
 
 int eda_furthest_point_sampling_progress(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
                                          int *progress, int every, void *stream) {
   if (!progress) return EDA_ERR_INVALID_ARGUMENT;
-  return fps_impl(xyz, B, N, m, scratch, idxs, progress, every, stream);
+  return fps_impl(xyz, B, N, m, scratch, idxs, progress, every, nullptr, stream);
 }
 
 // Stream-ordered wait on a device word: work queued on `stream` after this call starts once

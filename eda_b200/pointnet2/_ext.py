@@ -55,8 +55,26 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def furthest_point_sampling(points, nsamples):
-    """(B,N,3) f32 -> (B,nsamples) i32.  sampling.cpp:70-91."""
+def fps_identity_flags(points, nsamples):
+    """(B,n,3) f32 -> (B,) i32 device flags: 0 where FPS(points[b], nsamples) is verified to be 0..nsamples-1 (the input
+    is in FPS order and no step is decided by a tie), 1 where the full algorithm must run (eda_fps_identity_check)."""
+    _contig(points, "points")
+    _is_float(points, "points")
+    _require_cuda_primary(points)
+    lib = _lib.load()
+    B, n = points.size(0), points.size(1)
+    nsamples = int(nsamples)
+    flags = torch.empty((B,), dtype=torch.int32, device=points.device)
+    dsel = torch.empty((B, nsamples), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = lib.eda_fps_identity_check(_p(points), B, n, nsamples, _p(dsel), _p(flags), _stream(points))
+    _lib.check(rc, "fps_identity_check")
+    return flags
+
+
+def furthest_point_sampling(points, nsamples, not_identity=None):
+    """(B,N,3) f32 -> (B,nsamples) i32.  sampling.cpp:70-91.  `not_identity`: optional flags from fps_identity_flags
+    for the same (points, nsamples): verified scenes get 0..nsamples-1 without running the serial algorithm."""
     _contig(points, "points")
     _is_float(points, "points")
     _require_cuda_primary(points)
@@ -67,8 +85,12 @@ def furthest_point_sampling(points, nsamples):
     nbytes = lib.eda_fps_scratch_bytes(B, N, nsamples)
     scratch = torch.empty((nbytes,), dtype=torch.uint8, device=points.device) if nbytes else None
     with torch.cuda.device(points.device):
-        rc = lib.eda_furthest_point_sampling(_p(points), B, N, nsamples, _p(scratch) if nbytes else None, _p(out),
-                                             _stream(points))
+        if not_identity is None:
+            rc = lib.eda_furthest_point_sampling(_p(points), B, N, nsamples, _p(scratch) if nbytes else None, _p(out),
+                                                 _stream(points))
+        else:
+            rc = lib.eda_furthest_point_sampling_ex(_p(points), B, N, nsamples, _p(scratch) if nbytes else None, _p(out),
+                                                    None, 0, _p(not_identity), _stream(points))
     _lib.check(rc, "furthest_point_sampling")
     return out
 

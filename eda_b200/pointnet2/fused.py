@@ -364,8 +364,9 @@ class PipelinedFPS:
         _lib.check(rc, "stream_wait_value32")
 
 
-def launch_pipelined_fps(xyz, npoint, every, stream):
-    """Launches FPS(xyz, npoint) on `stream` with progress milestones.  Returns a PipelinedFPS."""
+def launch_pipelined_fps(xyz, npoint, every, stream, not_identity=None):
+    """Launches FPS(xyz, npoint) on `stream` with progress milestones.  Returns a PipelinedFPS.  `not_identity`:
+    optional device flags from _ext.fps_identity_flags (verified scenes publish all milestones at once)."""
     lib = _lib.load()
     B, N, _ = xyz.shape
     counter = ProgressCounter.get(xyz.device)
@@ -374,8 +375,8 @@ def launch_pipelined_fps(xyz, npoint, every, stream):
         nbytes = lib.eda_fps_scratch_bytes(B, N, npoint)
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=xyz.device) if nbytes else None
         with torch.cuda.device(xyz.device):
-            rc = lib.eda_furthest_point_sampling_progress(_p(xyz), B, N, npoint, _p(scratch), _p(inds), _p(counter.word),
-                                                          int(every), ctypes.c_void_p(stream.cuda_stream))
+            rc = lib.eda_furthest_point_sampling_ex(_p(xyz), B, N, npoint, _p(scratch), _p(inds), _p(counter.word),
+                                                    int(every), _p(not_identity), ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "furthest_point_sampling_progress")
         base = counter.total
         counter.total += B * ((npoint + every - 1) // every)

@@ -58,6 +58,16 @@ EDA_API unsigned long long eda_launch_count(void);
  * running minima live in registers and scratch is only needed by the large-N fallback.
  */
 EDA_API size_t eda_fps_scratch_bytes(int B, int N, int m);
+/* FPS of an FPS-ordered set (the backbone's stages 2-4 sample from the previous stage's output):
+ * eda_fps_identity_check verifies, in parallel and with the reference's exact distance arithmetic, whether the answer for
+ * scene b is 0, 1, ..., m-1 — true iff at every step i < m point i is the STRICT maximiser of the running minimum, so
+ * no tie-break is involved — and writes not_identity[b] = 0 (verified) or 1 (ties, duplicates, skipped points, NaNs:
+ * run the real thing).  dsel is scratch (B*m floats).  eda_furthest_point_sampling_ex is eda_furthest_point_sampling
+ * (+ optional progress milestones) that consults such a flag array on the device: verified scenes get the identity
+ * immediately, the others the full algorithm — bit-exact either way, no host synchronisation. */
+EDA_API int eda_fps_identity_check(const float *xyz, int B, int n, int m, float *dsel, int *not_identity, void *stream);
+EDA_API int eda_furthest_point_sampling_ex(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
+                                           int *progress, int every, const int *not_identity, void *stream);
 EDA_API int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
                                 void *stream);
 

@@ -83,3 +83,43 @@ def test_pipelined_sa1_equals_plain(every):
             assert torch.equal(got_inds, want_inds)
             assert torch.equal(got_xyz, want_xyz)
             assert torch.equal(got_f, want_f)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["surface", "uniform", "dup", "lattice", "origin"])
+def test_fps_identity_shortcut_is_bit_exact(family):
+    """Stages 2-4 of the backbone sample from FPS-ordered sets.  The parallel identity check +
+    flag-consulting sampler must return exactly what the full serial algorithm (and hence the reference) returns:
+    the identity where every step has a strict maximiser, the full result where ties / duplicates decide."""
+    from eda_b200.pointnet2 import _ext
+    from oracle import pointnet2_oracle as orc
+
+    B, N = 3, 20000
+    xyz = synthetic.point_clouds(B, N, family, channels=0).cuda().contiguous()
+    inds1 = _ext.furthest_point_sampling(xyz, 2048)
+    sub = torch.gather(xyz, 1, inds1.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    for n, m in ((2048, 1024), (1024, 512), (512, 256)):
+        cur = sub[:, :n].contiguous()
+        full = _ext.furthest_point_sampling(cur, m)
+        flags = _ext.fps_identity_flags(cur, m)
+        short = _ext.furthest_point_sampling(cur, m, not_identity=flags)
+        assert torch.equal(short, full), (family, n, m)
+        assert torch.equal(full.cpu(), orc.furthest_point_sampling(cur.cpu(), m))  # and both equal the oracle
+        ident = torch.arange(m, dtype=torch.int32, device="cuda")
+        for b in range(B):
+            if flags[b].item() == 0:
+                assert torch.equal(full[b], ident)       # verified scenes really are the identity
+        if family in ("surface", "uniform"):
+            assert flags.sum().item() == 0                # continuous data: no ties, the shortcut is taken
+        if family == "lattice":
+            assert flags.sum().item() == B                # every step is a tie: always the full algorithm
+    # a set that is NOT in FPS order is never reported as verified
+    perm = torch.randperm(2048, generator=torch.Generator().manual_seed(0)).cuda()
+    shuffled = sub[:, perm].contiguous()
+    flags = _ext.fps_identity_flags(shuffled, 1024)
+    assert flags.sum().item() == B
+    assert torch.equal(_ext.furthest_point_sampling(shuffled, 1024, not_identity=flags),
+                       _ext.furthest_point_sampling(shuffled, 1024))
+    # the sampler obeys the flags (forced zeros -> identity), i.e. the flags are what decides
+    forced = _ext.furthest_point_sampling(shuffled, 1024, not_identity=torch.zeros(B, dtype=torch.int32, device="cuda"))
+    assert torch.equal(forced, torch.arange(1024, dtype=torch.int32, device="cuda").expand(B, -1))
