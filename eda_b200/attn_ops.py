@@ -32,7 +32,10 @@ def _p(t):
 
 
 def _stream(dev):
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    # torch.cuda.current_stream() builds a Python Stream object through several pure-Python helpers (~5 us); the raw
+    # handle is all the C ABI needs
+    idx = dev.index
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch.cuda.current_device()))
 
 
 def _require_cuda(t, name="input"):

@@ -10,6 +10,19 @@ void set_last_cuda_error(cudaError_t e, const char *where) {
 }
 static const uint32_t *g_dropout_epoch = nullptr;
 const uint32_t *dropout_epoch_ptr() { return __atomic_load_n(&g_dropout_epoch, __ATOMIC_RELAXED); }
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int v = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+  if (v == 0) {
+    v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    __atomic_store_n(&cached[dev], v, __ATOMIC_RELAXED);
+  }
+  return v;
+}
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 }  // namespace eda

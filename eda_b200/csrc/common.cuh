@@ -148,6 +148,9 @@ __device__ __forceinline__ uint32_t effective_seed(uint32_t seed, const uint32_t
   return epoch ? seed + __ldg(epoch) : seed;
 }
 
+// SM count of the current device (cached per device: cudaDeviceGetAttribute costs ~1 us per call on the launch path).
+int sm_count();
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace eda

@@ -328,9 +328,7 @@ int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *st
   if (max_rows == 0) return EDA_OK;
   p.nprobs = nprobs; p.N = N; p.K = K;
   const int nt = (N + kWgTile - 1) / kWgTile, kt = (K + kWgTile - 1) / kWgTile;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   // enough row splits to fill the chip a few times over, but at least 128 rows per split
   long long splits = (4LL * sms + (long long)nt * kt * nprobs - 1) / ((long long)nt * kt * nprobs);
   const long long max_splits = (max_rows + 127) / 128;

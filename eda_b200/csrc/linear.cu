@@ -613,9 +613,7 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
   p.seed_epoch = dropout_epoch_ptr();
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   p.S = lin_splits(N, tiles, sms);
   p.NS = N / p.S;
   const int NS = p.NS;

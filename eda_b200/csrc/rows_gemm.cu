@@ -166,9 +166,7 @@ extern "C" int eda_rows_gemm(const float *x, int ldx, const float *in_scale, con
                    "rows_gemm smem attr");
     smem_set[which] = smem;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int ny = (N + kRgNc - 1) / kRgNc;
   long long gx = sms / ny;
   if (gx < 1) gx = 1;

@@ -590,9 +590,7 @@ static int sa_mlp_forward_impl(const float *xyz, const float *new_xyz, const int
                  "sa smem attr");
     attr_set = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
   sa_mlp_kernel<<<grid, kThreads, smem, st>>>(p);
   return check_launch("sa_mlp_kernel");

@@ -52,7 +52,8 @@ def _p(t):
 
 
 def _stream(t):
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    idx = t.device.index
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch.cuda.current_device()))
 
 
 def fps_identity_flags(points, nsamples):

@@ -22,7 +22,8 @@ def _p(t):
 
 
 def _stream(dev):
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    idx = dev.index
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch.cuda.current_device()))
 
 
 def transpose_last2(x):
