@@ -202,7 +202,7 @@ def gpu_arm(args):
     from eda_b200.backbone_module import fps_chain
     from eda_b200.pointnet2 import fused
 
-    PIPELINE_EVERY = 0 if args.no_pipeline else (512, 256)
+    PIPELINE_EVERY = 0 if args.no_pipeline else tuple(int(v) for v in os.environ.get("EDA_BENCH_PIPELINE", "512,1024").split(","))
     from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -331,8 +331,9 @@ def gpu_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "n_points": N_POINTS,
                    "l2": "512 MB memset between timed steps (inputs 9.6 MB < L2)", "sharding": "batch only, no collective",
-                   "overlap": ("ball query + fused MLP of each SA stage run on finished chunks of centres (512 / 256) while "
-                               "that stage's FPS continues on a side stream") if PIPELINE_EVERY else "SA2 FPS on a side stream",
+                   "overlap": ("SA1's ball query + fused MLP run on finished chunks of %d centres while its FPS continues on a "
+                               "side stream; SA2's FPS (of an FPS-ordered set) is the verified identity shortcut"
+                               % PIPELINE_EVERY[0]) if PIPELINE_EVERY else "SA2 FPS on a side stream",
                    "index_paths": "fp32, bit-exact", "mlp": "tcgen05 kind::tf32, fp32 accumulate"},
         "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},

@@ -84,7 +84,9 @@ class Pointnet2Backbone(nn.Module):
         self.overlap_fps = True  # False: plain back-to-back stages (tests compare the two)
         # inference only: SA1 consumes the sampler's output in chunks of this many centres while FPS is still
         # running (0 = off; also off under autograd, in training mode and inside CUDA-graph capture)
-        self.pipeline_every = (512, 256)  # SA1, SA2 (SA3 / SA4 are too small to matter)
+        # SA1: chunks of 512 centres; SA2: one chunk (its FPS is normally the verified identity shortcut, so all centres
+        # arrive at once and chunking would only add launches); SA3 / SA4 are too small to matter
+        self.pipeline_every = (512, 1024)
         self._side = None
 
     def _break_up_pc(self, pc):
