@@ -204,6 +204,52 @@ bn_relu_backward_apply_kernel(float4 *__restrict__ da, const float4 *__restrict_
   }
 }
 
+// per-channel (sum, sum of squares) of z (rows, C) -> fp64 accumulators (train-mode BatchNorm statistics of the
+// row-major training forward)
+__global__ void __launch_bounds__(256)
+col_stats_kernel(const float4 *__restrict__ z, long long rows, int C, double *__restrict__ stats) {
+  // Every thread owns a fixed set of rows and 4 columns; the row lanes of a column are then summed in a fixed order and
+  // each block contributes ONE fp64 atomic per entry, so the result does not depend on scheduling beyond fp64 rounding
+  // (train-mode outputs stay reproducible from run to run; see csrc/sa_mlp.cu for why that matters with tf32).
+  __shared__ float s_part[2048];  // [row lane][2 C]: rstep * 2 C = 2048 floats for every C
+  const int c4n = C >> 2;
+  const int col = threadIdx.x % c4n, lane_r = threadIdx.x / c4n, rstep = blockDim.x / c4n;
+  const int c = col << 2;
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+  if (lane_r < rstep) {
+    for (long long r = (long long)blockIdx.x * rstep + lane_r; r < rows; r += (long long)gridDim.x * rstep) {
+      const float4 v = __ldg(z + r * c4n + col);
+      a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+      a2.x = fmaf(v.x, v.x, a2.x); a2.y = fmaf(v.y, v.y, a2.y); a2.z = fmaf(v.z, v.z, a2.z); a2.w = fmaf(v.w, v.w, a2.w);
+    }
+    float *dst = s_part + (size_t)lane_r * 2 * C;
+    dst[c + 0] = a1.x; dst[c + 1] = a1.y; dst[c + 2] = a1.z; dst[c + 3] = a1.w;
+    dst[C + c + 0] = a2.x; dst[C + c + 1] = a2.y; dst[C + c + 2] = a2.z; dst[C + c + 3] = a2.w;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    double acc = 0.0;
+    for (int l = 0; l < rstep; ++l) acc += (double)s_part[(size_t)l * 2 * C + i];
+    atomicAdd(stats + i, acc);
+  }
+}
+
+// out[j][c] = max(0, max_s (z3[j*S + s][c] * scale[c] + shift[c])): BatchNorm-3 + ReLU + max-pool of the row-major
+// training forward; thread = channel, block loops over centres
+__global__ void __launch_bounds__(256)
+sa_pool_forward_kernel(const float *__restrict__ z3, const float *__restrict__ scale, const float *__restrict__ shift,
+                       long long centres, int S, int C, float *__restrict__ out) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+  for (long long j = blockIdx.x; j < centres; j += gridDim.x) {
+    const float *zr = z3 + j * S * (long long)C + c;
+    float best = 0.f;
+    for (int s = 0; s < S; ++s) best = fmaxf(best, fmaf(__ldg(zr + (long long)s * C), sc, sh));
+    out[j * C + c] = best;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sa_scatter_rows_kernel(const float *__restrict__ dx0, const int *__restrict__ idx, long long total_rows, int N, int MS,
                        int C, int K0pad, float *__restrict__ dfeat) {
@@ -317,6 +363,27 @@ int eda_bn_relu_backward_apply(float *da, const float *z, const float *scale, co
       reinterpret_cast<float4 *>(da), reinterpret_cast<const float4 *>(z), scale, shift, mean, invstd, stats,
       batch_stats ? (float)(1.0 / count) : 0.f, batch_stats, n4, C);
   return check_launch("bn_relu_backward_apply_kernel");
+}
+
+int eda_col_stats(const float *z, long long rows, int C, double *stats, void *stream) {
+  using namespace eda;
+  if (rows < 0 || C < 4 || (C & 3) || C > 512) return EDA_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return EDA_OK;
+  if (!z || !stats || !al16(z)) return EDA_ERR_INVALID_ARGUMENT;
+  const int rstep = 256 / (C >> 2);
+  col_stats_kernel<<<grid_for(rows, rstep * 8, 148 * 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4 *>(z),
+                                                                                   rows, C, stats);
+  return check_launch("col_stats_kernel");
+}
+
+int eda_sa_pool_forward(const float *z3, const float *scale, const float *shift, long long centres, int S, int C,
+                        float *out, void *stream) {
+  using namespace eda;
+  if (centres < 0 || S <= 0 || C < 1 || C > 256) return EDA_ERR_INVALID_ARGUMENT;
+  if (centres == 0) return EDA_OK;
+  if (!z3 || !scale || !shift || !out) return EDA_ERR_INVALID_ARGUMENT;
+  sa_pool_forward_kernel<<<grid_for(centres, 1, 148 * 8), 256, 0, as_stream(stream)>>>(z3, scale, shift, centres, S, C, out);
+  return check_launch("sa_pool_forward_kernel");
 }
 
 int eda_sa_scatter_rows(const float *dx0, const int *idx, int B, int N, int M, int S, int C, int K0pad, float *dfeat,

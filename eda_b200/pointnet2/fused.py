@@ -1,8 +1,10 @@
 """Host side of the fused set-abstraction kernel (eda_sa_mlp_forward): parameter folding, the
 train-mode BatchNorm statistics passes, layout bookkeeping and the autograd boundary.
 
-Forward is entirely hand-written CUDA (pack -> [stats pass -> finalize] x3 in train mode -> fused
-gather+MLP+max-pool).  Backward is hand-written CUDA too (csrc/sa_bwd.cu + the GEMM kernels): the grouped rows are
+Forward is entirely hand-written CUDA: inference and no-grad calls run the fused TMEM-chained kernel (pack ->
+[stats pass -> finalize] x3 in train mode -> fused gather+MLP+max-pool); calls under autograd run the row-major
+formulation (`sa_forward_rows`: gather -> rows GEMM -> column statistics -> ... -> pool) that keeps the pre-activations
+for the backward pass.  Backward is hand-written CUDA too (csrc/sa_bwd.cu + the GEMM kernels): the grouped rows are
 rebuilt row-major, the three layers recomputed on the tcgen05 GEMM, and max-pool / ReLU / BatchNorm backward, the
 activation and weight gradients and the feature scatter run as one-pass kernels (see `_sa_backward_cuda`).
 EDA_BACKWARD=torch selects the older path (unfused CUDA ops + autograd through cuDNN), kept as a cross-check.
@@ -148,6 +150,58 @@ def sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, tr
     return out
 
 
+def _w1_permuted(W1, C, K0pad):
+    """Layer-1 weight (C1, 3 + C) in the gathered column order [features | xyz | pad] (reference: [xyz | features])."""
+    W1p = torch.zeros((W1.size(0), K0pad), dtype=torch.float32, device=W1.device)
+    W1p[:, :C] = W1[:, 3:]
+    W1p[:, C:C + 3] = W1[:, :3]
+    return W1p
+
+
+def sa_forward_rows(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, training, state):
+    """Training forward of one SA stage in the row-major formulation the backward pass uses, KEEPING the
+    pre-activations: x0 = gather, z_l = relu(bn(z_{l-1})) W_l^T (eda_rows_gemm with the BatchNorm + ReLU prologue),
+    batch statistics by eda_col_stats -> eda_bn_finalize, out = max-pool(relu(bn(z3))) (eda_sa_pool_forward).
+    Same arithmetic class as the fused kernel (tf32 operands, fp32 accumulation); what it buys is that the backward
+    pass starts from (x0, z1, z2, z3) instead of recomputing them (1.5 ms per step at B = 8).
+    Returns out (B,M,C3) point-major and the tuple (x0, z1, z2, z3); `state` receives (scale, shift, [mean, invstd])."""
+    from .. import attn_ops as ops
+
+    lib = _lib.load()
+    dev = xyz.device
+    stream = _stream(dev)
+    B, N, _ = xyz.shape
+    M, S = idx.size(1), idx.size(2)
+    C = 0 if feat_pm is None else feat_pm.size(2)
+    widths = [conv.out_channels for conv, _ in layers]
+    K0pad = ((C + 3 + 15) // 16) * 16
+    R = B * M * S
+    feat_stride = 0 if feat_pm is None else feat_pm.stride(1)
+    Ws = [conv.weight.detach().reshape(conv.out_channels, -1) for conv, _ in layers]
+    Wl = [_w1_permuted(Ws[0], C, K0pad), Ws[1], Ws[2]]
+    with torch.cuda.device(dev):
+        x0 = torch.empty((R, K0pad), dtype=torch.float32, device=dev)
+        rc = lib.eda_sa_gather_rows(_p(xyz), _p(new_xyz), _p(feat_pm), feat_stride, _p(idx), B, N, M, S, C, K0pad,
+                                    float(radius), 1 if normalize_xyz else 0, _p(x0), stream)
+        _lib.check(rc, "sa_gather_rows")
+        zs, xin, sc, sh = [], x0, None, None
+        for l, (conv, bn) in enumerate(layers):
+            z = ops.rows_gemm(xin, Wl[l], in_scale=sc, in_shift=sh)
+            if training:
+                stats = torch.zeros(2 * widths[l], dtype=torch.float64, device=dev)
+                _lib.check(lib.eda_col_stats(_p(z), R, widths[l], _p(stats), stream), "col_stats")
+                sc, sh, mi = _bn_scale_shift(lib, dev, stats, float(R), bn, conv.bias, widths[l], True, want_stats=True)
+            else:
+                sc, sh, mi = _bn_scale_shift(lib, dev, None, 0.0, bn, conv.bias, widths[l], False, want_stats=True)
+            state.append((sc, sh, mi))
+            zs.append(z)
+            xin = z
+        out = torch.empty((B, M, widths[2]), dtype=torch.float32, device=dev)
+        rc = lib.eda_sa_pool_forward(_p(zs[2]), _p(sc), _p(sh), B * M, S, widths[2], _p(out), stream)
+        _lib.check(rc, "sa_pool_forward")
+    return out, (x0, zs[0], zs[1], zs[2])
+
+
 def _composed(xyz, new_xyz, features, idx, params, has_bn, radius, normalize_xyz, use_batch_stats, running, eps):
     """Unfused, differentiable restatement (used for the backward pass only)."""
     from . import pointnet2_utils as pu
@@ -191,8 +245,16 @@ class FusedSAFunction(torch.autograd.Function):
             # conv weights of layers 2 / 3 whose gradient buffers exist: their wgrad kernels accumulate straight
             # into them from the side stream (attn_ops.FUSED_WGRAD); layer 1 needs a column permutation, so it stays
             ctx.gbufs = attn_ops._grad_buffers((params[4], params[8]))
-        out_pm = sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, module.radius, module.normalize_xyz, training,
-                                state=ctx.state)
+        ctx.rows = None
+        if ctx.cuda_bw and training and os.environ.get("EDA_SA_RECOMPUTE", "0") != "1":
+            # training mode: keep the row-major pre-activations for the backward pass (EDA_SA_RECOMPUTE=1, and eval mode
+            # under autograd: fused forward kernel, the backward recomputes them — 1.9 GB less activation memory at
+            # B = 8, 1 ms more per step)
+            out_pm, ctx.rows = sa_forward_rows(xyz, new_xyz.contiguous(), feat_pm, idx, layers, module.radius,
+                                               module.normalize_xyz, training, ctx.state)
+        else:
+            out_pm = sa_forward_raw(xyz, new_xyz, feat_pm, idx, layers, module.radius, module.normalize_xyz, training,
+                                    state=ctx.state)
         out = transpose_last2(out_pm)
         ctx.save_for_backward(xyz, new_xyz, features, idx, *params)
         ctx.meta = (has_bn, float(module.radius), bool(module.normalize_xyz), training,
@@ -250,24 +312,28 @@ def _sa_backward_cuda(ctx, grad_out):
         _lib.check(rc, what)
 
     with torch.cuda.device(dev):
-        # ---- recompute the forward, row-major ----------------------------------------------------------------
-        x0 = torch.empty((R, K0pad), **f32)
-        chk(lib.eda_sa_gather_rows(_p(xyz), _p(new_xyz), _p(feat_pm), feat_stride, _p(idx), B, N, M, S, C, K0pad,
-                                   float(radius), 1 if normalize_xyz else 0, _p(x0), stream), "sa_gather_rows")
-        # layer-1 weight in the gathered column order [features | xyz | pad] (reference order: [xyz | features])
-        W1p = torch.zeros((widths[0], K0pad), **f32)
-        W1p[:, :C] = Ws[0][:, 3:]
-        W1p[:, C:C + 3] = Ws[0][:, :3]
+        W1p = _w1_permuted(Ws[0], C, K0pad)
         Wl = [W1p, Ws[1], Ws[2]]
         Kin = [K0pad, widths[0], widths[1]]
         # input of layer l as (tensor, scale, shift): layer 1 reads x0 as it is, layers 2 / 3 read relu(bn(z_{l-1}))
-        z = [None] * 3
-        src = [(x0, None, None)]
-        for l in range(3):
-            xin, sc, sh = src[l]
-            z[l] = ops.rows_gemm(xin, Wl[l], in_scale=sc, in_shift=sh)
-            if l < 2:
-                src.append((z[l], ctx.state[l][0], ctx.state[l][1]))
+        if ctx.rows is not None:
+            # the training forward kept them (sa_forward_rows); z3 is overwritten in place below, so they serve once
+            x0, z0, z1, z2 = ctx.rows
+            ctx.rows = None
+            z = [z0, z1, z2]
+            src = [(x0, None, None), (z0, ctx.state[0][0], ctx.state[0][1]), (z1, ctx.state[1][0], ctx.state[1][1])]
+        else:
+            # ---- recompute the forward, row-major ------------------------------------------------------------
+            x0 = torch.empty((R, K0pad), **f32)
+            chk(lib.eda_sa_gather_rows(_p(xyz), _p(new_xyz), _p(feat_pm), feat_stride, _p(idx), B, N, M, S, C, K0pad,
+                                       float(radius), 1 if normalize_xyz else 0, _p(x0), stream), "sa_gather_rows")
+            z = [None] * 3
+            src = [(x0, None, None)]
+            for l in range(3):
+                xin, sc, sh = src[l]
+                z[l] = ops.rows_gemm(xin, Wl[l], in_scale=sc, in_shift=sh)
+                if l < 2:
+                    src.append((z[l], ctx.state[l][0], ctx.state[l][1]))
         # ---- layer 3: max-pool + ReLU + BatchNorm backward -----------------------------------------------------
         g_pm = transpose_last2(grad_out.contiguous())  # (B, M, C3)
         stats = [torch.zeros(2 * widths[l], **f32) for l in range(3)]

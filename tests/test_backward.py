@@ -257,9 +257,11 @@ def test_sa_backward_cuda_vs_torch_at_backbone_shapes(training):
 
     got = _block_grads("cuda", run)
     want = _block_grads("torch", run)
-    # same forward kernels; train-mode batch statistics are accumulated with atomics, so only eval is bit-identical
+    # eval mode: the same fused forward kernel in both runs -> bit-identical.  Train mode: the CUDA-backward run uses
+    # the row-major forward that keeps its activations (sa_forward_rows), the cross-check run the fused TMEM kernel:
+    # same tf32 arithmetic class, different kernels
     if training:
-        torch.testing.assert_close(got["f2"], want["f2"], rtol=1e-3, atol=1e-3)
+        assert rel(got["f2"], want["f2"]) <= 5e-3
     else:
         assert torch.equal(got["f2"], want["f2"])
     errs = {n: rel(got[n], want[n]) for n in want}
