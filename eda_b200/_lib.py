@@ -78,7 +78,8 @@ PROTOTYPES = {
     "eda_bn_relu_backward_apply": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _c_int, ctypes.c_longlong,
                                             _c_int, _vp]),
     "eda_col_stats": (_c_int, [_vp, ctypes.c_longlong, _c_int, _vp, _vp]),
-    "eda_sa_pool_forward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _c_int, _c_int, _vp, _vp]),
+    "eda_sa_pool_forward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _c_int, _c_int, _vp, _vp, _vp]),
+    "eda_sa_pool_backward_stats": (_c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _c_int, _c_int, _vp, _vp]),
     "eda_sa_scatter_rows": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_selftest_umma": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_selftest_umma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),

@@ -238,16 +238,43 @@ col_stats_kernel(const float4 *__restrict__ z, long long rows, int C, double *__
 // training forward; thread = channel, block loops over centres
 __global__ void __launch_bounds__(256)
 sa_pool_forward_kernel(const float *__restrict__ z3, const float *__restrict__ scale, const float *__restrict__ shift,
-                       long long centres, int S, int C, float *__restrict__ out) {
+                       long long centres, int S, int C, float *__restrict__ out, int *__restrict__ amax) {
   const int c = threadIdx.x;
   if (c >= C) return;
   const float sc = __ldg(scale + c), sh = __ldg(shift + c);
   for (long long j = blockIdx.x; j < centres; j += gridDim.x) {
     const float *zr = z3 + j * S * (long long)C + c;
     float best = 0.f;
-    for (int s = 0; s < S; ++s) best = fmaxf(best, fmaf(__ldg(zr + (long long)s * C), sc, sh));
+    int bi = -1;  // first row that attains the maximum, -1 when nothing is positive (same rule as sa_pool_backward_kernel)
+    for (int s = 0; s < S; ++s) {
+      const float y = fmaf(__ldg(zr + (long long)s * C), sc, sh);
+      if (y > best) { best = y; bi = s; }
+    }
     out[j * C + c] = best;
+    if (amax) amax[j * C + c] = bi;
   }
+}
+
+// BatchNorm-3 reductions from a saved arg-max: stats[0:C] += sum dy, stats[C:2C] += sum dy * zhat, dy = grad_out at amax
+__global__ void __launch_bounds__(256)
+sa_pool_backward_stats_kernel(const float *__restrict__ z3, const int *__restrict__ amax, const float *__restrict__ mean,
+                              const float *__restrict__ invstd, const float *__restrict__ gout, long long centres, int S,
+                              int C, float *__restrict__ stats) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const float mu = __ldg(mean + c), is = __ldg(invstd + c);
+  float s1 = 0.f, s2 = 0.f;
+  for (long long j = blockIdx.x; j < centres; j += gridDim.x) {
+    const int bi = __ldg(amax + j * C + c);
+    if (bi >= 0) {
+      const float dy = __ldg(gout + j * C + c);
+      const float zv = __ldg(z3 + (j * S + bi) * (long long)C + c);
+      s1 += dy;
+      s2 = fmaf(dy, (zv - mu) * is, s2);
+    }
+  }
+  atomicAdd(stats + c, s1);
+  atomicAdd(stats + C + c, s2);
 }
 
 __global__ void __launch_bounds__(256)
@@ -376,13 +403,25 @@ int eda_col_stats(const float *z, long long rows, int C, double *stats, void *st
   return check_launch("col_stats_kernel");
 }
 
+int eda_sa_pool_backward_stats(const float *z3, const int *amax, const float *mean, const float *invstd,
+                               const float *grad_out, long long centres, int S, int C, float *stats, void *stream) {
+  using namespace eda;
+  if (centres < 0 || S <= 0 || C < 1 || C > 256) return EDA_ERR_INVALID_ARGUMENT;
+  if (centres == 0) return EDA_OK;
+  if (!z3 || !amax || !mean || !invstd || !grad_out || !stats) return EDA_ERR_INVALID_ARGUMENT;
+  sa_pool_backward_stats_kernel<<<grid_for(centres, 4, 148 * 8), 256, 0, as_stream(stream)>>>(z3, amax, mean, invstd, grad_out,
+                                                                                          centres, S, C, stats);
+  return check_launch("sa_pool_backward_stats_kernel");
+}
+
 int eda_sa_pool_forward(const float *z3, const float *scale, const float *shift, long long centres, int S, int C,
-                        float *out, void *stream) {
+                        float *out, int *amax, void *stream) {
   using namespace eda;
   if (centres < 0 || S <= 0 || C < 1 || C > 256) return EDA_ERR_INVALID_ARGUMENT;
   if (centres == 0) return EDA_OK;
   if (!z3 || !scale || !shift || !out) return EDA_ERR_INVALID_ARGUMENT;
-  sa_pool_forward_kernel<<<grid_for(centres, 1, 148 * 8), 256, 0, as_stream(stream)>>>(z3, scale, shift, centres, S, C, out);
+  sa_pool_forward_kernel<<<grid_for(centres, 1, 148 * 8), 256, 0, as_stream(stream)>>>(z3, scale, shift, centres, S, C, out,
+                                                                                   amax);
   return check_launch("sa_pool_forward_kernel");
 }
 

@@ -197,9 +197,10 @@ def sa_forward_rows(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, t
             zs.append(z)
             xin = z
         out = torch.empty((B, M, widths[2]), dtype=torch.float32, device=dev)
-        rc = lib.eda_sa_pool_forward(_p(zs[2]), _p(sc), _p(sh), B * M, S, widths[2], _p(out), stream)
+        amax = torch.empty((B * M, widths[2]), dtype=torch.int32, device=dev)
+        rc = lib.eda_sa_pool_forward(_p(zs[2]), _p(sc), _p(sh), B * M, S, widths[2], _p(out), _p(amax), stream)
         _lib.check(rc, "sa_pool_forward")
-    return out, (x0, zs[0], zs[1], zs[2])
+    return out, (x0, zs[0], zs[1], zs[2], amax)
 
 
 def _composed(xyz, new_xyz, features, idx, params, has_bn, radius, normalize_xyz, use_batch_stats, running, eps):
@@ -316,9 +317,10 @@ def _sa_backward_cuda(ctx, grad_out):
         Wl = [W1p, Ws[1], Ws[2]]
         Kin = [K0pad, widths[0], widths[1]]
         # input of layer l as (tensor, scale, shift): layer 1 reads x0 as it is, layers 2 / 3 read relu(bn(z_{l-1}))
+        amax = None
         if ctx.rows is not None:
             # the training forward kept them (sa_forward_rows); z3 is overwritten in place below, so they serve once
-            x0, z0, z1, z2 = ctx.rows
+            x0, z0, z1, z2, amax = ctx.rows
             ctx.rows = None
             z = [z0, z1, z2]
             src = [(x0, None, None), (z0, ctx.state[0][0], ctx.state[0][1]), (z1, ctx.state[1][0], ctx.state[1][1])]
@@ -339,9 +341,13 @@ def _sa_backward_cuda(ctx, grad_out):
         stats = [torch.zeros(2 * widths[l], **f32) for l in range(3)]
         dWl = [torch.zeros((widths[l], Kin[l]), **f32) for l in range(3)]
         scale, shift, mi = ctx.state[2]
-        amax = torch.empty((B * M, widths[2]), dtype=torch.int32, device=dev)
-        chk(lib.eda_sa_pool_backward(_p(z[2]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), _p(g_pm), B * M, S, widths[2],
-                                     _p(amax), _p(stats[2]), stream), "sa_pool_backward")
+        if amax is not None:  # saved by the training forward: only the reductions are left to do
+            chk(lib.eda_sa_pool_backward_stats(_p(z[2]), _p(amax), _p(mi[0]), _p(mi[1]), _p(g_pm), B * M, S, widths[2],
+                                               _p(stats[2]), stream), "sa_pool_backward_stats")
+        else:
+            amax = torch.empty((B * M, widths[2]), dtype=torch.int32, device=dev)
+            chk(lib.eda_sa_pool_backward(_p(z[2]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), _p(g_pm), B * M, S,
+                                         widths[2], _p(amax), _p(stats[2]), stream), "sa_pool_backward")
         chk(lib.eda_sa_pool_backward_apply(_p(z[2]), _p(amax), _p(g_pm), _p(scale), _p(mi[0]), _p(mi[1]), _p(stats[2]),
                                            float(R), 1 if training else 0, B * M, S, widths[2], stream),
             "sa_pool_backward_apply")

@@ -346,10 +346,15 @@ EDA_API int eda_bn_relu_backward_apply(float *da, const float *z, const float *s
 /* Row-major TRAINING forward of the same stage (activations are kept for the backward pass instead of being
  * recomputed): z_l from eda_rows_gemm, then
  *   eda_col_stats        stats[0:C] += sum_r z[r][c], stats[C:2C] += sum_r z[r][c]^2 (fp64; zero first) -> eda_bn_finalize
- *   eda_sa_pool_forward  out (centres, C) = max(0, max_s (z3 * scale + shift)) over the S rows of each centre */
+ *   eda_sa_pool_forward  out (centres, C) = max(0, max_s (z3 * scale + shift)) over the S rows of each centre; optional
+ *                        amax (centres, C): the first row attaining it, -1 where nothing is positive
+ *   eda_sa_pool_backward_stats  the reductions of eda_sa_pool_backward from such a saved amax (no scan over S) */
 EDA_API int eda_col_stats(const float *z, long long rows, int C, double *stats, void *stream);
 EDA_API int eda_sa_pool_forward(const float *z3, const float *scale, const float *shift, long long centres, int S, int C,
-                                float *out, void *stream);
+                                float *out, int *amax, void *stream);
+EDA_API int eda_sa_pool_backward_stats(const float *z3, const int *amax, const float *mean, const float *invstd,
+                                       const float *grad_out, long long centres, int S, int C, float *stats,
+                                       void *stream);
 EDA_API int eda_sa_scatter_rows(const float *dx0, const int *idx, int B, int N, int M, int S, int C, int K0pad,
                                 float *dfeat, void *stream);
 

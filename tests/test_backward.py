@@ -371,6 +371,20 @@ def test_sa_pool_bn_relu_backward_kernels(training, S, C):
     assert rel(z_work, zd.grad) <= 2e-3
     assert rel(stats[:C], bd.grad) <= 2e-3 and rel(stats[C:], gd.grad) <= 2e-3
     assert amax[5].max() <= 0  # the all-identical centre picks row 0 (or is gated off)
+    # the training forward's pool kernel returns the same arg-max, and the reductions follow from it without a scan
+    out_f = torch.empty(centres, C, device="cuda")
+    amax_f = torch.empty(centres, C, dtype=torch.int32, device="cuda")
+    assert lib.eda_sa_pool_forward(_vp(z), _vp(scale), _vp(shift), centres, S, C, _vp(out_f), _vp(amax_f), _stream()) == 0
+    assert torch.equal(amax_f, amax)
+    torch.testing.assert_close(out_f, torch.relu(z * scale + shift).view(centres, S, C).max(dim=1).values, rtol=1e-6, atol=1e-6)
+    stats_f = torch.zeros(2 * C, device="cuda")
+    assert lib.eda_sa_pool_backward_stats(_vp(z), _vp(amax_f), _vp(meanf), _vp(invstdf), _vp(gout), centres, S, C,
+                                          _vp(stats_f), _stream()) == 0
+    torch.testing.assert_close(stats_f, stats, rtol=1e-4, atol=1e-4)  # fp32 sums in a different order
+    cs = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    assert lib.eda_col_stats(_vp(z), R, C, _vp(cs), _stream()) == 0
+    torch.testing.assert_close(cs[:C], z.double().sum(0), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(cs[C:], z.double().pow(2).sum(0), rtol=1e-6, atol=1e-6)
 
     # ---- layers 1 / 2: ReLU + BN ----
     zd.grad = gd.grad = bd.grad = None
