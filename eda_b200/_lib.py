@@ -45,6 +45,7 @@ PROTOTYPES = {
     "eda_transpose_last2": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_linear_packed_floats": (_sz, [_c_int, _c_int]),
     "eda_linear_pack": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp]),
+    "eda_linear_pack_batch": (_c_int, [_vp, _c_int, _c_int, _vp]),
     "eda_linear_forward": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_float, _c_int, _c_float,
                                     ctypes.c_uint, _vp]),
     "eda_dropout_mask": (_c_int, [ctypes.c_uint, _c_float, ctypes.c_longlong, _c_int, ctypes.c_uint, ctypes.c_uint, _vp,

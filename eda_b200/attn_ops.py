@@ -52,6 +52,62 @@ def _require_cuda(t, name="input"):
 PACK_CACHE = True
 
 
+class PackRegistry:
+    """Persistent packed copies of a model's weights that ONE kernel launch refreshes (eda_linear_pack_batch).
+
+    Used by graphs.GraphedTrainStep: while a registry is active (attn_ops.PACK_REGISTRY), pack_weight / pack_weight_t
+    calls that carry a cache key return the registry's buffer for that (module, name) — created and registered on
+    first sight — without launching anything; `refresh()` at the start of every step re-packs all of them from the
+    current parameter values.  Parameters must keep their storage (as in any CUDA-graph training loop)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = {}   # (id(owner), name, transposed) -> packed tensor
+        self.owners = []    # keep the modules alive so ids stay unique
+        self.rows = []      # descriptor rows: w ptr, dst ptr, stride_n, stride_k, N | K << 32, Kpad
+        self.descs = None
+        self.max_elements = 0
+
+    def get(self, owner, name, transposed, W):
+        key = (id(owner), name, transposed)
+        hit = self.entries.get(key)
+        if hit is not None:
+            return hit
+        lib = _lib.load()
+        if transposed:   # packs W^T: N' = W.size(1), K' = W.size(0), element (n, k) = W[k, n]
+            N, K, sn, sk = W.size(1), W.size(0), W.stride(1), W.stride(0)
+        else:
+            N, K, sn, sk = W.size(0), W.size(1), W.stride(0), W.stride(1)
+        n = lib.eda_linear_packed_floats(N, K)
+        if n == 0:
+            raise RuntimeError(f"eda_b200.linear: unsupported weight shape ({N},{K})")
+        packed = torch.empty(n, dtype=torch.float32, device=W.device)
+        with torch.cuda.device(W.device):  # valid from the start; later steps rely on refresh()
+            rc = lib.eda_linear_pack_strided(_p(W), int(sn), int(sk), N, K, _p(packed), _stream(W.device))
+        _lib.check(rc, "linear_pack_strided")
+        kpad = (K + 7) & ~7
+        self.rows.append([W.data_ptr(), packed.data_ptr(), int(sn), int(sk), N | (K << 32), kpad])
+        self.max_elements = max(self.max_elements, N * kpad)
+        self.entries[key] = packed
+        self.owners.append(owner)
+        self.descs = None  # rebuilt by the next refresh()
+        return packed
+
+    def refresh(self):
+        """Re-packs every registered weight on the current stream (one launch)."""
+        if not self.rows:
+            return
+        if self.descs is None:
+            self.descs = torch.tensor(self.rows, dtype=torch.int64).to(self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().eda_linear_pack_batch(_p(self.descs), len(self.rows), int(self.max_elements),
+                                                   _stream(self.device))
+        _lib.check(rc, "linear_pack_batch")
+
+
+PACK_REGISTRY = None
+
+
 def _cache_of(owner):
     """The packed-weight cache lives ON the owning module, so it dies with it (a process-wide dict keyed by
     id() / data_ptr() could hand a new module the packed weights of a dead one whose memory it reuses)."""
@@ -69,6 +125,8 @@ def pack_weight(W, scale=None, cache_key=None):
     lib = _lib.load()
     N, K = W.shape
     cache = None
+    if PACK_REGISTRY is not None and cache_key is not None and scale is None:
+        return PACK_REGISTRY.get(cache_key[0], cache_key[1], False, W.detach())
     if cache_key is not None and scale is None and PACK_CACHE:
         cache = _cache_of(cache_key[0])
         tag = (W.data_ptr(), W._version, N, K, W.device)
@@ -196,6 +254,8 @@ def pack_weight_t(W, cache_key=None):
     Nout, Kin = W.shape
     assert W.stride(1) == 1
     cache = None
+    if PACK_REGISTRY is not None and cache_key is not None:
+        return PACK_REGISTRY.get(cache_key[0], cache_key[1], True, W.detach())
     if cache_key is not None and PACK_CACHE:
         cache = _cache_of(cache_key[0])
         tag = (W.data_ptr(), W._version, Nout, Kin, W.stride(0), W.device)

@@ -501,6 +501,27 @@ __global__ void pack_linear_kernel(const float *__restrict__ W, const float *__r
   }
 }
 
+// Batched variant: block (x, y) packs part of weight y of a descriptor array in device memory.  One launch re-packs
+// every weight of a model (a captured training step does this once per replay instead of ~370 single launches).
+struct PackDesc {
+  const float *w;
+  float *dst;
+  long long sn, sk;
+  int N, K, Kpad, pad_;
+};
+__global__ void pack_linear_batch_kernel(const PackDesc *__restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  const int total = d.N * d.Kpad;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int kb = e / (kKBlock * d.N);
+    const int rem = e - kb * kKBlock * d.N;
+    const int c = rem / (4 * d.N);
+    const int n = (rem >> 2) % d.N;
+    const int k = kb * kKBlock + c * 4 + (rem & 3);
+    d.dst[e] = to_tf32(k < d.K ? d.w[n * d.sn + k * d.sk] : 0.f);
+  }
+}
+
 // How many CTAs share the N columns of a row tile.  A 128 x 288 x 288 tile moves A 147 KB [+ pos], W 332 KB, residual and
 // output 147 KB each through ONE SM, which sustains ~30 B/clk to and from L2 (scripts/lin_ts.py: K loop 14k cycles,
 // residual pass 8k, store pass 5.5k of a 36k-cycle tile), so a launch with few row tiles is bound by per-SM bandwidth
@@ -582,6 +603,19 @@ int eda_linear_pack_strided(const float *W, long long stride_n, long long stride
   pack_linear_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W, nullptr, N, K, kpad_of(K), N,
                                                                          stride_n, stride_k, packed);
   return check_launch("pack_linear_kernel");
+}
+
+int eda_linear_pack_batch(const void *descs_device, int count, int max_elements, void *stream) {
+  using namespace eda;
+  static_assert(sizeof(PackDesc) == sizeof(eda_linear_pack_desc), "descriptor layout");
+  if (count < 0 || max_elements < 0) return EDA_ERR_INVALID_ARGUMENT;
+  if (count == 0 || max_elements == 0) return EDA_OK;
+  if (!descs_device || count > 65535) return EDA_ERR_INVALID_ARGUMENT;
+  int bx = (max_elements + 255) / 256;
+  if (bx > 64) bx = 64;
+  pack_linear_batch_kernel<<<dim3((unsigned)bx, (unsigned)count), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const PackDesc *>(descs_device));
+  return check_launch("pack_linear_batch_kernel");
 }
 
 int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu, const float *ln_gamma,

@@ -62,9 +62,9 @@ class GraphedTrainStep:
         fg.all_reduce_mean(); optimizer.step()
 
     Eagerly the step is ~900 kernel launches of 5-50 us each issued from Python through ctypes / autograd and is bound
-    by that host work; replayed, only the device time remains.  The weight-pack kernels are captured too (the
-    packed-weight caches are switched off during warm-up and capture), so replays after an optimizer step use the
-    updated parameters; BatchNorm running statistics and `num_batches_tracked` are updated by captured device ops.
+    by that host work; replayed, only the device time remains.  Weight packing is captured too — one batched launch at the
+    start of the step refreshes persistent packed copies of every weight (attn_ops.PackRegistry) — so replays after an
+    optimizer step use the updated parameters; BatchNorm running statistics and `num_batches_tracked` are updated by captured device ops.
     Restrictions: fixed shapes; parameters, gradients (FlatGradients) and inputs must stay at their addresses.  Dropout
     (the reference's default 0.1) is supported: the host-drawn seeds are frozen into the graph, and a device epoch word
     that the graph increments once per replay is added to them by the kernels (`self.dropout_epoch`)."""
@@ -90,9 +90,15 @@ class GraphedTrainStep:
         self.dropout_epoch = torch.zeros(1, dtype=torch.int32, device=self.device) if has_dropout else None
         epoch = self.dropout_epoch
 
+        # all packed weights (forward and transposed-for-backward) live in persistent buffers that one kernel launch
+        # refreshes at the start of every step, instead of ~370 pack launches spread over the step
+        self.pack_registry = attn_ops.PackRegistry(self.device)
+        registry = self.pack_registry
+
         def step():
             if epoch is not None:
                 epoch.add_(1)
+            registry.refresh()
             flat_grads.zero()
             loss = loss_fn(model(*self.static_inputs))
             loss.backward()
@@ -101,6 +107,7 @@ class GraphedTrainStep:
 
         saved = attn_ops.PACK_CACHE
         attn_ops.PACK_CACHE = False
+        attn_ops.PACK_REGISTRY = registry
         lib = _lib.load()
         if epoch is not None:
             lib.eda_dropout_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
@@ -117,6 +124,7 @@ class GraphedTrainStep:
                 self.loss = step()
         finally:
             attn_ops.PACK_CACHE = saved
+            attn_ops.PACK_REGISTRY = None
             lib.eda_dropout_set_epoch(None)  # eager launches after this are unaffected; the graph keeps the baked pointer
 
     def __call__(self, *inputs):

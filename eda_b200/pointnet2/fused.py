@@ -245,7 +245,7 @@ class FusedSAFunction(torch.autograd.Function):
             from .. import attn_ops
             # conv weights of layers 2 / 3 whose gradient buffers exist: their wgrad kernels accumulate straight
             # into them from the side stream (attn_ops.FUSED_WGRAD); layer 1 needs a column permutation, so it stays
-            ctx.gbufs = attn_ops._grad_buffers((params[4], params[8]))
+            ctx.gbufs = attn_ops._grad_buffers((params[4], params[8], params[0]))
         ctx.rows = None
         if ctx.cuda_bw and training and os.environ.get("EDA_SA_RECOMPUTE", "0") != "1":
             # training mode: keep the row-major pre-activations for the backward pass (EDA_SA_RECOMPUTE=1, and eval mode
@@ -354,9 +354,23 @@ def _sa_backward_cuda(ctx, grad_out):
         dz = z[2]  # overwritten in place
         z[2] = None
         fused_w = [None, ctx.gbufs[0], ctx.gbufs[1]]
+        g1 = ctx.gbufs[2]  # layer 1: scratch + column permutation, but also off the critical path when a buffer exists
         for l in (2, 1, 0):
             xin, sc, sh = src[l]
-            if fused_w[l] is not None:
+            if l == 0 and g1 is not None:
+                dev_i = dev.index if dev.index is not None else torch.cuda.current_device()
+                cur, side = torch.cuda.current_stream(dev), ops._wgrad_side(dev)
+                side.wait_stream(cur)
+                ops._wgrad_pending.add(dev_i)
+                with torch.cuda.stream(side):
+                    ops.wgrad([dict(dy=dz, x=xin, dw=dWl[0])], widths[0], Kin[0])
+                    gv = g1.view(widths[0], C + 3)
+                    gv[:, :3] += dWl[0][:, C:C + 3]
+                    if C:
+                        gv[:, 3:] += dWl[0][:, :C]
+                for t in (dz, xin, dWl[0]):
+                    t.record_stream(side)
+            elif fused_w[l] is not None:
                 ops.wgrad_side([dict(dy=dz, x=xin, dw=fused_w[l].view(widths[l], Kin[l]), x_scale=sc, x_shift=sh)],
                                widths[l], Kin[l])
             else:
@@ -381,10 +395,10 @@ def _sa_backward_cuda(ctx, grad_out):
     for l in range(3):
         w = params[4 * l]
         if l == 0:
-            dW = torch.cat([dWl[0][:, C:C + 3], dWl[0][:, :C]], dim=1)
+            dW = None if g1 is not None else torch.cat([dWl[0][:, C:C + 3], dWl[0][:, :C]], dim=1)
         else:
-            dW = dWl[l]
-        gps += [None if fused_w[l] is not None else dW.reshape(w.shape), None, stats[l][widths[l]:], stats[l][:widths[l]]]
+            dW = None if fused_w[l] is not None else dWl[l]
+        gps += [None if dW is None else dW.reshape(w.shape), None, stats[l][widths[l]:], stats[l][:widths[l]]]
     return (None, None, None, gf, None, *gps)
 
 

@@ -219,6 +219,16 @@ EDA_API int eda_linear_pack(const float *W, const float *scale, int N, int K, fl
  * activation-gradient GEMM dX = dY W of a layer y = x W^T (autograd's mm backward in the reference). */
 EDA_API int eda_linear_pack_strided(const float *W, long long stride_n, long long stride_k, int N, int K, float *packed,
                                     void *stream);
+/* Batched packing: `descs_device` is an array of `count` descriptors IN DEVICE MEMORY; weight i (N_i, K_i; element (n, k) at
+ * w[n * stride_n + k * stride_k]) is packed into dst_i (eda_linear_packed_floats(N_i, K_i) floats).  max_elements =
+ * max_i N_i * roundup8(K_i).  One launch for all weights of a model. */
+typedef struct eda_linear_pack_desc {
+  const float *w;
+  float *dst;
+  long long stride_n, stride_k;
+  int N, K, Kpad, reserved; /* Kpad = K rounded up to a multiple of 8 */
+} eda_linear_pack_desc;
+EDA_API int eda_linear_pack_batch(const void *descs_device, int count, int max_elements, void *stream);
 EDA_API int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu,
                                const float *ln_gamma, const float *ln_beta, float ln_eps, int layer_norm,
                                float dropout_p, unsigned int dropout_seed, void *stream);

@@ -517,3 +517,38 @@ def test_graphed_train_step_with_dropout_draws_fresh_masks_and_correct_gradients
         assert rel(grads["cuda"], grads["torch"]) <= 2e-2
     finally:
         ops.FUSED_WGRAD = False
+
+
+def test_graphed_train_step_follows_parameter_updates():
+    """Weight packing inside the captured step (one batched launch refreshing persistent packed copies): after an
+    in-place parameter update the replayed step must give the same loss and gradients as an eager step."""
+    from eda_b200 import attn_ops as ops, ddp, encoder_decoder_layers as edl
+    from eda_b200.graphs import GraphedTrainStep
+
+    inp = {k: v.cuda() for k, v in ac.make_inputs("dec_layer").items()}
+    args = [inp["query"], inp["vis"], inp["text"], inp["query_pos"], inp["det"]]
+    tmask, dmask = inp["text_mask"], inp["det_mask"]
+    m = edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.0, "relu", self_position_embedding="loc_learned", butd=True)
+    ac.fill_params(m, seed=5).cuda().eval()
+    wrapper = torch.nn.Module()
+    wrapper.m = m
+    wrapper.forward = lambda q, v, t, qp, d: m(q, v, t, qp, None, tmask, detected_feats=d, detected_mask=dmask)
+    loss_fn = lambda out: out.pow(2).mean()  # noqa: E731
+    try:
+        fg = ddp.FlatGradients(m)
+        step = GraphedTrainStep(wrapper, loss_fn, args, fg)
+        assert len(step.pack_registry.rows) >= 30
+        with torch.no_grad():
+            for prm in m.parameters():
+                prm.mul_(1.05).add_(0.01)  # "optimizer step"
+        lg = step(*args).item()
+        gg = fg.flat.clone()
+        fg.zero()
+        le = loss_fn(wrapper(*args))
+        le.backward()
+        fg.sync()
+        torch.cuda.synchronize()
+        assert abs(lg - le.item()) <= 1e-5 * abs(le.item())
+        assert rel(gg, fg.flat) <= 1e-3
+    finally:
+        ops.FUSED_WGRAD = False
