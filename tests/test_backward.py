@@ -383,8 +383,9 @@ def test_sa_pool_bn_relu_backward_kernels(training, S, C):
     torch.testing.assert_close(stats_f, stats, rtol=1e-4, atol=1e-4)  # fp32 sums in a different order
     cs = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
     assert lib.eda_col_stats(_vp(z), R, C, _vp(cs), _stream()) == 0
-    torch.testing.assert_close(cs[:C], z.double().sum(0), rtol=1e-6, atol=1e-6)
-    torch.testing.assert_close(cs[C:], z.double().pow(2).sum(0), rtol=1e-6, atol=1e-6)
+    # per-thread fp32 partials (a few rows each), fixed-order fp64 beyond that
+    torch.testing.assert_close(cs[:C], z.double().sum(0), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(cs[C:], z.double().pow(2).sum(0), rtol=1e-5, atol=1e-4)
 
     # ---- layers 1 / 2: ReLU + BN ----
     zd.grad = gd.grad = bd.grad = None
