@@ -311,18 +311,27 @@ def _grad_buffers(params):
     return out
 
 
-def wgrad_side(problems, N, K):
+def wgrad_side(problems, N, K, sums=()):
     """eda_wgrad on the side stream, ordered after everything issued on the current stream so far.  Only for
-    problems whose outputs are fused-accumulation buffers (see FUSED_WGRAD)."""
+    problems whose outputs are fused-accumulation buffers (see FUSED_WGRAD).  `sums`: (problem index, a, b) triples —
+    that problem's x is a + b, formed on the side stream too (one elementwise add instead of a second wgrad problem
+    for "x + pos" inputs)."""
     dev = problems[0]["dy"].device
     cur, side = torch.cuda.current_stream(dev), _wgrad_side(dev)
     side.wait_stream(cur)
     _wgrad_pending.add(dev.index if dev.index is not None else torch.cuda.current_device())
     with torch.cuda.stream(side):
+        for i, a, b in sums:
+            problems[i]["x"] = a + b  # allocated and consumed on the side stream
         wgrad(problems, N, K)
-    for pr in problems:  # inputs were allocated on `cur`: keep them alive until the side-stream kernel has run
+    for i, a, b in sums:
+        a.record_stream(side)
+        b.record_stream(side)
+    summed = {i for i, _, _ in sums}
+    for i, pr in enumerate(problems):  # inputs allocated on `cur`: keep them alive until the side-stream kernel has run
         pr["dy"].record_stream(side)
-        pr["x"].record_stream(side)
+        if i not in summed:
+            pr["x"].record_stream(side)
 
 
 def wgrad(problems, N, K):
@@ -600,11 +609,18 @@ class _MHABlockFn(torch.autograd.Function):
         probs = [dict(dy=dq, x=q_in, dw=d_in_w[:E], db=d_in_b[:E]),
                  dict(dy=dk, x=k_in, dw=d_in_w[E:2 * E], db=d_in_b[E:2 * E]),
                  dict(dy=dv, x=v_in, dw=d_in_w[2 * E:], db=d_in_b[2 * E:])]
-        if q_pos is not None:
-            probs.append(dict(dy=dq, x=q_pos.contiguous(), dw=d_in_w[:E]))
-        if k_pos is not None:
-            probs.append(dict(dy=dk, x=k_pos.contiguous(), dw=d_in_w[E:2 * E]))
-        run_wgrad(probs, E, E)
+        if fused:
+            # dW_q = dq^T (q_in + q_pos): the sum is formed on the side stream (one add) instead of a second product
+            sums = [(0, q_in, q_pos.contiguous())] if q_pos is not None else []
+            if k_pos is not None:
+                sums.append((1, k_in, k_pos.contiguous()))
+            wgrad_side(probs, E, E, sums=sums)
+        else:
+            if q_pos is not None:
+                probs.append(dict(dy=dq, x=q_pos.contiguous(), dw=d_in_w[:E]))
+            if k_pos is not None:
+                probs.append(dict(dy=dk, x=k_pos.contiguous(), dw=d_in_w[E:2 * E]))
+            wgrad(probs, E, E)
         dq_in = dq_in.view(B, Nq, E)
         dk_in = dk_in.view(B, Nk, E)
         dv_in = dv_in.view(B, Nk, E)
