@@ -1,0 +1,63 @@
+"""Host-side logic that needs no GPU: synthetic configs[3] inputs, gradient-bucket plumbing switches, ABI struct
+layouts the Python side builds by hand."""
+import ctypes
+
+import torch
+
+from eda_b200 import _lib, attn_ops, ddp, hotpath
+
+
+def test_synthetic_inputs_have_configs3_shapes():
+    pc, pos, text, text_mask, det, det_mask, query, qpos = hotpath.synthetic_inputs(2, N=4096)
+    assert pc.shape == (2, 4096, 6) and pos.shape == (2, 1024, hotpath.D_MODEL)
+    assert text.shape == (2, 80, 288) and det.shape == (2, 132, 288) and query.shape == (2, 256, 288)
+    assert qpos.shape == (2, 256, 6) and (qpos[..., 3:] > 0).all()          # box sizes are positive
+    assert text_mask.dtype == torch.bool and text_mask.shape == (2, 80) and det_mask.shape == (2, 132)
+    assert not text_mask[0].any() and not det_mask[0].any()                  # row 0 keeps every token (L = 80 exactly)
+    keep = (~text_mask).sum(1)
+    assert (keep >= 20).all() and ((~text_mask).long().cumsum(1) == torch.arange(1, 81).clamp(max=keep[:, None])).all()
+    again = hotpath.synthetic_inputs(2, N=4096)
+    assert all(torch.equal(a, b) for a, b in zip((pc, pos, text, query), (again[0], again[1], again[2], again[6])))
+
+
+def test_flat_gradients_on_cpu_leaves_the_cuda_switches_alone():
+    before = attn_ops.FUSED_WGRAD
+    m = torch.nn.Linear(4, 3)
+    fg = ddp.FlatGradients(m)
+    assert attn_ops.FUSED_WGRAD == before            # only a CUDA bucket turns fused weight gradients on
+    assert fg.check_views() and fg.flat.numel() == 15
+    m(torch.ones(2, 4)).sum().backward()
+    fg.sync()                                        # no side stream on CPU: a no-op
+    assert torch.equal(m.bias.grad, torch.full((3,), 2.0)) and fg.flat.abs().sum() > 0
+    attn_ops.join_wgrad()                            # nothing pending: must not touch CUDA
+    fg.zero()
+    assert fg.flat.abs().sum() == 0 and fg.check_views()
+
+
+def test_grad_buffers_only_when_enabled():
+    p = torch.nn.Parameter(torch.zeros(3, 3))
+    p.grad = torch.zeros(3, 3)
+    saved = attn_ops.FUSED_WGRAD
+    try:
+        attn_ops.FUSED_WGRAD = False
+        assert attn_ops._grad_buffers((p, None)) == [None, None]
+        attn_ops.FUSED_WGRAD = True
+        got = attn_ops._grad_buffers((p, None, torch.nn.Parameter(torch.zeros(2))))
+        assert got[0] is p.grad and got[1] is None and got[2] is None   # no .grad yet -> autograd path
+    finally:
+        attn_ops.FUSED_WGRAD = saved
+
+
+def test_hand_built_abi_structs_match_the_header_layout():
+    # attn_ops.PackRegistry writes descriptor rows as 6 int64 (w, dst, stride_n, stride_k, N | K << 32, Kpad):
+    # struct eda_linear_pack_desc { const float *w; float *dst; long long stride_n, stride_k; int N, K, Kpad, reserved; }
+    class Desc(ctypes.Structure):
+        _fields_ = [("w", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("sn", ctypes.c_longlong), ("sk", ctypes.c_longlong),
+                    ("N", ctypes.c_int), ("K", ctypes.c_int), ("Kpad", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+    assert ctypes.sizeof(Desc) == 48
+    row = (ctypes.c_longlong * 6)(0x1000, 0x2000, 288, 1, 288 | (256 << 32), 256)
+    d = Desc.from_buffer_copy(bytes(row))
+    assert (d.w, d.dst, d.sn, d.sk, d.N, d.K, d.Kpad, d.reserved) == (0x1000, 0x2000, 288, 1, 288, 256, 256, 0)
+    assert ctypes.sizeof(_lib.LinearProblem) == 6 * 8 + 4 * 4 + 8      # 6 pointers, 4 ints, pre_ln
+    assert ctypes.sizeof(_lib.WgradProblem) == 4 * 8 + 8 + 3 * 4 + 4 + 2 * 8  # 4 pointers, rows, 3 ints (+pad), 2 pointers
