@@ -58,7 +58,7 @@ PROTOTYPES = {
     "eda_linear_pack_strided": (_c_int, [_vp, ctypes.c_longlong, ctypes.c_longlong, _c_int, _c_int, _vp, _vp]),
     "eda_attention_forward_lse": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                                            _c_float, ctypes.c_uint, _vp, _vp, _vp]),
-    "eda_attention_backward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
+    "eda_attention_backward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
                                         _c_int, _c_int, _c_float, _c_float, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp]),
     "eda_attention_backward_tc": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp,
                                            _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, ctypes.c_uint,

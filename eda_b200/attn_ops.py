@@ -432,7 +432,6 @@ def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, 
     E = q.size(-1)
     D = E // H
     ld = vt.size(2)
-    v = _transpose_last2(vt)  # (B, ld, E): row-major values, rows >= Nk are padding and never read
     dq = torch.empty_like(q)
     dk = torch.empty_like(k)
     dv = torch.empty_like(k)
@@ -445,6 +444,7 @@ def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, 
         m = m.contiguous().view(torch.uint8)
     dp, dseed = dropout if dropout is not None else (0.0, 0)
     if impl == "tc":
+        v = _transpose_last2(vt)  # (B, ld, E): row-major values, rows >= Nk are padding and never read
         kt, ldk = _channel_major(k, B, Nk, E)
         qt, ldq = _channel_major(q, B, Nq, E)
         dot, _ = _channel_major(dctx, B, Nq, E)
@@ -454,8 +454,10 @@ def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, 
                                                int(dseed), _p(delta), _p(dq), _p(dk), _p(dv), _stream(q.device))
         _lib.check(rc, "attention_backward_tc")
         return dq, dk, dv
-    with torch.cuda.device(q.device):
-        rc = lib.eda_attention_backward(_p(q), _p(k), _p(v), ld * E, _p(dctx), _p(c), _p(lse), _p(m), B, Nq, Nk, H, D,
+    v_nat = _transpose_last2(vt) if impl == "mma_natural" else None  # the ABI's row-major-values variant (tests)
+    with torch.cuda.device(q.device):  # the warp-level kernel reads the channel-major values as they are
+        rc = lib.eda_attention_backward(_p(q), _p(k), _p(v_nat), ld * E if v_nat is not None else 0,
+                                        None if v_nat is not None else _p(vt), ld, _p(dctx), _p(c), _p(lse), _p(m), B, Nq, Nk, H, D,
                                         1.0 / math.sqrt(D), float(dp), int(dseed), _p(delta), _p(dq), _p(dk), _p(dv),
                                         _stream(q.device))
     _lib.check(rc, "attention_backward")

@@ -34,6 +34,8 @@ struct AttnBwdParams {
   float *delta;               // (B, H, Nq): written by the rows = queries launch, read by the rows = keys launch
   float *dq, *dk, *dv;
   long long v_batch_stride;   // floats between scenes of v (rows may be padded)
+  const float *vt;            // alternative to v: channel-major values (B, H*D, ldv) exactly as the forward kernel took them
+  int ldv;
   int Nq, Nk, H;
   float scale;
   uint32_t drop_thresh, drop_seed;
@@ -78,7 +80,9 @@ attention_backward_kernel(const AttnBwdParams p) {
   constexpr int PITCH = DP + 4;      // (12 g + t) % 32 and (24 t + g) % 32 are conflict-free for PITCH = 44
   static_assert(D % 4 == 0, "head dim must be a multiple of 4");
   __shared__ __align__(16) float sC1[2][kBwCols][PITCH];  // rows=queries: K block; rows=keys: Q block
-  __shared__ __align__(16) float sC2[2][kBwCols][PITCH];  // rows=queries: V block; rows=keys: dctx block
+  constexpr int PT = kBwCols + 8;                         // pitch of the transposed V block: (8 t + g) % 32 conflict-free
+  constexpr int C2N = (kBwCols * PITCH > DP * PT) ? kBwCols * PITCH : DP * PT;
+  __shared__ __align__(16) float sC2[2][C2N];  // rows=queries: V block ([key][PITCH], or [dim][PT] from channel-major V); rows=keys: dctx block
   __shared__ float sStat[2][2][kBwCols];                  // [buf][0: additive mask or lse, 1: delta][col]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -87,6 +91,8 @@ attention_backward_kernel(const AttnBwdParams p) {
   const int Nrows = kKeyRows ? p.Nk : p.Nq, Ncols = kKeyRows ? p.Nq : p.Nk;
   const int row0 = blockIdx.x * kBwRows + warp * 16;
   const float *x1base = kKeyRows ? p.k + (size_t)b * p.Nk * HD : p.q + (size_t)b * p.Nq * HD;
+  const bool v_t = p.vt != nullptr;  // values arrive channel-major
+  const float *vtb = v_t ? p.vt + ((size_t)b * HD + h * D) * p.ldv : nullptr;
   const float *x2base = kKeyRows ? p.v + (size_t)b * p.v_batch_stride : p.dctx + (size_t)b * p.Nq * HD;
   const float *c1base = kKeyRows ? p.q + (size_t)b * p.Nq * HD : p.k + (size_t)b * p.Nk * HD;
   const float *c2base = kKeyRows ? p.dctx + (size_t)b * p.Nq * HD : p.v + (size_t)b * p.v_batch_stride;
@@ -96,12 +102,22 @@ attention_backward_kernel(const AttnBwdParams p) {
 
   auto issue = [&](int blk, int buf) {
     const int c0 = blk * kBwCols;
+    const bool c2_t = !kKeyRows && v_t;  // V block staged [dim][key] from the channel-major source
     for (int id = tid; id < kBwCols * DC; id += kBwThreads) {
       const int r = id / DC, ch = id - r * DC;
       const bool in = c0 + r < Ncols;
       const size_t off = (size_t)(c0 + r) * HD + h * D + ch * 4;
       cp_async16_zfill(&sC1[buf][r][ch * 4], in ? c1base + off : c1base, in ? 16u : 0u);
-      cp_async16_zfill(&sC2[buf][r][ch * 4], in ? c2base + off : c2base, in ? 16u : 0u);
+      if (!c2_t) cp_async16_zfill(&sC2[buf][r * PITCH + ch * 4], in ? c2base + off : c2base, in ? 16u : 0u);
+    }
+    if (c2_t) {
+      for (int id = tid; id < D * (kBwCols / 4); id += kBwThreads) {
+        const int d = id / (kBwCols / 4), kg = id - d * (kBwCols / 4);
+        const int key = c0 + 4 * kg;
+        const int left = Ncols - key;
+        const uint32_t bytes = left >= 4 ? 16u : (left > 0 ? (uint32_t)left * 4u : 0u);
+        cp_async16_zfill(&sC2[buf][d * PT + 4 * kg], bytes ? vtb + (size_t)d * p.ldv + key : vtb, bytes);
+      }
     }
     cp_async_commit_group();
     if (tid < kBwCols) {
@@ -123,8 +139,10 @@ attention_backward_kernel(const AttnBwdParams p) {
   for (int i = tid; i < 2 * kBwCols * (PITCH - D); i += kBwThreads) {
     const int bufr = i / (PITCH - D), c = D + i % (PITCH - D);
     sC1[bufr / kBwCols][bufr % kBwCols][c] = 0.f;
-    sC2[bufr / kBwCols][bufr % kBwCols][c] = 0.f;
+    if (kKeyRows || !v_t) sC2[bufr / kBwCols][(bufr % kBwCols) * PITCH + c] = 0.f;
   }
+  if (!kKeyRows && v_t)  // transposed V block: the padded depth rows D..DP-1
+    for (int i = tid; i < 2 * (DP - D) * PT; i += kBwThreads) sC2[i / ((DP - D) * PT)][D * PT + i % ((DP - D) * PT)] = 0.f;
   issue(0, 0);
 
   // ---- this warp's 16 rows: A fragments of X1 (q or k) and X2 (dctx or v), kept for the whole kernel -------------
@@ -141,7 +159,7 @@ attention_backward_kernel(const AttnBwdParams p) {
       const bool ok = ((e & 1) ? vB : vA) && d < D;
       const size_t off = (size_t)row * HD + h * D + d;
       const float a = ok ? __ldg(x1base + off) : 0.f;
-      const float c = ok ? __ldg(x2base + off) : 0.f;
+      const float c = ok ? ((kKeyRows && v_t) ? __ldg(vtb + (size_t)d * p.ldv + row) : __ldg(x2base + off)) : 0.f;
       x1f[ks][e] = f2tf32(a);
       x2f[ks][e] = f2tf32(c);
       if (!kKeyRows && ok) {
@@ -195,11 +213,15 @@ attention_backward_kernel(const AttnBwdParams p) {
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) { s[j][e] = 0.f; dp[j][e] = 0.f; }
-      const float *c1r = &sC1[buf][j * 8 + g][t], *c2r = &sC2[buf][j * 8 + g][t];
+      const float *c1r = &sC1[buf][j * 8 + g][t];
+      // V block: [key][PITCH] (element (key, dim) at key * PITCH + dim) or transposed [dim][PT]
+      const bool c2_t = !kKeyRows && v_t;
+      const float *c2r = c2_t ? &sC2[buf][t * PT + j * 8 + g] : &sC2[buf][(j * 8 + g) * PITCH + t];
+      const int c2s = c2_t ? PT : 1;  // stride of one depth step
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         mma_m16n8k8_tf32(s[j], x1f[ks], f2tf32(c1r[ks * 8]), f2tf32(c1r[ks * 8 + 4]));
-        mma_m16n8k8_tf32(dp[j], x2f[ks], f2tf32(c2r[ks * 8]), f2tf32(c2r[ks * 8 + 4]));
+        mma_m16n8k8_tf32(dp[j], x2f[ks], f2tf32(c2r[(ks * 8) * c2s]), f2tf32(c2r[(ks * 8 + 4) * c2s]));
       }
     }
     // ---- P, dS (element e of tile j: row (e & 2 ? rB : rA), column c0 + 8 j + 2 t + (e & 1)) ------------------------
@@ -240,7 +262,7 @@ attention_backward_kernel(const AttnBwdParams p) {
     for (int j = 0; j < 8; ++j) {
       const uint32_t a1[4] = {dsf[j][0], dsf[j][2], dsf[j][1], dsf[j][3]};
       const uint32_t a2[4] = {pf[j][0], pf[j][2], pf[j][1], pf[j][3]};
-      const float *c1r = &sC1[buf][j * 8 + 2 * t][g], *c2r = &sC2[buf][j * 8 + 2 * t][g];
+      const float *c1r = &sC1[buf][j * 8 + 2 * t][g], *c2r = &sC2[buf][(j * 8 + 2 * t) * PITCH + g];
 #pragma unroll
       for (int nt = 0; nt < KS; ++nt) {
         mma_m16n8k8_tf32(o1[nt], a1, f2tf32(c1r[nt * 8]), f2tf32(c1r[PITCH + nt * 8]));
@@ -287,7 +309,7 @@ int launch_attention_backward(const AttnBwdParams &p, int B, cudaStream_t st) {
 }  // namespace eda
 
 extern "C" int eda_attention_backward(const float *q, const float *k, const float *v, long long v_batch_stride,
-                                      const float *dctx, const float *ctx, const float *lse,
+                                      const float *vt, int ldv, const float *dctx, const float *ctx, const float *lse,
                                       const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
                                       float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
                                       float *dk, float *dv, void *stream) {
@@ -295,15 +317,21 @@ extern "C" int eda_attention_backward(const float *q, const float *k, const floa
   if (B < 0 || Nq < 0 || Nk < 1 || H < 1 || D < 1) return EDA_ERR_INVALID_ARGUMENT;
   if (H > 65535 || B > 65535) return EDA_ERR_UNSUPPORTED;
   if (B == 0 || Nq == 0) return EDA_OK;
-  if (!q || !k || !v || !dctx || !ctx || !lse || !delta || !dq || !dk || !dv) return EDA_ERR_INVALID_ARGUMENT;
-  if (v_batch_stride < (long long)Nk * H * D || (v_batch_stride & 3)) return EDA_ERR_INVALID_ARGUMENT;
-  const void *ptrs[] = {q, k, v, dctx, ctx, dq, dk, dv};
+  if (!q || !k || (!v && !vt) || !dctx || !ctx || !lse || !delta || !dq || !dk || !dv) return EDA_ERR_INVALID_ARGUMENT;
+  if (vt) {
+    if (ldv < Nk || (ldv & 3)) return EDA_ERR_INVALID_ARGUMENT;
+  } else if (v_batch_stride < (long long)Nk * H * D || (v_batch_stride & 3)) {
+    return EDA_ERR_INVALID_ARGUMENT;
+  }
+  const void *ptrs[] = {q, k, vt ? vt : v, dctx, ctx, dq, dk, dv};
   for (const void *ptr : ptrs)
     if (reinterpret_cast<uintptr_t>(ptr) & 15) return EDA_ERR_INVALID_ARGUMENT;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   AttnBwdParams p = {};
   p.q = q; p.k = k; p.v = v; p.dctx = dctx; p.ctx = ctx; p.lse = lse; p.mask = key_padding_mask; p.delta = delta;
   p.dq = dq; p.dk = dk; p.dv = dv; p.v_batch_stride = v_batch_stride; p.Nq = Nq; p.Nk = Nk; p.H = H; p.scale = scale;
+  p.vt = vt; p.ldv = ldv;
+  if (vt) p.v = vt;  // never dereferenced in that mode; keeps the pointer arithmetic defined
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
   p.seed_epoch = dropout_epoch_ptr();
   cudaStream_t st = as_stream(stream);

@@ -351,8 +351,10 @@ int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, 
   if (!aligned16(dy) || !aligned16(u) || !aligned16(du) || (dproj && !aligned16(dproj)) || (gamma && !aligned16(gamma)))
     return EDA_ERR_INVALID_ARGUMENT;
   if (rows * 3 > 0xffffffffLL) return EDA_ERR_UNSUPPORTED;
-  long long blocks = (rows + kLnWarps * 4 - 1) / (kLnWarps * 4);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  // every block ends with 2 N global atomics onto the same 2 N addresses: few, fat blocks (each warp keeps >= 8 rows)
+  long long blocks = (rows + kLnWarps * 8 - 1) / (kLnWarps * 8);
+  const int sms = sm_count();
+  if (blocks > sms) blocks = sms;
   if (blocks < 1) blocks = 1;
   const uint32_t thresh = dropout_thresh(dropout_p);
   layernorm_backward_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(

@@ -253,7 +253,8 @@ EDA_API int eda_attention_forward_lse(const float *q, const float *k, const floa
  * eda_attention_backward: q (B,Nq,H*D), k (B,Nk,H*D), v (B,Nk,H*D; scenes v_batch_stride floats apart) are the
  *   PROJECTED inputs of eda_attention_forward_lse (v row-major here), ctx / lse its outputs, dctx the gradient of ctx.
  *   Recomputes the probabilities from lse tile by tile and writes dq, dk, dv (same layouts; fully overwritten, no
- *   atomics, deterministic).  delta (B,H,Nq) is scratch (rowsum(dctx * ctx)).  The dropout mask of the forward call
+ *   atomics, deterministic).  Instead of v, the values may be given channel-major as the forward call took them:
+ *   vt (B, H*D, ldv) with v = NULL — no transposed copy is needed then.  delta (B,H,Nq) is scratch (rowsum(dctx * ctx)).  The dropout mask of the forward call
  *   (dropout_p, dropout_seed) is regenerated from the same hash.  Head dims compiled: D in {32, 36}.
  * eda_wgrad: for every problem i, dw_i (N, K; row stride ldw) += dy_i (rows, N; ldy)^T x_i (rows, K; ldx) and, when db_i
  *   is not NULL, db_i (N) += column sums of dy_i.  ACCUMULATES (atomics): zero the outputs first.  N, K, ldy, ldx
@@ -274,7 +275,7 @@ typedef struct eda_wgrad_problem {
   const float *x_shift; /* BatchNorm + ReLU of the layer that produced it (both NULL: x as it is)          */
 } eda_wgrad_problem;
 EDA_API int eda_attention_backward(const float *q, const float *k, const float *v, long long v_batch_stride,
-                                   const float *dctx, const float *ctx, const float *lse,
+                                   const float *vt, int ldv, const float *dctx, const float *ctx, const float *lse,
                                    const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
                                    float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
                                    float *dk, float *dv, void *stream);

@@ -78,7 +78,7 @@ def test_layernorm_backward_kernel(R, N, p):
         assert dproj is du
 
 
-@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("impl", ["tc", "mma", "mma_natural"])
 @pytest.mark.parametrize("B,Nq,Nk,masked,p", [(2, 80, 80, True, 0.0), (2, 256, 132, True, 0.1), (2, 200, 1024, False, 0.0),
                                               (1, 1024, 1024, False, 0.1), (3, 7, 5, True, 0.0), (2, 129, 257, True, 0.1)])
 def test_attention_backward_kernel(B, Nq, Nk, masked, p, impl):
