@@ -91,6 +91,69 @@ def test_oracle_matches_reference_fixture(name):
         torch.testing.assert_close(v, torch.from_numpy(fx[k]), rtol=2e-5, atol=2e-5)
 
 
+GRAD_CASES = ["enc_layer", "dec_layer"]
+
+
+def _grad_w(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))  # make_golden_attention.grad_weights
+
+
+def _check_against_grad_fixture(fx, input_grads, param_grads, tol):
+    """fx: tests/golden/attn_grad_<case>.npz — gradients of the REFERENCE module (autograd on CPU): inputs and 1-D
+    parameters in full, matrices as row sums / column sums / norm (+ one full matrix)."""
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-20)).item()
+
+    checked, failures = 0, []
+    for key in fx.files:
+        kind_, name = key.split(".", 1)
+        want = torch.from_numpy(np.asarray(fx[key]))
+        if kind_ == "input":
+            got = input_grads[name]
+        else:
+            g = param_grads[name]
+            g2 = g.reshape(g.shape[0], -1) if g.dim() > 1 else g
+            got = {"param": g, "rowsum": g2.sum(1) if g.dim() > 1 else g, "colsum": g2.sum(0) if g.dim() > 1 else g,
+                   "norm": g2.norm()}[kind_]
+        # absolute floor of 1e-4 per element: some gradients are zero up to rounding (the key-projection bias — softmax
+        # is shift-invariant — and a bias in front of a BatchNorm), a relative comparison of noise means nothing
+        # (the floor follows the tolerance: with tf32 operands such a "zero" is a sum of ~1e-3-relative rounding errors)
+        floor = max(1e-4, 0.06 * tol) * math.sqrt(want.numel())
+        if kind_ in ("rowsum", "colsum"):
+            # a sum over a matrix whose entries are right to `tol` can be off by tol * ||matrix||: the column sums of a
+            # weight gradient in front of a LayerNorm vanish by exact cancellation (sum_n du[r, n] = 0), which tf32
+            # rounding of du does not preserve — the matrix itself (param.* / norm.* / rowsum.*) is what is checked
+            floor += tol * float(fx["norm." + name])
+        if kind_ == "norm":
+            ok = abs(got.item() - want.item()) <= tol * want.item() + floor
+            err = abs(got.item() - want.item())
+        else:
+            err = (got.cpu().double() - want.double()).norm().item()
+            ok = err <= tol * want.double().norm().item() + floor
+        if not ok:
+            failures.append((key, round(err, 6), round(float(want.double().norm()), 6)))
+        checked += 1
+    assert not failures, failures
+    assert checked >= 50
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_oracle_gradients_match_reference_fixture(name):
+    """Backward parity is pinned by the reference too: autograd through the oracle restatement reproduces the gradients
+    the reference's own modules give on the same inputs (fixtures made by make_golden_attention.py)."""
+    kind = ac.CASES[name][0]
+    fx = np.load(os.path.join(HERE, "golden", f"attn_grad_{name}.npz"))
+    m = ac.fill_params(build(kind), seed=100 + len(name)).eval()
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    inp = ac.make_inputs(name)
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in (("vis", "text") if kind == "bi_encoder_layer" else ("query",))}
+    out = oracle_run(kind, sd, {**inp, **leaves})
+    loss = sum((v * _grad_w(v.shape, 1234 + i)).sum() for i, v in enumerate(out.values()))
+    loss.backward()
+    _check_against_grad_fixture(fx, {k: v.grad for k, v in leaves.items()},
+                                {k: v.grad for k, v in sd.items() if v.grad is not None}, tol=1e-3)
+
+
 def test_layers_refuse_cpu_tensors():
     m = build("bi_decoder_layer").eval()
     inp = ac.make_inputs("dec_layer")
@@ -384,3 +447,21 @@ def test_train_mode_dropout_layer_forward_backward():
         ve, te = m.eval()(inp["vis"], inp["pos"], None, inp["text"], inp["text_mask"], {}, detected_feats=inp["det"],
                           detected_mask=inp["det_mask"])
     assert (v1 - ve).abs().max() > 1e-2  # dropout really happened
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_cuda_backward_matches_reference_gradient_fixture(name):
+    """The CUDA backward (attention / LayerNorm / weight-gradient kernels) against the gradients of the REFERENCE's own
+    modules (fixture): relative Frobenius error <= 5e-2 per tensor (tf32 operands; ReLU units within the forward
+    tolerance of zero flip between the two paths)."""
+    kind = ac.CASES[name][0]
+    fx = np.load(os.path.join(HERE, "golden", f"attn_grad_{name}.npz"))
+    m = ac.fill_params(build(kind), seed=100 + len(name)).eval().cuda()
+    inp = _cuda(ac.make_inputs(name))
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in (("vis", "text") if kind == "bi_encoder_layer" else ("query",))}
+    out = module_run(kind, m, {**inp, **leaves})
+    loss = sum((v * _grad_w(v.shape, 1234 + i).cuda()).sum() for i, v in enumerate(out.values()))
+    loss.backward()
+    _check_against_grad_fixture(fx, {k: v.grad for k, v in leaves.items()},
+                                {k: p.grad for k, p in m.named_parameters() if p.grad is not None}, tol=5e-2)
