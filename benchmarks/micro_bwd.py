@@ -1,6 +1,9 @@
 """Per-kernel timings of the backward building blocks at the shapes of the attention stack and the SA stages
 (B = 8 scenes, E = 288, H = 8): CUDA events, median of 20 after 5 warm-ups, L2 not flushed (operands of these
-kernels are produced by the preceding kernel in the real step, i.e. L2-warm there too).
+kernels are produced by the preceding kernel in the real step, i.e. L2-warm there too).  Each sample brackets ONE call of
+the Python wrapper, so entries below ~100 us are dominated by host time (allocation + ctypes + launch), not by the kernel:
+device times per kernel are in profiles/r1_bwd_kernel_metrics.json (ncu) — e.g. the 1024 x 1024 attention backward is
+74 + 90 us on the device, 369 us through the wrapper.
 
   python benchmarks/micro_bwd.py [out.json]
 """
