@@ -91,6 +91,31 @@ void oracle_furthest_point_sampling(int b, int n, int m, const float *dataset, i
   }
 }
 
+/* NOT a reference function: a PROPERTY of the reference's FPS (sampling_gpu.cu:74-178) that the product exploits for the
+ * backbone's stages 2-4, whose inputs are already in FPS order (models/backbone_module.py:92-144).
+ * Returns 1 iff FPS(pts[0..n), m) is provably 0, 1, ..., m-1 WITHOUT appeal to the tie-break: at every step i < m point i
+ * is the strict maximiser of the running minimum (and is not skipped by the |p|^2 <= 1e-3 rule).  Sequential restatement
+ * of the criterion eda_fps_identity_check evaluates in parallel, same arithmetic as the sampler above. */
+int oracle_fps_identity_verified(int n, int m, const float *pts) {
+  if (m <= 0) return 1;
+  if (m > n) return 0;
+  float *run = (float *)malloc(sizeof(float) * (size_t)n);
+  for (int j = 0; j < n; ++j) run[j] = (float)1e10;
+  int ok = 1;
+  for (int i = 1; i < m && ok; ++i) {
+    const float x1 = pts[(i - 1) * 3 + 0], y1 = pts[(i - 1) * 3 + 1], z1 = pts[(i - 1) * 3 + 2];
+    for (int j = 0; j < n; ++j)
+      run[j] = fminf(run[j], sq3(pts[j * 3 + 0] - x1, pts[j * 3 + 1] - y1, pts[j * 3 + 2] - z1));
+    const float di = run[i];
+    const float mag = sq3(pts[i * 3 + 0], pts[i * 3 + 1], pts[i * 3 + 2]);
+    if ((double)mag <= 1e-3 || !(di > 0.0f)) { ok = 0; break; }
+    for (int j = 0; j < n; ++j)
+      if (j != i && !(run[j] < di)) { ok = 0; break; }
+  }
+  free(run);
+  return ok;
+}
+
 /* ball_query_gpu.cu:14-49, ball_query.cpp:24-26 (idx zero-init).
  * new_xyz (b,m,3), xyz (b,n,3) -> idx (b,m,nsample) */
 void oracle_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,

@@ -68,6 +68,18 @@ def furthest_point_sampling(points, nsamples):
     return out
 
 
+def fps_identity_verified(points, nsamples):
+    """(B,n,3) -> (B,) int32: 1 where FPS(points[b], nsamples) is provably 0..nsamples-1 with no tie-break involved
+    (the criterion behind eda_fps_identity_check; a property of the reference algorithm, see the C file)."""
+    B, n, _ = points.shape
+    L = lib()
+    L.oracle_fps_identity_verified.restype = ctypes.c_int
+    out = torch.zeros(B, dtype=torch.int32)
+    for b in range(B):
+        out[b] = L.oracle_fps_identity_verified(int(n), int(nsamples), _f(points[b].contiguous()))
+    return out
+
+
 def ball_query(new_xyz, xyz, radius, nsample):
     B, M, _ = new_xyz.shape
     N = xyz.shape[1]

@@ -189,3 +189,27 @@ def test_three_nn_and_interpolate(oracle):
     contrib = go[:, :, :, None] * w[:, None]
     want.scatter_add_(2, idx.long().reshape(2, 1, 150).expand(-1, 6, -1), contrib.reshape(2, 6, 150))
     torch.testing.assert_close(gp, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("family", ["surface", "uniform", "dup", "lattice", "origin"])
+def test_fps_of_an_fps_ordered_set_is_the_identity_when_no_step_is_a_tie(oracle, family):
+    """SURVEY.md A.4 / the product's FPS shortcut for the backbone's stages 2-4, on the oracle alone: whenever the
+    strict-maximiser criterion holds, the reference algorithm (literal emulation, tie-break included) returns
+    0..m-1; continuous data always satisfies it, tie-heavy data never does, and a shuffled set is never verified."""
+    B, N = 2, 6000
+    xyz = synthetic.point_clouds(B, N, family, channels=0).contiguous()
+    inds1 = oracle.furthest_point_sampling(xyz, 512)
+    sub = torch.gather(xyz, 1, inds1.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    for n, m in ((512, 256), (256, 128)):
+        cur = sub[:, :n].contiguous()
+        ver = oracle.fps_identity_verified(cur, m)
+        full = oracle.furthest_point_sampling(cur, m)
+        for b in range(B):
+            if ver[b].item() == 1:
+                assert torch.equal(full[b], torch.arange(m, dtype=torch.int32)), (family, n, m, b)
+        if family in ("surface", "uniform"):
+            assert ver.sum().item() == B
+        if family == "lattice":
+            assert ver.sum().item() == 0
+    perm = torch.randperm(512, generator=torch.Generator().manual_seed(0))
+    assert oracle.fps_identity_verified(sub[:, perm].contiguous(), 256).sum().item() == 0
