@@ -66,6 +66,15 @@ class FlatGradients:
     def zero(self):
         self.flat.zero_()
 
+    def release(self):
+        """Switches fused weight-gradient accumulation off again (process-wide flag): afterwards the backward kernels
+        return their gradients to autograd like any other op.  Call it when this bucket stops being the owner of the
+        model's gradients (e.g. before handing the model to a stock optimizer loop that never calls `sync()`)."""
+        self.sync()
+        if self.flat.is_cuda:
+            from . import attn_ops
+            attn_ops.FUSED_WGRAD = False
+
     def sync(self):
         """Gradients are complete on the current stream after this (joins the side-stream weight-gradient kernels)."""
         if self.flat.is_cuda:

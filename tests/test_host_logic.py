@@ -32,6 +32,8 @@ def test_flat_gradients_on_cpu_leaves_the_cuda_switches_alone():
     attn_ops.join_wgrad()                            # nothing pending: must not touch CUDA
     fg.zero()
     assert fg.flat.abs().sum() == 0 and fg.check_views()
+    fg.release()                                     # CPU bucket: nothing to switch off, must not raise
+    assert attn_ops.FUSED_WGRAD == before
 
 
 def test_grad_buffers_only_when_enabled():
