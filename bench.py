@@ -213,6 +213,9 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the contract is ONE JSON line on stdout: NCCL prints "NCCL version ..." there at the VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()  # fails loudly when the CUDA library is missing
 
