@@ -47,21 +47,23 @@ def _require_cuda(t, name="input"):
 # packed weights
 # ---------------------------------------------------------------------------------------------------
 # Packed-weight caches are keyed on the parameter's (data_ptr, _version): right for eager execution, wrong inside a
-# CUDA graph of a TRAINING step (the graph must re-pack after every optimizer step).  graphs.GraphedTrainStep turns
-# the caches off while it warms up and captures, so the pack kernels become part of the graph.
-PACK_CACHE = True
+# CUDA graph of a TRAINING step (the graph must re-pack after every optimizer step).  graphs.GraphedTrainStep attaches
+# a PackRegistry to the modules of ITS model and activates it while it warms up and captures; nothing here is
+# process-wide, so two models (or two graphs) in one process do not interfere.
+PACK_CACHE = True  # debugging switch only (False: re-pack on every call); never toggled by the library itself
 
 
 class PackRegistry:
     """Persistent packed copies of a model's weights that ONE kernel launch refreshes (eda_linear_pack_batch).
 
-    Used by graphs.GraphedTrainStep: while a registry is active (attn_ops.PACK_REGISTRY), pack_weight / pack_weight_t
+    Used by graphs.GraphedTrainStep: while a registry is attached to the model and active, pack_weight / pack_weight_t
     calls that carry a cache key return the registry's buffer for that (module, name) — created and registered on
     first sight — without launching anything; `refresh()` at the start of every step re-packs all of them from the
     current parameter values.  Parameters must keep their storage (as in any CUDA-graph training loop)."""
 
     def __init__(self, device):
         self.device = device
+        self.active = False  # True while the owning GraphedTrainStep warms up / captures
         self.entries = {}   # (id(owner), name, transposed) -> packed tensor
         self.owners = []    # keep the modules alive so ids stay unique
         self.rows = []      # descriptor rows: w ptr, dst ptr, stride_n, stride_k, N | K << 32, Kpad
@@ -105,7 +107,21 @@ class PackRegistry:
         _lib.check(rc, "linear_pack_batch")
 
 
-PACK_REGISTRY = None
+    def attach(self, model):
+        """Makes this registry the one the modules of `model` consult (while it is `active`)."""
+        for m in model.modules():
+            m.__dict__["_eda_pack_registry"] = self
+
+    def detach(self, model):
+        for m in model.modules():
+            if m.__dict__.get("_eda_pack_registry") is self:
+                del m.__dict__["_eda_pack_registry"]
+
+
+def active_registry(owner):
+    """The PackRegistry attached to `owner` (a module) if it is currently recording, else None."""
+    reg = getattr(owner, "__dict__", {}).get("_eda_pack_registry")
+    return reg if (reg is not None and reg.active) else None
 
 
 def _cache_of(owner):
@@ -125,8 +141,9 @@ def pack_weight(W, scale=None, cache_key=None):
     lib = _lib.load()
     N, K = W.shape
     cache = None
-    if PACK_REGISTRY is not None and cache_key is not None and scale is None:
-        return PACK_REGISTRY.get(cache_key[0], cache_key[1], False, W.detach())
+    reg = active_registry(cache_key[0]) if (cache_key is not None and scale is None) else None
+    if reg is not None:
+        return reg.get(cache_key[0], cache_key[1], False, W.detach())
     if cache_key is not None and scale is None and PACK_CACHE:
         cache = _cache_of(cache_key[0])
         tag = (W.data_ptr(), W._version, N, K, W.device)
@@ -243,6 +260,9 @@ def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H, dropout=None, lse=No
 # ---------------------------------------------------------------------------------------------------
 # backward building blocks (csrc/grad_ops.cu, csrc/attn_bwd.cu)
 # ---------------------------------------------------------------------------------------------------
+CUDA_BACKWARD_HEAD_DIMS = (32, 36)  # csrc/attn_bwd.cu: launch_attention_backward<D>
+
+
 def use_cuda_backward():
     return os.environ.get("EDA_BACKWARD", "cuda") != "torch"
 
@@ -254,8 +274,9 @@ def pack_weight_t(W, cache_key=None):
     Nout, Kin = W.shape
     assert W.stride(1) == 1
     cache = None
-    if PACK_REGISTRY is not None and cache_key is not None:
-        return PACK_REGISTRY.get(cache_key[0], cache_key[1], True, W.detach())
+    reg = active_registry(cache_key[0]) if cache_key is not None else None
+    if reg is not None:
+        return reg.get(cache_key[0], cache_key[1], True, W.detach())
     if cache_key is not None and PACK_CACHE:
         cache = _cache_of(cache_key[0])
         tag = (W.data_ptr(), W._version, Nout, Kin, W.stride(0), W.device)
@@ -274,15 +295,17 @@ def pack_weight_t(W, cache_key=None):
     return packed
 
 
-# Fused gradient accumulation (opt-in, switched on by ddp.FlatGradients): when a parameter already owns a gradient
-# buffer (param.grad, e.g. a view of the flat all-reduce bucket), the weight-gradient kernels accumulate straight into
-# it and the autograd Function returns None for that parameter — no per-block zeroed scratch, no AccumulateGrad add
-# kernel.  Because nothing downstream in the backward pass reads those buffers, the wgrad launches then run on a side
-# stream, off the critical path (most kernels of the attention backward occupy < 64 of the 148 SMs); join_wgrad()
-# makes the current stream wait for them (FlatGradients.all_reduce_mean / GraphedTrainStep call it once per step).
-FUSED_WGRAD = False
+# Fused gradient accumulation (opt-in per PARAMETER: ddp.FlatGradients tags the parameters it owns): when a tagged
+# parameter owns a gradient buffer (param.grad, a view of the flat all-reduce bucket), the weight-gradient kernels
+# accumulate straight into it and the autograd Function returns None for that parameter — no per-block zeroed
+# scratch, no AccumulateGrad add kernel.  Because nothing downstream in the backward pass reads those buffers, the wgrad
+# launches then run on a side stream, off the critical path (most kernels of the attention backward occupy < 64 of the
+# 148 SMs).  The side stream is joined automatically at the END of the backward pass that used it (an autograd engine
+# callback), so after loss.backward() every .grad is complete on the current stream like with any other op — clipping,
+# optimizer.step or hooks need no extra call; join_wgrad() remains for callers outside an autograd backward.
 _wgrad_streams = {}
 _wgrad_pending = set()  # devices whose side stream has work the current stream has not waited for yet
+_join_queued = False
 
 
 def _wgrad_side(dev):
@@ -295,6 +318,8 @@ def _wgrad_side(dev):
 
 def join_wgrad():
     """The current stream waits for every weight-gradient kernel issued on the side streams so far."""
+    global _join_queued
+    _join_queued = False
     # only streams with un-joined work: waiting on an idle side stream would, during CUDA-graph capture, make the
     # capturing stream depend on a stream that is not part of the capture
     for key in list(_wgrad_pending):
@@ -302,24 +327,44 @@ def join_wgrad():
     _wgrad_pending.clear()
 
 
+def mark_side_pending(dev):
+    """Records that `dev`'s side stream carries un-joined gradient work and arranges the join at the end of the
+    running backward pass (no-op outside one: the caller joins with join_wgrad / FlatGradients.sync)."""
+    global _join_queued
+    _wgrad_pending.add(dev.index if dev.index is not None else torch.cuda.current_device())
+    if not _join_queued:
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join_wgrad)
+            _join_queued = True
+        except RuntimeError:  # not inside a backward pass
+            pass
+
+
+def fused_grad_enabled(p):
+    """True when parameter `p` is owned by a live ddp.FlatGradients with fused accumulation switched on."""
+    ref = getattr(p, "_eda_fused_grad_owner", None)
+    owner = ref() if ref is not None else None
+    return owner is not None and owner.fused
+
+
 def _grad_buffers(params):
     """Per parameter: its existing gradient buffer when fused accumulation applies, else None."""
     out = []
     for p in params:
-        g = getattr(p, "grad", None) if (FUSED_WGRAD and p is not None) else None
+        g = getattr(p, "grad", None) if (p is not None and fused_grad_enabled(p)) else None
         out.append(g if (g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.shape == p.shape) else None)
     return out
 
 
 def wgrad_side(problems, N, K, sums=()):
     """eda_wgrad on the side stream, ordered after everything issued on the current stream so far.  Only for
-    problems whose outputs are fused-accumulation buffers (see FUSED_WGRAD).  `sums`: (problem index, a, b) triples —
+    problems whose outputs are fused-accumulation buffers (see fused_grad_enabled).  `sums`: (problem index, a, b) triples —
     that problem's x is a + b, formed on the side stream too (one elementwise add instead of a second wgrad problem
     for "x + pos" inputs)."""
     dev = problems[0]["dy"].device
     cur, side = torch.cuda.current_stream(dev), _wgrad_side(dev)
     side.wait_stream(cur)
-    _wgrad_pending.add(dev.index if dev.index is not None else torch.cuda.current_device())
+    mark_side_pending(dev)
     with torch.cuda.stream(side):
         for i, a, b in sums:
             problems[i]["x"] = a + b  # allocated and consumed on the side stream
@@ -511,7 +556,9 @@ class _MHABlockFn(torch.autograd.Function):
             dict(x=v_in, w_packed=wv, bias=ib[2 * E:], y_batch_rows=Nk, round_tf32=True),
         ], E, E)
         p_attn, seed_attn, p_out, seed_out = drop
-        train = any(ctx.needs_input_grad) and use_cuda_backward()
+        # eda_attention_backward is instantiated for head dims 32 and 36 (the forward also takes 64): other sizes
+        # differentiate through the torch restatement instead of failing at backward() time
+        train = any(ctx.needs_input_grad) and use_cuda_backward() and (E // H) in CUDA_BACKWARD_HEAD_DIMS
         lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if train else None
         c = attention_raw(q, k, v, mask, B, Nq, Nk, H, dropout=(p_attn, seed_attn) if p_attn > 0 else None, lse=lse)
         res = residual.contiguous() if residual is not None else None

@@ -98,19 +98,24 @@ class Pointnet2Backbone(nn.Module):
         if self._side is None or self._side.device != xyz.device:
             self._side = torch.cuda.Stream(device=xyz.device)
         return fps_chain(xyz, [sa.npoint for sa in (self.sa1, self.sa2, self.sa3, self.sa4)], self._side,
-                         pipeline_every=self._pipeline_every(features))
+                         pipeline_every=self._pipeline_every(xyz, features))
 
-    def _pipeline_every(self, features):
+    def _pipeline_every(self, xyz, features):
         if not self.pipeline_every or self.training or torch.is_grad_enabled():
             return 0
         if torch.cuda.is_current_stream_capturing() or self.sa1._fusable(features) is None:
             return 0
-        # SA2's features are SA1's output: width known from the module, fusability checked the same way
-        f2 = torch.empty(1, self.sa2.mlp_module.fusable_layers()[0][0].in_channels - 3, 1, device=features.device) \
-            if self.sa2.mlp_module.fusable_layers() else None
-        if f2 is None or self.sa2._fusable(f2) is None:
-            return (self.pipeline_every[0],) if isinstance(self.pipeline_every, (list, tuple)) else self.pipeline_every
-        return self.pipeline_every
+        first = self.pipeline_every[0] if isinstance(self.pipeline_every, (list, tuple)) else self.pipeline_every
+        # SA2's features are SA1's output: its width is known from the modules, so fusability is decided on channel
+        # counts alone (nothing is allocated; `features` may be None for an xyz-only cloud)
+        l1, l2 = self.sa1.mlp_module.fusable_layers(), self.sa2.mlp_module.fusable_layers()
+        sa2_ok = (l1 is not None and l2 is not None and len(l2) == 3 and self.sa2.fuse and self.sa2.pooling == "max"
+                  and self.sa2.use_xyz and self.sa2.npoint is not None
+                  and l2[0][0].in_channels == l1[-1][0].out_channels + 3
+                  and fused.fusable(l1[-1][0].out_channels, [conv.out_channels for conv, _ in l2], self.sa2.nsample))
+        if not sa2_ok or not isinstance(self.pipeline_every, (list, tuple)):
+            return (first,)
+        return tuple(self.pipeline_every)
 
     def forward(self, pointcloud, end_points=None):
         """pointcloud (B, N, 3 + input_feature_dim) -> end_points dict with sa{1..4}_{xyz,features},

@@ -8,8 +8,10 @@ static thread_local char g_last_err[256] = "";
 void set_last_cuda_error(cudaError_t e, const char *where) {
   snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
-static const uint32_t *g_dropout_epoch = nullptr;
-const uint32_t *dropout_epoch_ptr() { return __atomic_load_n(&g_dropout_epoch, __ATOMIC_RELAXED); }
+// A launch attribute of the CALLING THREAD (like the current device / stream), not process state: two threads driving
+// two models or devices never see each other's epoch word.
+static thread_local const uint32_t *t_dropout_epoch = nullptr;
+const uint32_t *dropout_epoch_ptr() { return t_dropout_epoch; }
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -34,7 +36,7 @@ unsigned long long eda_launch_count(void) { return __atomic_load_n(&eda::g_launc
 int eda_version(void) { return 100; }
 
 int eda_dropout_set_epoch(const unsigned int *device_word) {
-  __atomic_store_n(&eda::g_dropout_epoch, reinterpret_cast<const uint32_t *>(device_word), __ATOMIC_RELAXED);
+  eda::t_dropout_epoch = reinterpret_cast<const uint32_t *>(device_word);
   return EDA_OK;
 }
 

@@ -347,14 +347,11 @@ template <int D>
 int launch_attention(const AttnParams &p, int B, cudaStream_t st) {
   size_t smem = Dims<D>::smem_bytes;
   if (smem < 80 * 1024) smem = 80 * 1024;  // at most two CTAs per SM: their 2 x 256 TMEM columns always fit
-  static bool attr_set = false;
-  if (!attr_set) {
-    EDA_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "attention smem attr");
-    EDA_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "attention smem attr");
-    attr_set = true;
-  }
+  static SmemAttr attr_plain, attr_drop;  // per template instance (D), per device inside
+  if (p.drop_thresh)
+    EDA_CUDA_TRY(attr_drop.ensure(attention_kernel<D, true>, smem), "attention smem attr");
+  else
+    EDA_CUDA_TRY(attr_plain.ensure(attention_kernel<D, false>, smem), "attention smem attr");
   dim3 grid((unsigned)((p.Nq + kRows - 1) / kRows), (unsigned)p.H, (unsigned)B);
   if (p.drop_thresh)
     attention_kernel<D, true><<<grid, kThreads, smem, st>>>(p);

@@ -374,14 +374,11 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
 template <int D, bool kKeyRows>
 int launch_one(const AttnBwdTcParams &p, int B, cudaStream_t st) {
   const size_t smem = BDims<D>::smem_bytes(kKeyRows);
-  static bool attr_set = false;
-  if (!attr_set) {
-    EDA_CUDA_TRY(cudaFuncSetAttribute(attention_backward_tc_kernel<D, kKeyRows, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attn bwd smem attr");
-    EDA_CUDA_TRY(cudaFuncSetAttribute(attention_backward_tc_kernel<D, kKeyRows, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attn bwd smem attr");
-    attr_set = true;
-  }
+  static SmemAttr attr_plain, attr_drop;
+  if (p.drop_thresh)
+    EDA_CUDA_TRY(attr_drop.ensure(attention_backward_tc_kernel<D, kKeyRows, true>, smem), "attn bwd smem attr");
+  else
+    EDA_CUDA_TRY(attr_plain.ensure(attention_backward_tc_kernel<D, kKeyRows, false>, smem), "attn bwd smem attr");
   const int n = kKeyRows ? p.Nk : p.Nq;
   dim3 grid((unsigned)((n + kRows - 1) / kRows), (unsigned)p.H, (unsigned)B);
   if (p.drop_thresh)

@@ -184,9 +184,8 @@ int launch_ball_query(const float *new_xyz, const int *centre_idx, const float *
   }
   const size_t smem = (size_t)2 * kTile * 3 * sizeof(float) + (size_t)kBqWarps * kQ * nsample * sizeof(int);
   if (smem > 200 * 1024) return EDA_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024)
-    EDA_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "ball_query smem attr");
+  static SmemAttr attr;
+  if (smem > 48 * 1024) EDA_CUDA_TRY(attr.ensure(ball_query_kernel, smem), "ball_query smem attr");
   // bulk copies need 16-byte aligned sources and sizes: every scene/tile starts at a multiple of 4 points
   const int use_tma = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(xyz) & 15u) == 0);
   const float r2 = radius * radius;  // f32 product, ball_query_gpu.cu:27

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include "../../include/eda_b200.h"
 
 namespace eda {
@@ -147,6 +149,28 @@ const uint32_t *dropout_epoch_ptr();
 __device__ __forceinline__ uint32_t effective_seed(uint32_t seed, const uint32_t *epoch) {
   return epoch ? seed + __ldg(epoch) : seed;
 }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function attribute: this records, per device, the
+// largest value already applied for ONE kernel (one static instance per kernel / template instance) so the launch path
+// pays an atomic load instead of a driver call; raising it is serialised by a mutex (threads, several devices in one
+// process).  Devices beyond kMaxDev simply set the attribute on every launch.
+struct SmemAttr {
+  static constexpr int kMaxDev = 64;
+  std::atomic<size_t> applied[kMaxDev];
+  std::mutex mu;
+  template <typename F>
+  cudaError_t ensure(F *fn, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool tracked = dev >= 0 && dev < kMaxDev;
+    if (tracked && bytes <= applied[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(mu);
+    if (tracked && bytes <= applied[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && tracked) applied[dev].store(bytes, std::memory_order_release);
+    return e;
+  }
+};
 
 // SM count of the current device (cached per device: cudaDeviceGetAttribute costs ~1 us per call on the launch path).
 int sm_count();

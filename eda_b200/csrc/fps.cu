@@ -87,13 +87,16 @@ struct Layout {
   }
 };
 
-// One CTA writes idxs = 0 .. m-1 and publishes every progress milestone the full kernel would have.
+// One CTA writes idxs = 0 .. m-1 and publishes every progress milestone the full kernel would have: milestone j
+// has its OWN counter word progress[j] (a single shared word would let the scenes of an early wave release a chunk
+// that later scenes have not reached yet).
 __device__ __forceinline__ void fps_write_identity(int *__restrict__ idxs, int m, int *__restrict__ progress, int every) {
   for (int i = threadIdx.x; i < m; i += blockDim.x) idxs[i] = i;
   if (progress != nullptr) {
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(progress, (m + every - 1) / every);
+    const int nmarks = (m + every - 1) / every;
+    for (int j = threadIdx.x; j < nmarks; j += blockDim.x) atomicAdd(progress + j, 1);
   }
 }
 
@@ -168,6 +171,7 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
   if (rank == 0 && tid == 0) idxs[0] = 0;
 
   int next_mark = (progress != nullptr) ? min(every, m) : 0;  // sample count at which the next milestone is published
+  int mark = 0;                                               // its index = which counter word it increments
   for (int it = 1; it < m; ++it) {
     const int buf = it & 1;
     if (CL > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], CL * 20);
@@ -272,7 +276,7 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
       if (it + 1 == next_mark) {  // (no per-iteration division: thread 0's warp is on the critical chain)
         next_mark = min(next_mark + every, m);
         __threadfence();
-        atomicAdd(progress, 1);
+        atomicAdd(progress + mark++, 1);
       }
     }
   }
@@ -314,6 +318,7 @@ fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float
   if (tid == 0) idxs[0] = 0;
   __syncthreads();
   int next_mark = (progress != nullptr) ? min(every, m) : 0;
+  int mark = 0;
   for (int it = 1; it < m; ++it) {
     const int buf = it & 1;
     float best = -1.0f;
@@ -343,7 +348,7 @@ fps_global_kernel(const float *__restrict__ xyz_all, int N, int m, int lb, float
       if (it + 1 == next_mark) {  // (no per-iteration division: thread 0's warp is on the critical chain)
         next_mark = min(next_mark + every, m);
         __threadfence();
-        atomicAdd(progress, 1);
+        atomicAdd(progress + mark++, 1);
       }
     }
   }
@@ -429,9 +434,18 @@ int launch_cluster(const float *xyz, int B, int N, int m, const Layout &lay, int
                    cudaStream_t st) {
   auto kern = fps_cluster_kernel<P2, CL, T>;
   const size_t smem = (size_t)2 * P2 * T * 4 * sizeof(float);
-  EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps smem attr");
-  if (CL > 8)
-    EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "fps cluster attr");
+  static SmemAttr smem_attr;  // per template instance
+  static std::atomic<unsigned long long> nonportable_devs{0};
+  EDA_CUDA_TRY(smem_attr.ensure(kern, smem), "fps smem attr");
+  if (CL > 8) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (!bit || !(nonportable_devs.load(std::memory_order_acquire) & bit)) {
+      EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "fps cluster attr");
+      nonportable_devs.fetch_or(bit, std::memory_order_release);
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * CL));
   cfg.blockDim = dim3(T);
@@ -606,13 +620,10 @@ int eda_fps_identity_check(const float *xyz, int B, int n, int m, float *dsel, i
   const int np = n < m ? n : m;
   const size_t smem1 = (size_t)np * 3 * sizeof(float), smem2 = (size_t)np * 4 * sizeof(float);
   if (smem2 > 200 * 1024) return EDA_ERR_UNSUPPORTED;
-  static size_t smem_set = 0;
-  if (smem2 > 48 * 1024 && smem2 > smem_set) {
-    EDA_CUDA_TRY(cudaFuncSetAttribute(fps_identity_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
-                 "identity smem attr");
-    EDA_CUDA_TRY(cudaFuncSetAttribute(fps_identity_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
-                 "identity smem attr");
-    smem_set = smem2;
+  static SmemAttr attr1, attr2;
+  if (smem2 > 48 * 1024) {
+    EDA_CUDA_TRY(attr1.ensure(fps_identity_pass1_kernel, smem2), "identity smem attr");
+    EDA_CUDA_TRY(attr2.ensure(fps_identity_pass2_kernel, smem2), "identity smem attr");
   }
   dim3 g1((unsigned)((m + kIdThreads - 1) / kIdThreads), (unsigned)B), g2((unsigned)((n + kIdThreads - 1) / kIdThreads), (unsigned)B);
   fps_identity_pass1_kernel<<<g1, kIdThreads, smem1, st>>>(xyz, n, m, dsel, not_identity);

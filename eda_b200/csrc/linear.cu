@@ -660,12 +660,8 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   const size_t out_tile = (size_t)kRows * (NS + 4) * sizeof(float);
   if (smem < out_tile) smem = out_tile;
   smem += 1024;  // alignment slack
-  static size_t smem_set = 0;  // one process per GPU: the attribute is raised once per size increase
-  if (smem > smem_set) {
-    EDA_CUDA_TRY(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "linear smem attr");
-    smem_set = smem;
-  }
+  static SmemAttr attr;  // raised once per size increase and device
+  EDA_CUDA_TRY(attr.ensure(linear_kernel, smem), "linear smem attr");
   if (p.ln && p.S > 1) {
     // LayerNorm needs whole rows: the S column slices of a row tile form a thread-block cluster and exchange
     // their per-row statistics through distributed shared memory

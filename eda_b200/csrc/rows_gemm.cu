@@ -157,17 +157,12 @@ extern "C" int eda_rows_gemm(const float *x, int ldx, const float *in_scale, con
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.y = y; p.rows = rows; p.w_sn = w_stride_n;
   p.w_sk = w_stride_k; p.ldx = ldx; p.ldy = ldy; p.K = K; p.N = N; p.ntiles = (int)ntiles;
   const size_t smem = (size_t)kRgNc * (K + 4) * 4 + (size_t)kRgStages * kRgRows * kRgPx * 4 + 2 * kRgMaxK * 4;
-  static size_t smem_set[2] = {0, 0};
+  static SmemAttr attr[2];
   const int which = in_scale ? 1 : 0;
-  if (smem > smem_set[which]) {
-    if (which)
-      EDA_CUDA_TRY(cudaFuncSetAttribute(rows_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                   "rows_gemm smem attr");
-    else
-      EDA_CUDA_TRY(cudaFuncSetAttribute(rows_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                   "rows_gemm smem attr");
-    smem_set[which] = smem;
-  }
+  if (which)
+    EDA_CUDA_TRY(attr[1].ensure(rows_gemm_kernel<true>, smem), "rows_gemm smem attr");
+  else
+    EDA_CUDA_TRY(attr[0].ensure(rows_gemm_kernel<false>, smem), "rows_gemm smem attr");
   const int sms = sm_count();
   const int ny = (N + kRgNc - 1) / kRgNc;
   long long gx = sms / ny;

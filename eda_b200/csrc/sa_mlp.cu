@@ -584,12 +584,8 @@ static int sa_mlp_forward_impl(const float *xyz, const float *new_xyz, const int
   }
 
   const size_t smem = (size_t)kRing * kSlotBytes + 3 * kMaxC * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    EDA_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                 "sa smem attr");
-    attr_set = true;
-  }
+  static SmemAttr attr;
+  EDA_CUDA_TRY(attr.ensure(sa_mlp_kernel, smem), "sa smem attr");
   const int sms = sm_count();
   const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
   sa_mlp_kernel<<<grid, kThreads, smem, st>>>(p);

@@ -9,6 +9,8 @@ all-reduce — on NVSwitch the cost is launch latency, not link count, so one 85
 25 MB ones.  Inference needs no collective at all: scenes are independent (every kernel indexes
 blockIdx = scene), so rank r simply owns scenes [r*B, (r+1)*B).
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -39,9 +41,11 @@ class FlatGradients:
     """
 
     def __init__(self, module, fused_weight_grads=True):
-        """fused_weight_grads: let the attention-layer backward accumulate weight gradients straight into these
-        buffers from a side stream (attn_ops.FUSED_WGRAD) instead of returning them to autograd; `sync()` (called by
-        `all_reduce_mean`) orders the current stream after those kernels."""
+        """fused_weight_grads: let the backward kernels accumulate weight gradients of THESE parameters straight into
+        these buffers from a side stream instead of returning them to autograd.  The parameters are tagged with a weak
+        reference to this object (nothing process-wide: other models in the process are untouched, and the tag dies
+        with the object); the side stream is joined at the end of every backward pass, so `.grad` is complete on the
+        current stream after `loss.backward()` returns."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise RuntimeError("FlatGradients: module has no trainable parameters")
@@ -55,9 +59,11 @@ class FlatGradients:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             off += n
-        if fused_weight_grads and dev.type == "cuda":
-            from . import attn_ops
-            attn_ops.FUSED_WGRAD = True
+        self.fused = bool(fused_weight_grads and dev.type == "cuda")
+        if self.fused:
+            ref = weakref.ref(self)
+            for p in self.params:
+                p._eda_fused_grad_owner = ref
 
     @property
     def nbytes(self):
@@ -67,13 +73,13 @@ class FlatGradients:
         self.flat.zero_()
 
     def release(self):
-        """Switches fused weight-gradient accumulation off again (process-wide flag): afterwards the backward kernels
-        return their gradients to autograd like any other op.  Call it when this bucket stops being the owner of the
-        model's gradients (e.g. before handing the model to a stock optimizer loop that never calls `sync()`)."""
+        """Switches fused weight-gradient accumulation off for this bucket's parameters: afterwards the backward
+        kernels return their gradients to autograd like any other op."""
         self.sync()
-        if self.flat.is_cuda:
-            from . import attn_ops
-            attn_ops.FUSED_WGRAD = False
+        self.fused = False
+        for p in self.params:
+            if getattr(p, "_eda_fused_grad_owner", None) is not None:
+                del p._eda_fused_grad_owner
 
     def sync(self):
         """Gradients are complete on the current stream after this (joins the side-stream weight-gradient kernels)."""

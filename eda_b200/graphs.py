@@ -65,6 +65,10 @@ class GraphedTrainStep:
     by that host work; replayed, only the device time remains.  Weight packing is captured too — one batched launch at the
     start of the step refreshes persistent packed copies of every weight (attn_ops.PackRegistry) — so replays after an
     optimizer step use the updated parameters; BatchNorm running statistics and `num_batches_tracked` are updated by captured device ops.
+    Warm-up runs real steps on the example inputs; BatchNorm buffers (running statistics, num_batches_tracked) and the
+    dropout epoch are snapshotted before and restored after it, so the first user step starts from the state the model
+    had when it was handed in.  BatchNorm `momentum` is read on the host while recording and is FROZEN into the graph
+    (a BNMomentumScheduler or momentum=None needs a re-capture).
     Restrictions: fixed shapes; parameters, gradients (FlatGradients) and inputs must stay at their addresses.  Dropout
     (the reference's default 0.1) is supported: the host-drawn seeds are frozen into the graph, and a device epoch word
     that the graph increments once per replay is added to them by the kernels (`self.dropout_epoch`)."""
@@ -105,12 +109,12 @@ class GraphedTrainStep:
             flat_grads.sync()  # side-stream weight-gradient kernels rejoin the (capturing) stream
             return loss.detach()
 
-        saved = attn_ops.PACK_CACHE
-        attn_ops.PACK_CACHE = False
-        attn_ops.PACK_REGISTRY = registry
+        registry.attach(model)  # per-model context: only THIS model's modules consult the registry
+        registry.active = True
         lib = _lib.load()
         if epoch is not None:
             lib.eda_dropout_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
+        buffers = [(b, b.detach().clone()) for b in model.buffers()]
         try:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -122,9 +126,14 @@ class GraphedTrainStep:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.loss = step()
+            with torch.no_grad():  # undo the warm-up's side effects (capture itself executes nothing)
+                for b, saved in buffers:
+                    b.copy_(saved)
+                if epoch is not None:
+                    epoch.zero_()
+                flat_grads.zero()
         finally:
-            attn_ops.PACK_CACHE = saved
-            attn_ops.PACK_REGISTRY = None
+            registry.active = False  # eager calls on the model go back to the version-keyed caches
             lib.eda_dropout_set_epoch(None)  # eager launches after this are unaffected; the graph keeps the baked pointer
 
     def __call__(self, *inputs):

@@ -43,13 +43,22 @@ def point_major(features):
     """(B,C,N) -> a (B,N,C)-shaped tensor whose rows are contiguous, reusing the copy a previous fused
     layer left behind when there is one."""
     cached = getattr(features, "_eda_point_major", None)
-    if cached is not None and cached.shape == (features.size(0), features.size(2), features.size(1)) \
-            and cached.device == features.device:
-        return cached
+    if cached is not None:
+        pm, f_version, pm_version = cached
+        # an in-place edit of either tensor since the copy was attached (scaling, masking, relu_ ...) bumps its
+        # `_version`: the copy is stale then and is rebuilt from `features`
+        if pm.shape == (features.size(0), features.size(2), features.size(1)) and pm.device == features.device \
+                and features._version == f_version and pm._version == pm_version:
+            return pm
     t = features.transpose(1, 2)
     if t.is_contiguous():
         return t
     return transpose_last2(features.contiguous())
+
+
+def attach_point_major(features, pm):
+    """Remembers `pm` (B,N,C) as the point-major copy of `features` (B,C,N), valid while neither is modified."""
+    features._eda_point_major = (pm, features._version, pm._version)
 
 
 def fusable(C, widths, nsample):
@@ -244,7 +253,7 @@ class FusedSAFunction(torch.autograd.Function):
         if ctx.cuda_bw:
             from .. import attn_ops
             # conv weights of layers 2 / 3 whose gradient buffers exist: their wgrad kernels accumulate straight
-            # into them from the side stream (attn_ops.FUSED_WGRAD); layer 1 needs a column permutation, so it stays
+            # into them from the side stream (attn_ops.fused_grad_enabled); layer 1 needs a column permutation, so it stays
             ctx.gbufs = attn_ops._grad_buffers((params[4], params[8], params[0]))
         ctx.rows = None
         if ctx.cuda_bw and training and os.environ.get("EDA_SA_RECOMPUTE", "0") != "1":
@@ -358,10 +367,9 @@ def _sa_backward_cuda(ctx, grad_out):
         for l in (2, 1, 0):
             xin, sc, sh = src[l]
             if l == 0 and g1 is not None:
-                dev_i = dev.index if dev.index is not None else torch.cuda.current_device()
                 cur, side = torch.cuda.current_stream(dev), ops._wgrad_side(dev)
                 side.wait_stream(cur)
-                ops._wgrad_pending.add(dev_i)
+                ops.mark_side_pending(dev)
                 with torch.cuda.stream(side):
                     ops.wgrad([dict(dy=dz, x=xin, dw=dWl[0])], widths[0], Kin[0])
                     gv = g1.view(widths[0], C + 3)
@@ -419,13 +427,26 @@ def sa_params(layers):
 # Pipelined inference path: ball query + fused MLP on the centres FPS has already produced
 # ---------------------------------------------------------------------------------------------------
 class ProgressCounter:
-    """A device word that eda_furthest_point_sampling_progress increments (never reset) plus the host-side
-    running total, so every launch knows which absolute values its milestones will reach."""
+    """Device words that eda_furthest_point_sampling_progress increments (never reset) — ONE WORD PER MILESTONE, so
+    "word j reached its previous total + B" means every scene has passed milestone j, however the scenes were
+    scheduled — plus the host-side running totals, so every launch knows which absolute values it will reach."""
     _by_device = {}
+    MAX_MARKS = 64      # milestones per launch
+    RING = 4096         # words; consecutive launches take consecutive slices, so launches in flight at the same time
+                        # (other streams, other models) never share a word
 
     def __init__(self, device):
-        self.word = torch.zeros(1, dtype=torch.int32, device=device)
-        self.total = 0
+        self.words = torch.zeros(self.RING, dtype=torch.int32, device=device)
+        self.totals = [0] * self.RING
+        self.next = 0
+
+    def take(self, n):
+        """First word index of a fresh slice of n words."""
+        if self.next + n > self.RING:
+            self.next = 0
+        first = self.next
+        self.next += n
+        return first
 
     @classmethod
     def get(cls, device):
@@ -439,15 +460,16 @@ class ProgressCounter:
 class PipelinedFPS:
     """Handle of an in-flight furthest-point sampling launched with progress milestones every `every` samples."""
 
-    def __init__(self, inds, counter, base, every, done_event):
-        self.inds, self.counter, self.base, self.every, self.done_event = inds, counter, base, every, done_event
+    def __init__(self, inds, counter, first, targets, every, done_event):
+        self.inds, self.counter, self.targets, self.every, self.done_event = inds, counter, targets, every, done_event
+        self.first = first
         self.B, self.m = inds.shape
-        self.nchunks = (self.m + every - 1) // every
+        self.nchunks = len(targets)
 
     def wait_chunk(self, stream, j):
-        """Makes `stream` wait (on the device, no SM occupied) until centres [0, (j+1)*every) of every scene exist."""
-        rc = _lib.load().eda_stream_wait_value32(ctypes.c_void_p(stream.cuda_stream), _p(self.counter.word),
-                                                 int(self.base + self.B * (j + 1)))
+        """Makes `stream` wait (on the device, no SM occupied) until centres [0, (j+1)*every) of EVERY scene exist."""
+        word = ctypes.c_void_p(self.counter.words.data_ptr() + 4 * (self.first + j))
+        rc = _lib.load().eda_stream_wait_value32(ctypes.c_void_p(stream.cuda_stream), word, int(self.targets[j]))
         _lib.check(rc, "stream_wait_value32")
 
 
@@ -457,19 +479,27 @@ def launch_pipelined_fps(xyz, npoint, every, stream, not_identity=None):
     lib = _lib.load()
     B, N, _ = xyz.shape
     counter = ProgressCounter.get(xyz.device)
+    nchunks = (npoint + every - 1) // every
+    if nchunks > ProgressCounter.MAX_MARKS:
+        raise RuntimeError(f"eda_b200: at most {ProgressCounter.MAX_MARKS} FPS progress milestones per launch")
+    first = counter.take(nchunks)
     with torch.cuda.stream(stream):
         inds = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
         nbytes = lib.eda_fps_scratch_bytes(B, N, npoint)
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=xyz.device) if nbytes else None
         with torch.cuda.device(xyz.device):
-            rc = lib.eda_furthest_point_sampling_ex(_p(xyz), B, N, npoint, _p(scratch), _p(inds), _p(counter.word),
+            rc = lib.eda_furthest_point_sampling_ex(_p(xyz), B, N, npoint, _p(scratch), _p(inds),
+                                                    ctypes.c_void_p(counter.words.data_ptr() + 4 * first),
                                                     int(every), _p(not_identity), ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "furthest_point_sampling_progress")
-        base = counter.total
-        counter.total += B * ((npoint + every - 1) // every)
+        targets = []
+        for j in range(first, first + nchunks):  # every scene adds exactly 1 to each of its milestone words
+            counter.totals[j] = (counter.totals[j] + B) & 0xFFFFFFFF
+            t = counter.totals[j]
+            targets.append(t - (1 << 32) if t >= (1 << 31) else t)
         done = torch.cuda.Event()
         done.record(stream)
-    return PipelinedFPS(inds, counter, base, every, done)
+    return PipelinedFPS(inds, counter, first, targets, every, done)
 
 
 def eval_packed(module, layers, C, widths, dev):
@@ -484,7 +514,9 @@ def eval_packed(module, layers, C, widths, dev):
             tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
     key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (C, str(dev))
     from .. import attn_ops
-    hit = module.__dict__.get("_eda_sa_eval_cache") if attn_ops.PACK_CACHE else None
+    # inside a GraphedTrainStep capture of this model the fold + pack must be recorded, not reused
+    use_cache = attn_ops.PACK_CACHE and attn_ops.active_registry(module) is None
+    hit = module.__dict__.get("_eda_sa_eval_cache") if use_cache else None
     if hit is not None and hit[0] == key:
         return hit[1], hit[2]
     nfl = lib.eda_sa_mlp_packed_floats(C, *widths)
@@ -538,5 +570,5 @@ def sa_forward_pipelined(module, xyz, features, fps):
     main.wait_event(fps.done_event)
     new_xyz = torch.gather(xyz, 1, fps.inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     new_features = transpose_last2(out)
-    new_features._eda_point_major = out
+    attach_point_major(new_features, out)
     return new_xyz, new_features, out, fps.inds

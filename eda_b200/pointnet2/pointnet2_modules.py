@@ -77,7 +77,7 @@ class PointnetSAModuleVotes(nn.Module):
             idx = pointnet2_utils.ball_query(self.radius, self.nsample, xyz, new_xyz)
             new_features, feat_pm = fused.FusedSAFunction.apply(self, xyz, new_xyz, features, idx,
                                                                 *fused.sa_params(layers))
-            new_features._eda_point_major = feat_pm  # lets the next fused layer skip a transpose
+            fused.attach_point_major(new_features, feat_pm)  # lets the next fused layer skip a transpose
             return new_xyz, new_features, inds
 
         unique_cnt = None

@@ -72,8 +72,10 @@ EDA_API int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, v
                                 void *stream);
 
 /* Same sampling, publishing progress: after every `every` samples (and after the last one) of a scene, that
- * scene's cluster makes its indices so far visible device-wide and adds 1 to *progress (never reset by the
- * library: the caller tracks the running total, B increments per milestone).  Together with
+ * scene's cluster makes its indices so far visible device-wide and adds 1 to progress[j], j = 0, 1, ... the index
+ * of the milestone — `progress` is an array of ceil(m / every) words, ONE PER MILESTONE, so that progress[j]
+ * reaching (previous total + B) means every scene of the batch has passed milestone j even when the scenes run in
+ * several waves (never reset by the library: the caller tracks each word's running total).  Together with
  * eda_stream_wait_value32 this lets a second stream run ball query + the fused MLP on the first centres while
  * the strictly serial sampling of the remaining ones continues on otherwise idle SMs.  every >= 2. */
 EDA_API int eda_furthest_point_sampling_progress(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
@@ -308,8 +310,10 @@ EDA_API int eda_dropout_mask(unsigned int seed, float p, long long rows, int col
 /* Optional dropout epoch: a device word whose value every dropout-applying kernel of this library (forward and
  * backward) adds to its dropout_seed when it RUNS.  A CUDA graph of a training step freezes the host-drawn seeds; with
  * an epoch word that a captured device op increments once per step, every replay still draws fresh masks, identical in
- * that step's forward and backward.  Process-wide setting (the one piece of library state besides the error string and
- * the launch counter); NULL = off (default).  The word must stay allocated while kernels launched under it run. */
+ * that step's forward and backward.  A launch attribute of the CALLING THREAD (thread-local, like the current device):
+ * it applies to kernels this thread launches after the call; NULL = off (default).  Library state is therefore limited
+ * to per-thread values (this pointer, the last error string), a launch counter, and per-device caches of function
+ * attributes (thread-safe).  The word must stay allocated while kernels launched under it run. */
 EDA_API int eda_dropout_set_epoch(const unsigned int *device_word);
 
 /* ---------------------------------------------------------------------------------------

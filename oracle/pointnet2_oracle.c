@@ -9,8 +9,9 @@
  * Parity status: the reference ships NO golden vectors for these ops (its only test is a
  * gradcheck, pointnet2/pointnet2_test.py:18-30).  This oracle is pinned instead against
  * outputs of the reference's own compiled `_ext` (oracle/_ref, built by oracle/build_ref.py)
- * run on the B200 box: see tests/golden/ (fixtures + generating script) and
- * tests/test_gpu_parity.py::test_oracle_matches_reference_ext.
+ * run on the B200 box: see tests/golden/ (fixtures + generating script),
+ * tests/test_golden.py::test_oracle_matches_reference_ext_golden (CPU suite) and
+ * tests/test_gpu_ops.py::test_reference_ext_agrees_on_all_index_ops (GPU box, live against oracle/_ref).
  *
  * Float-op order is taken from the SASS of the reference build for sm_100a
  * (nvcc 12.9 -O2, default -fmad=true):

@@ -86,6 +86,88 @@ def test_pipelined_sa1_equals_plain(every):
 
 
 @pytest.mark.gpu
+def test_pipelined_sa1_many_scenes_in_waves():
+    """B = 40 scenes x 8-CTA clusters do not fit the GPU at once, so the sampler's clusters run in waves: the scenes of
+    the first wave publish ALL their milestones before later scenes start.  Each milestone has its own counter word,
+    so a chunk is only released when every scene reached it (a single summed word released chunks early
+    and the consumers read unwritten centre indices)."""
+    from eda_b200.backbone_module import fps_chain
+    from eda_b200.pointnet2 import fused
+    from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
+
+    torch.manual_seed(0)
+    sa = PointnetSAModuleVotes(npoint=1024, radius=0.2, nsample=32, mlp=[3, 64, 64, 128], use_xyz=True,
+                               normalize_xyz=True).cuda().eval()
+    _randomise_bn(sa, 2)
+    pc = synthetic.point_clouds(40, 50000, "surface").cuda()
+    xyz, feats = pc[..., :3].contiguous(), pc[..., 3:].transpose(1, 2).contiguous()
+    side = torch.cuda.Stream()
+    with torch.no_grad():
+        want_xyz, want_f, want_inds = sa(xyz, feats)
+        for _ in range(2):
+            (handle, _ev), = fps_chain(xyz, [1024], side, pipeline_every=256)
+            got_xyz, got_f, _, got_inds = fused.sa_forward_pipelined(sa, xyz, feats, handle)
+            torch.cuda.synchronize()
+            assert torch.equal(got_inds, want_inds)
+            assert torch.equal(got_xyz, want_xyz)
+            assert torch.equal(got_f, want_f)
+
+
+@pytest.mark.gpu
+def test_pipelined_chunks_with_identity_flags_mixed():
+    """Identity-verified scenes publish all milestones at once while the others are still sampling: with several
+    chunks the consumer must still wait for the slow scenes (one counter word per milestone)."""
+    from eda_b200.pointnet2 import _ext, fused
+    from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
+
+    torch.manual_seed(0)
+    B, n, m = 6, 8192, 2048
+    base = synthetic.point_clouds(B, 30000, "surface", channels=0).cuda().contiguous()
+    inds1 = _ext.furthest_point_sampling(base, n)
+    cur = torch.gather(base, 1, inds1.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()  # FPS-ordered sets
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(0)).cuda()
+    cur[1::2] = cur[1::2][:, perm]  # odd scenes are shuffled: they need the real, serial sampler
+    flags = _ext.fps_identity_flags(cur, m)
+    assert flags.tolist() == [0, 1, 0, 1, 0, 1]
+    sa = PointnetSAModuleVotes(npoint=m, radius=0.3, nsample=16, mlp=[3, 64, 64, 128], use_xyz=True,
+                               normalize_xyz=True).cuda().eval()
+    _randomise_bn(sa, 3)
+    feats = torch.rand(B, 3, n, generator=torch.Generator().manual_seed(1)).cuda()
+    side = torch.cuda.Stream()
+    with torch.no_grad():
+        want_xyz, want_f, want_inds = sa(cur, feats)
+        side.wait_stream(torch.cuda.current_stream())
+        handle = fused.launch_pipelined_fps(cur, m, 256, side, not_identity=flags)
+        got_xyz, got_f, _, got_inds = fused.sa_forward_pipelined(sa, cur, feats, handle)
+        torch.cuda.synchronize()
+    assert torch.equal(got_inds, want_inds)
+    assert torch.equal(got_xyz, want_xyz)
+    assert torch.equal(got_f, want_f)
+
+
+@pytest.mark.gpu
+def test_backbone_xyz_only_input_eval_and_train():
+    """input_feature_dim = 0 (the class default; the reference without --use_color): SA1 has no input features.
+    ADVICE r1: the eval / no_grad forward dereferenced features.device on None."""
+    from oracle import modules_oracle as mo
+
+    torch.manual_seed(0)
+    m = Pointnet2Backbone(input_feature_dim=0, width=1).eval()
+    _randomise_bn(m, 4)
+    pc = synthetic.point_clouds(2, 6000, "surface", channels=0)
+    with torch.no_grad():
+        want = mo.backbone_forward(m.state_dict(), pc)
+        got = m.cuda()(pc.cuda())
+    assert torch.equal(got["sa1_inds"].cpu(), want["sa1_inds"])
+    err = (got["fp2_features"].cpu() - want["fp2_features"]).abs()
+    assert err.max() <= 1e-2 * max(1.0, want["fp2_features"].abs().max().item())
+    m.train()
+    out = m(pc.cuda())
+    out["fp2_features"].sum().backward()
+    assert m.sa1.mlp_module.layer0.conv.weight.grad is not None
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("family", ["surface", "uniform", "dup", "lattice", "origin"])
 def test_fps_identity_shortcut_is_bit_exact(family):
     """Stages 2-4 of the backbone sample from FPS-ordered sets.  The parallel identity check +

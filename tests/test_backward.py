@@ -440,8 +440,8 @@ def test_wgrad_kernel_with_bn_relu_prologue():
 
 
 def test_fused_weight_grad_accumulation_matches_autograd_path():
-    """ddp.FlatGradients lets the wgrad kernels accumulate into param.grad from a side stream (attn_ops.FUSED_WGRAD);
-    after fg.sync() the gradients equal the ones the plain autograd path returns, also when accumulated twice."""
+    """ddp.FlatGradients lets the wgrad kernels accumulate into param.grad from a side stream (per-parameter
+    tag, attn_ops.fused_grad_enabled); after backward() returns the gradients equal the ones the plain autograd path returns, also when accumulated twice."""
     from eda_b200 import attn_ops as ops, ddp, encoder_decoder_layers as edl
 
     m = edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.0, "relu", self_position_embedding="loc_learned", butd=True)
@@ -456,23 +456,30 @@ def test_fused_weight_grad_accumulation_matches_autograd_path():
 
     for prm in m.parameters():
         prm.grad = None
-    assert not ops.FUSED_WGRAD
+    assert not any(ops.fused_grad_enabled(prm) for prm in m.parameters())
     run()
     want = {n: prm.grad.clone() for n, prm in m.named_parameters()}
     try:
         fg = ddp.FlatGradients(m)
-        assert ops.FUSED_WGRAD and fg.check_views()
+        assert all(ops.fused_grad_enabled(prm) for prm in m.parameters()) and fg.check_views()
         run()
         run()
-        fg.sync()
+        # no fg.sync(): the side stream is joined by an autograd-engine callback at the end of each backward pass
+        # (ADVICE r1), so clip_grad_norm_ / optimizer.step right after backward() see complete gradients
+        assert not ops._wgrad_pending
         torch.cuda.synchronize()
         assert fg.check_views()
         # same kernels; the fused path forms q + pos before the tf32 rounding of the weight-gradient operand (as the
         # forward GEMM does), the plain path rounds q and pos separately: ~1e-3 apart on the in-projection weights
         for n, prm in m.named_parameters():
             assert rel(prm.grad, 2 * want[n]) <= 3e-3, n
+        # a second model in the same process is untouched by the first one's bucket
+        other = edl.BiDecoderLayer(ac.E, ac.HEADS, ac.FF, 0.0, "relu", self_position_embedding="loc_learned", butd=True)
+        assert not any(ops.fused_grad_enabled(prm) for prm in other.parameters())
+        fg.release()
+        assert not any(ops.fused_grad_enabled(prm) for prm in m.parameters())
     finally:
-        ops.FUSED_WGRAD = False
+        pass
 
 
 def test_graphed_train_step_with_dropout_draws_fresh_masks_and_correct_gradients():
@@ -507,19 +514,24 @@ def test_graphed_train_step_with_dropout_draws_fresh_masks_and_correct_gradients
             wrapper.forward = fwd
             fg = ddp.FlatGradients(m)
             torch.manual_seed(11)
+            bn = m.self_posembed.position_embedding_head[1]
+            rm0, nb0 = bn.running_mean.clone(), int(bn.num_batches_tracked.item())
             step = _block_grads(mode, lambda: GraphedTrainStep(wrapper, loss_fn, args, fg))
             assert step.dropout_epoch is not None
+            # warm-up steps must not leave BatchNorm buffers / the epoch advanced before the first user step
+            assert torch.equal(bn.running_mean, rm0) and int(bn.num_batches_tracked.item()) == nb0
+            assert int(step.dropout_epoch.item()) == 0
             l1 = step(*args).item()
             g1 = fg.flat.clone()
             l2 = step(*args).item()
             torch.cuda.synchronize()
             assert l1 != l2 and not torch.equal(g1, fg.flat), "replays must draw different dropout masks"
-            assert int(step.dropout_epoch.item()) == 3 + 2  # 3 warm-up steps + 2 replays
+            assert int(step.dropout_epoch.item()) == 2  # 2 replays; the warm-up's 3 increments were rolled back
             grads[mode], losses[mode] = g1, l1
         assert abs(losses["cuda"] - losses["torch"]) <= 1e-5 * abs(losses["torch"])
         assert rel(grads["cuda"], grads["torch"]) <= 2e-2
     finally:
-        ops.FUSED_WGRAD = False
+        pass
 
 
 def test_graphed_train_step_follows_parameter_updates():
@@ -554,4 +566,4 @@ def test_graphed_train_step_follows_parameter_updates():
         assert abs(lg - le.item()) <= 1e-5 * abs(le.item())
         assert rel(gg, fg.flat) <= 1e-3
     finally:
-        ops.FUSED_WGRAD = False
+        pass

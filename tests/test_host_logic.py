@@ -20,11 +20,11 @@ def test_synthetic_inputs_have_configs3_shapes():
     assert all(torch.equal(a, b) for a, b in zip((pc, pos, text, query), (again[0], again[1], again[2], again[6])))
 
 
-def test_flat_gradients_on_cpu_leaves_the_cuda_switches_alone():
-    before = attn_ops.FUSED_WGRAD
+def test_flat_gradients_on_cpu_tags_nothing():
     m = torch.nn.Linear(4, 3)
     fg = ddp.FlatGradients(m)
-    assert attn_ops.FUSED_WGRAD == before            # only a CUDA bucket turns fused weight gradients on
+    assert not fg.fused                              # only a CUDA bucket turns fused weight gradients on
+    assert not any(attn_ops.fused_grad_enabled(p) for p in m.parameters())
     assert fg.check_views() and fg.flat.numel() == 15
     m(torch.ones(2, 4)).sum().backward()
     fg.sync()                                        # no side stream on CPU: a no-op
@@ -33,21 +33,44 @@ def test_flat_gradients_on_cpu_leaves_the_cuda_switches_alone():
     fg.zero()
     assert fg.flat.abs().sum() == 0 and fg.check_views()
     fg.release()                                     # CPU bucket: nothing to switch off, must not raise
-    assert attn_ops.FUSED_WGRAD == before
 
 
-def test_grad_buffers_only_when_enabled():
-    p = torch.nn.Parameter(torch.zeros(3, 3))
-    p.grad = torch.zeros(3, 3)
-    saved = attn_ops.FUSED_WGRAD
-    try:
-        attn_ops.FUSED_WGRAD = False
-        assert attn_ops._grad_buffers((p, None)) == [None, None]
-        attn_ops.FUSED_WGRAD = True
-        got = attn_ops._grad_buffers((p, None, torch.nn.Parameter(torch.zeros(2))))
-        assert got[0] is p.grad and got[1] is None and got[2] is None   # no .grad yet -> autograd path
-    finally:
-        attn_ops.FUSED_WGRAD = saved
+def test_fused_grad_buffers_are_scoped_to_the_owning_bucket():
+    """fused weight-gradient accumulation must not be a process-wide switch.  Only parameters tagged by a
+    live FlatGradients whose `fused` flag is on hand their .grad to the kernels; other models in the process, released
+    buckets and dropped buckets go through autograd."""
+    import gc
+
+    class Owner:  # stands in for a CUDA FlatGradients (no GPU in this suite): the tag protocol is what is tested
+        fused = True
+
+    import weakref
+    p, q = torch.nn.Parameter(torch.zeros(3, 3)), torch.nn.Parameter(torch.zeros(3, 3))
+    p.grad, q.grad = torch.zeros(3, 3), torch.zeros(3, 3)
+    assert attn_ops._grad_buffers((p, q, None)) == [None, None, None]        # nobody owns them
+    owner = Owner()
+    p._eda_fused_grad_owner = weakref.ref(owner)
+    got = attn_ops._grad_buffers((p, q, None, torch.nn.Parameter(torch.zeros(2))))
+    assert got[0] is p.grad and got[1] is None and got[2] is None and got[3] is None  # q belongs to "another model"
+    owner.fused = False                                                       # release()
+    assert attn_ops._grad_buffers((p,)) == [None]
+    owner.fused = True
+    del owner
+    gc.collect()
+    assert attn_ops._grad_buffers((p,)) == [None]                             # bucket dropped without release()
+
+
+def test_pack_registry_is_per_model():
+    """the packed-weight registry of a GraphedTrainStep is attached to ITS model's modules."""
+    a, b = torch.nn.Linear(4, 4), torch.nn.Linear(4, 4)
+    reg = attn_ops.PackRegistry(torch.device("cpu"))
+    reg.attach(a)
+    assert attn_ops.active_registry(a) is None       # attached but not recording
+    reg.active = True
+    assert attn_ops.active_registry(a) is reg and attn_ops.active_registry(b) is None
+    reg.active = False
+    reg.detach(a)
+    assert "_eda_pack_registry" not in a.__dict__
 
 
 def test_hand_built_abi_structs_match_the_header_layout():
