@@ -3,16 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (BASELINE.json configs[1]): PointnetSAModuleVotes forward, B = 8 scenes per GPU,
-N = 50 000 points (xyz + rgb) -> SA1 (2048 centres, r = 0.2, nsample 64, MLP 6-64-64-128)
--> SA2 (1024 centres, r = 0.4, nsample 32, MLP 131-128-128-256), the first two stages of
-models/backbone_module.py:44-60, eval-mode BatchNorm.  One step = FPS -> gather -> ball query ->
-fused group+MLP+max-pool, twice.  Metric: scenes/s.
+Workload = BASELINE.json's metric, on the configuration it is quoted on (configs[3]): ONE TRAINING STEP (forward +
+backward + DDP gradient all-reduce) of the hot path — Pointnet2Backbone (models/backbone_module.py:26-144) ->
+3 x BiEncoderLayer -> 6 x BiDecoderLayer (models/encoder_decoder_layers.py:189-407) — on B = 8 scenes per GPU of
+N = 50 000 points (xyz + rgb), L = 80 text tokens, D = 132 detected boxes, K = 256 queries, d_model 288, 8 heads,
+train-mode BatchNorm (SyncBatchNorm semantics on > 1 GPU like main_utils.py:335-338), dropout 0 (the parity
+configuration), synthetic quadratic loss (the reference's loss / heads / text tower are outside the path),
+weak scaling over GPUs.  Metric: scenes/s.
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, L2 flushed between
-steps); `e2e` = same step through the module API from pinned host buffers with H2D/D2H inside the timed
-region; `roofline` = the dominant kernel (SA1 furthest-point sampling) against the measured HBM peak;
-`cpu_baseline` / `--impl reference` = the CPU port of the reference path (oracle/) on the host cores.
+One JSON line on stdout (rank 0):
+  value         K steps with all inputs resident in HBM (CUDA events per step, L2 flushed between steps), max over ranks
+  e2e           the same step through the public API with HOST inputs: every step copies all eight input tensors from
+                pinned host memory and reads the loss back; copies inside the timed region
+  roofline      the dominant kernel family of the step (the tcgen05 linear GEMM) timed alone against the measured tf32 peak
+  cpu_baseline  the reference's own Python modules on CPU (+ the C port of `_ext`, which the reference does not have on
+                CPU), same step, bounded sample
+  extras        ref_cuda (the reference CUDA build timed on this box: the denominator of the >= 10x north-star target),
+                eval_forward (configs[2] shapes), sa_forward (configs[1]), rooflines (FPS / ball query / attention / SA
+                MLP), sweep (configs[4]), dropout_0.1
+`--impl reference`: the same training step on the host CPU (reference Python modules + C port of `_ext`), bounded sample.
 """
 import argparse
 import json
@@ -29,10 +38,22 @@ if ROOT not in sys.path:
 
 B_PER_GPU = 8
 N_POINTS = 50000
-SA1 = dict(npoint=2048, radius=0.2, nsample=64, mlp=[3, 64, 64, 128])
-SA2 = dict(npoint=1024, radius=0.4, nsample=32, mlp=[128, 128, 128, 256])
-WORKLOAD = ("configs[1]: PointnetSAModuleVotes forward B=8/GPU N=50000 -> SA1(2048,r.2,ns64,[6,64,64,128]) -> "
-            "SA2(1024,r.4,ns32,[131,128,128,256]), eval-mode BN")
+L_TEXT, D_BOXES, K_QUERIES = 80, 132, 256
+METRIC = "scenes/sec fwd+bwd (N=50000 pts, 256 queries, L=80)"
+WORKLOAD = ("configs[3]: training step (forward + backward + DDP gradient all-reduce) of the hot path "
+            "Pointnet2Backbone -> 3 BiEncoderLayer -> 6 BiDecoderLayer; B=8 scenes/GPU, N=50000 points (xyz+rgb), L=80 text "
+            "tokens, D=132 boxes, K=256 queries, d_model 288, 8 heads, train-mode BatchNorm, dropout 0, synthetic "
+            "quadratic loss")
+CPU_SAMPLE_SCENES = 2  # scenes per step of the CPU legs (bounded sample of the same workload)
+
+
+def config():
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "n_points": N_POINTS, "text_tokens": L_TEXT,
+            "boxes": D_BOXES, "queries": K_QUERIES, "d_model": 288, "loss": "synthetic quadratic (hotpath.quadratic_loss)",
+            "batchnorm": "train mode (batch statistics; synchronised across ranks when n_gpus > 1)", "dropout": 0.0,
+            "sharding": "batch only; one gradient all-reduce per step",
+            "l2": "512 MB memset between timed steps (a step streams ~2 GB of activations, far beyond the 126 MB L2)"}
 
 
 def parse():
@@ -42,90 +63,64 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="eda_b200", choices=["eda_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (development)")
-    ap.add_argument("--no-pipeline", action="store_true", help="SA1 waits for the whole FPS result (development)")
-    ap.add_argument("--no-train", action="store_true", help="skip the fwd_bwd (training step) leg (development)")
+    ap.add_argument("--no-extras", action="store_true", help="skip ref_cuda / eval / sweep / roofline extras (development)")
+    ap.add_argument("--quick-sweep", action="store_true", help="sweep only N in {20k, 50k} (development)")
     return ap.parse_args()
 
 
-def measured_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        try:
-            d = json.load(open(path))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        except Exception:  # noqa: BLE001
-            pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
-
-
 # ------------------------------------------------------------------------------------------------
-# CPU port of the reference path (oracle/) — the reported baseline and the --impl reference arm
+# CPU legs: the reference's own Python modules + the C port of `_ext` (oracle/) — reported baseline and reference arm
 # ------------------------------------------------------------------------------------------------
-def build_cpu_modules(seed=0):
-    """Reference-named parameters for SA1/SA2 (kaiming conv weights, default BatchNorm), as nn modules on CPU."""
-    import torch
-
-    from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
-
-    torch.manual_seed(seed)
-    sa1 = PointnetSAModuleVotes(use_xyz=True, normalize_xyz=True, **{**SA1, "mlp": list(SA1["mlp"])})
-    sa2 = PointnetSAModuleVotes(use_xyz=True, normalize_xyz=True, **{**SA2, "mlp": list(SA2["mlp"])})
-    return sa1.eval(), sa2.eval()
-
-
-def cpu_step(pc, sd1, sd2):
-    """One pass of the workload over the scenes in `pc` (b,N,6) with the CPU oracle; returns sa2 features."""
-    import torch
-
-    from oracle import modules_oracle as mo
-
-    xyz = pc[..., :3].contiguous()
-    feats = pc[..., 3:].transpose(1, 2).contiguous()
-    with torch.no_grad():
-        l1 = mo.layers_from_state_dict(sd1, "mlp_module.", 3)
-        x1, f1, _, _ = mo.sa_module_forward(xyz, feats, SA1["npoint"], SA1["radius"], SA1["nsample"], l1, True, False)
-        l2 = mo.layers_from_state_dict(sd2, "mlp_module.", 3)
-        _, f2, _, _ = mo.sa_module_forward(x1, f1, SA2["npoint"], SA2["radius"], SA2["nsample"], l2, True, False)
-    return f2
-
-
 def run_cpu(steps, warmup, scenes):
-    """Times `steps` passes over `scenes` scenes (one oracle thread per scene + torch intra-op threads)."""
+    """Times `steps` training steps of the hot path over `scenes` scenes on the host CPU.  Returns (scenes/s, ms/step,
+    cores, kind)."""
     import torch
 
-    from eda_b200 import synthetic
-    from oracle import pointnet2_oracle
+    from eda_b200 import hotpath
+    from oracle import pointnet2_oracle, ref_hotpath, ref_model
 
     pointnet2_oracle.build()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sa1, sa2 = build_cpu_modules()
-    sd1, sd2 = sa1.state_dict(), sa2.state_dict()
-    pc = synthetic.point_clouds(scenes, N_POINTS, "surface")
+    torch.manual_seed(0)
+    model = ref_hotpath.build(ref_model.oracle_ext(), dropout=0.0).train()
+    inputs = hotpath.synthetic_inputs(scenes, N_POINTS, L_TEXT, D_BOXES, K_QUERIES, seed=100)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        loss = hotpath.quadratic_loss(model(*inputs))
+        loss.backward()
+        return float(loss.detach())
+
     for _ in range(warmup):
-        cpu_step(pc, sd1, sd2)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(pc, sd1, sd2)
+        step()
     dt = time.perf_counter() - t0
-    return scenes * steps / dt, dt / steps * 1e3, min(cores, max(scenes, 1)), cores
+    return scenes * steps / dt, dt / steps * 1e3, cores
+
+
+def cpu_sample_text(scenes, cores, ms):
+    return (f"{scenes} of the {B_PER_GPU} scenes of one batch per step (reference Python modules unmodified: "
+            f"Pointnet2Backbone, BiEncoder, BiDecoderLayer under torch CPU autograd with {cores} intra-op threads + the C "
+            f"port of the nine `_ext` ops, which the reference only has for CUDA; one thread per scene), "
+            f"{ms:.0f} ms per step; scenes/s = scenes * steps / time")
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU reference arm
-    cores = os.cpu_count() or 1
-    scenes = max(1, min(B_PER_GPU, cores))
-    sps, ms, threads, _ = run_cpu(args.steps, max(args.warmup, 1), scenes)
-    sample = (f"{scenes} of the {B_PER_GPU} scenes of one batch per step (one oracle thread per scene, torch intra-op "
-              f"threads = {cores}); scenes/s = scenes*steps/time")
+    warm = max(min(args.warmup, 2), 1)
+    sps, ms, cores = run_cpu(args.steps, warm, CPU_SAMPLE_SCENES)
     line = {
-        "impl": "reference", "metric": "scenes/sec (SA1+SA2 forward, N=50000)", "value": sps, "unit": "scenes/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "device": "host CPU", "batch_per_step": scenes},
-        "cpu_baseline": {"value": sps, "unit": "scenes/s", "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "scenes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(),
+        "cpu_baseline": {"value": sps, "unit": "scenes/s", "cores": cores, "kind": "port",
+                         "sample": cpu_sample_text(CPU_SAMPLE_SCENES, cores, ms)},
         "e2e": {"value": sps, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,16 +189,43 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def build_train_step(dev, world, rank, dropout, inputs):
+    """Model + flat gradient bucket + the step recorded as one CUDA graph; returns (step callable, state dict)."""
+    import torch
+
+    from eda_b200 import _lib, ddp, hotpath
+    from eda_b200.graphs import GraphedTrainStep
+
+    lib = _lib.load()
+    torch.manual_seed(0)
+    model = hotpath.HotPath(dropout=dropout).to(dev).train()
+    ddp.broadcast_parameters(model)
+    sync_bn = False
+    if world > 1 and hasattr(ddp, "convert_sync_batchnorm"):
+        ddp.convert_sync_batchnorm(model)  # what main_utils.py:335-338 does when more than one GPU is used
+        sync_bn = True
+    fg = ddp.FlatGradients(model)
+    l0 = lib.eda_launch_count()
+    warm = 3
+    gstep = GraphedTrainStep(model, hotpath.quadratic_loss, inputs, fg, warmup=warm)
+    kernels_per_step = (lib.eda_launch_count() - l0) // (warm + 1)  # warm-up steps + the captured one launch the same list
+    overlapped = bool(getattr(gstep, "overlapped_allreduce", False))
+
+    def step():
+        loss = gstep(*inputs)
+        if not overlapped:
+            fg.all_reduce_mean()
+        return loss
+
+    return step, dict(model=model, fg=fg, gstep=gstep, kernels_per_step=int(kernels_per_step), sync_bn=sync_bn,
+                      overlapped=overlapped)
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from eda_b200 import _lib, synthetic
-    from eda_b200.backbone_module import fps_chain
-    from eda_b200.pointnet2 import fused
-
-    PIPELINE_EVERY = 0 if args.no_pipeline else tuple(int(v) for v in os.environ.get("EDA_BENCH_PIPELINE", "512,1024").split(","))
-    from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
+    from eda_b200 import _lib, hotpath
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,241 +240,273 @@ def gpu_arm(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()  # fails loudly when the CUDA library is missing
+    K = args.steps
+    W = max(args.warmup, 3)
 
-    torch.manual_seed(0)
-    sa1 = PointnetSAModuleVotes(use_xyz=True, normalize_xyz=True, **{**SA1, "mlp": list(SA1["mlp"])}).to(dev).eval()
-    sa2 = PointnetSAModuleVotes(use_xyz=True, normalize_xyz=True, **{**SA2, "mlp": list(SA2["mlp"])}).to(dev).eval()
-    assert sa1._fusable(torch.empty(1, 3, 1, device=dev)) is not None
-
-    pc_host = synthetic.point_clouds(B_PER_GPU, N_POINTS, "surface", seed=synthetic.SEED + rank).pin_memory()
-    pc = pc_host.to(dev)
+    host = [t.pin_memory() for t in hotpath.synthetic_inputs(B_PER_GPU, N_POINTS, L_TEXT, D_BOXES, K_QUERIES, seed=100 + rank)]
+    inputs = [t.to(dev) for t in host]
+    step, st = build_train_step(dev, world, rank, 0.0, inputs)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-    fps_ev = []
-
-    side = torch.cuda.Stream(device=dev)
-
-    def step(pc_dev, timed_fps=None):
-        """The hot path through the module API.  FPS depends on xyz only, so the two FPS stages run as one
-        chain on a side stream (eda_b200.backbone_module.fps_chain, what Pointnet2Backbone.forward does) and
-        reach the SA modules through their `inds=` argument: SA2's FPS overlaps SA1's ball query + MLP."""
-        xyz = pc_dev[..., :3].contiguous()
-        feats = pc_dev[..., 3:].transpose(1, 2).contiguous()
-        main = torch.cuda.current_stream(dev)
-        (fps1, ev1), (fps2, ev2) = fps_chain(xyz, [SA1["npoint"], SA2["npoint"]], side, timed_fps,
-                                             pipeline_every=PIPELINE_EVERY)
-        if PIPELINE_EVERY:
-            # each SA stage consumes its sampler's centres in chunks while that FPS is still running (progress
-            # milestones + stream-ordered cuStreamWaitValue32): ball query + fused MLP fill the SMs FPS leaves idle
-            x1, f1, _, _ = fused.sa_forward_pipelined(sa1, xyz, feats, fps1)
-            x2, f2, _, i2 = fused.sa_forward_pipelined(sa2, x1, f1, fps2)
-        else:
-            main.wait_event(ev1)
-            x1, f1, _ = sa1(xyz, feats, fps1)
-            main.wait_event(ev2)
-            x2, f2, i2 = sa2(x1, f1, fps2)
-        return x2, f2, i2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            step(pc)
-        barrier()
-        # ---------------- device-resident timing ----------------
-        sampler = ClockSampler(local)
-        sampler.start()
-        time.sleep(0.25)
-        launches0 = lib.eda_launch_count()
-        evs = []
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            flush.zero_()  # evict L2 between timed iterations (not timed)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            step(pc, (f0, f1e))
-            b.record()
-            evs.append((a, b))
-            fps_ev.append((f0, f1e))
-        barrier()
-        t1 = time.perf_counter()
-        launches = lib.eda_launch_count() - launches0
-        clocks = sampler.stop(t0, t1)
-        step_ms = [a.elapsed_time(b) for a, b in evs]
-        fps_ms = [a.elapsed_time(b) for a, b in fps_ev]
-        total_ms = sum(step_ms)
+    for _ in range(W):
+        step()
+    barrier()
+    # ---------------- value: inputs resident in HBM ----------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    evs = []
+    t0 = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()  # evict L2 between timed iterations (not timed)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = step()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    loss_value = float(loss.item())
 
-        # ---------------- end to end: pinned host -> device -> module API -> host ----------------
-        out_host = torch.empty((B_PER_GPU, SA2["mlp"][-1] if False else 256, SA2["npoint"]), dtype=torch.float32).pin_memory()
-        xyz_host = torch.empty((B_PER_GPU, SA2["npoint"], 3), dtype=torch.float32).pin_memory()
-        ind_host = torch.empty((B_PER_GPU, SA2["npoint"]), dtype=torch.int32).pin_memory()
-        for _ in range(2):
-            x2, f2, i2 = step(pc_host.to(dev, non_blocking=True))
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            pcd = pc_host.to(dev, non_blocking=True)
-            x2, f2, i2 = step(pcd)
-            out_host.copy_(f2, non_blocking=True)
-            xyz_host.copy_(x2, non_blocking=True)
-            ind_host.copy_(i2, non_blocking=True)
-        e1.record()
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
+    # ---------------- e2e: host inputs -> device -> step -> loss back on the host, every step ----------------
+    loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
 
-    h2d = pc_host.numel() * 4
-    d2h = out_host.numel() * 4 + xyz_host.numel() * 4 + ind_host.numel() * 4
+    def e2e_step(i):
+        for dst, src in zip(inputs, host):
+            dst.copy_(src, non_blocking=True)
+        out = step()
+        loss_host[i:i + 1].copy_(out.reshape(1), non_blocking=True)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = 4
+
     times = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = times.tolist()
-    scenes = B_PER_GPU * world * args.steps
-    value = scenes / (total_ms * 1e-3)
-    e2e = scenes / (e2e_ms * 1e-3)
-
-    # roofline of the dominant kernel: SA1 furthest-point sampling (memory-system bound, no contraction).
-    # Algorithmic bytes (SURVEY.md 8d): (m-1) * N * 20 B per scene — every iteration reads each point's xyz
-    # (12 B) and running minimum (4 B) and writes the minimum back (4 B).
-    peak, peak_src = measured_peaks()
-    fps_avg_ms = sum(fps_ms) / len(fps_ms)
-    alg_bytes = (SA1["npoint"] - 1) * N_POINTS * 20 * B_PER_GPU
-    achieved = alg_bytes / (fps_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("fps_cluster_kernel_dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            traffic = None
+    scenes = B_PER_GPU * world * K
     line = {
-        "metric": "scenes/sec (SA1+SA2 forward, N=50000)", "value": value, "unit": "scenes/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "n_points": N_POINTS,
-                   "l2": "512 MB memset between timed steps (inputs 9.6 MB < L2)", "sharding": "batch only, no collective",
-                   "overlap": ("SA1's ball query + fused MLP run on finished chunks of %d centres while its FPS continues on a "
-                               "side stream; SA2's FPS (of an FPS-ordered set) is the verified identity shortcut"
-                               % PIPELINE_EVERY[0]) if PIPELINE_EVERY else "SA2 FPS on a side stream",
-                   "index_paths": "fp32, bit-exact", "mlp": "tcgen05 kind::tf32, fp32 accumulate"},
-        "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
+        "metric": METRIC, "value": scenes / (total_ms * 1e-3), "unit": "scenes/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32", "data": "synthetic", "config": config(),
+        "e2e": {"value": scenes / (e2e_ms * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+        "gpu_launches": st["kernels_per_step"] * K,
         "clocks": clocks,
-        "roofline": {"kernel": "fps_cluster_kernel<13,8,256> (SA1 FPS 50000->2048, B=8)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel_ms": fps_avg_ms, "share_of_step": fps_avg_ms / (total_ms / args.steps),
-                     "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "points and running minima stay in registers: algorithmic GB/s can exceed the HBM peak"},
+        "execution": {"step": "one CUDA graph per step (forward, backward, weight packing%s)" %
+                              (", bucketed gradient all-reduce overlapped with backward" if st["overlapped"] else
+                               "); NCCL all-reduce of the flat fp32 gradient bucket after it"),
+                      "kernels_per_step": st["kernels_per_step"], "gradient_floats": int(st["fg"].flat.numel()),
+                      "sync_batchnorm": st["sync_bn"], "loss": loss_value,
+                      "index_paths": "fp32, bit-exact", "contractions": "tcgen05 kind::tf32, fp32 accumulate"},
     }
-    # The literal BASELINE.json metric (fwd+bwd, 256 queries, L=80) on the whole hot path, same run, as an extra object
-    if not args.no_train:
-        try:
-            line["fwd_bwd"] = train_leg(args, dev, world, rank)
-        except Exception as e:  # noqa: BLE001  (never lose the main line to the extra leg)
-            line["fwd_bwd"] = {"error": repr(e)[:300]}
+    if True:
+        extras = {}
+        if not args.no_extras:
+            try:
+                extras = extra_legs(args, dev, world, rank, inputs, host, total_ms / K)
+            except Exception as e:  # noqa: BLE001  (never lose the main line to an extra leg)
+                extras = {"extras_error": repr(e)[:400]}
+        line.update(extras)
+    if "roofline" not in line:
+        line["roofline"] = {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
+                            "traffic": None, "note": "extras skipped"}
     if rank == 0:
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            scenes_cpu = max(1, min(B_PER_GPU, cores))
-            sps, ms, _, _ = run_cpu(3, 1, scenes_cpu)
-            line["cpu_baseline"] = {"value": sps, "unit": "scenes/s", "cores": cores, "kind": "port",
-                                    "sample": f"3 passes over {scenes_cpu} scenes of the same batch (oracle C ops, one "
-                                              f"thread per scene + torch CPU MLP with {cores} threads), {ms:.0f} ms/pass"}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                sps, ms, cores = run_cpu(2, 1, CPU_SAMPLE_SCENES)
+                line["cpu_baseline"] = {"value": sps, "unit": "scenes/s", "cores": cores, "kind": "port",
+                                        "sample": "2 timed steps; " + cpu_sample_text(CPU_SAMPLE_SCENES, cores, ms)}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "failed: " + repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def train_leg(args, dev, world, rank):
-    """Training step of the hot path at BASELINE.json configs[3] shapes (B=8 scenes/GPU, N=50 000, L=80, D=132, K=256):
-    Pointnet2Backbone -> 3 BiEncoderLayer -> 6 BiDecoderLayer forward (train-mode BatchNorm, dropout 0 — the parity
-    configuration), synthetic quadratic loss, backward through the CUDA backward kernels, ONE flat fp32 gradient
-    all-reduce over NCCL.  The step is recorded once as a CUDA graph (eda_b200.graphs.GraphedTrainStep) and replayed;
-    the point cloud is copied from pinned host memory inside the timed region.  Max over ranks."""
+def extra_legs(args, dev, world, rank, inputs, host, step_ms):
+    """Everything besides the headline: kernel rooflines, the reference CUDA build on this box, eval forward, SA
+    forward, dropout 0.1, the configs[4] sweep.  Multi-GPU runs only keep the collective-bearing legs."""
     import torch
     import torch.distributed as dist
 
-    from eda_b200 import _lib, ddp, hotpath
-    from eda_b200.graphs import GraphedTrainStep
+    from benchmarks import kernels as kn
+    from eda_b200 import hotpath
+    from eda_b200.graphs import GraphedCallable
 
-    torch.manual_seed(0)
-    model = hotpath.HotPath(dropout=0.0).to(dev).train()
-    ddp.broadcast_parameters(model)
-    fg = ddp.FlatGradients(model)
-    host = hotpath.synthetic_inputs(B_PER_GPU, N_POINTS, seed=100 + rank)
-    pc_host = host[0].pin_memory()
-    inputs = [t.to(dev) for t in host]
-    gstep = GraphedTrainStep(model, hotpath.quadratic_loss, inputs, fg)
+    out = {}
+    hbm, tf32, tf32_sus, sm_mhz, src = kn.peaks()
+    traffic = kn.traffic_table()
 
-    def step():
-        inputs[0].copy_(pc_host, non_blocking=True)
-        loss = gstep(*inputs)
-        fg.all_reduce_mean()
-        return loss
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    lib = _lib.load()
-    l0 = lib.eda_launch_count()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        loss = step()
-    b.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = ms.item()
-    loss_value = float(loss.item())
-    launches_delta = lib.eda_launch_count() - l0
-    # the same step in the reference's default configuration, dropout 0.1 (masks from the in-kernel hash; the graph's
-    # device epoch word gives every replay fresh masks)
-    drop_ms = None
-    try:
-        del gstep, fg, model
-        torch.manual_seed(0)
-        model = hotpath.HotPath(dropout=0.1).to(dev).train()
-        ddp.broadcast_parameters(model)
-        fg = ddp.FlatGradients(model)
-        gstep = GraphedTrainStep(model, hotpath.quadratic_loss, inputs, fg)
-        for _ in range(3):
-            step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            step()
-        b.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    def maxed(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        drop_ms = t.item() / args.steps
+        return t.item()
+
+    # ---- the step with the reference's default dropout 0.1 (masks from the in-kernel hash) ----
+    try:
+        step_d, st_d = build_train_step(dev, world, rank, 0.1, inputs)
+        ms = maxed(kn.time_ms(step_d, 3, max(5, args.steps // 2)))
+        out["dropout_0.1"] = {"ms_per_step": ms, "value": B_PER_GPU * world / (ms * 1e-3), "unit": "scenes/s"}
+        del step_d, st_d
     except Exception as e:  # noqa: BLE001
-        drop_ms = repr(e)[:200]
-    return {"metric": "scenes/sec fwd+bwd (hot path: backbone + 3 BiEncoder + 6 BiDecoder layers)",
-            "value": B_PER_GPU * world * args.steps / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms / args.steps,
-            "workload": "configs[3] shapes: B=8/GPU N=50000 L=80 D=132 K=256, train-mode BN, dropout 0, synthetic "
-                        "quadratic loss, flat fp32 gradient all-reduce (%d floats)" % fg.flat.numel(),
-            "execution": "one CUDA graph per step (forward, backward, weight packing) + NCCL all-reduce outside it",
-            "h2d_bytes_per_step": pc_host.numel() * 4, "loss": loss_value,
-            "ms_per_step_dropout_0.1": drop_ms,
-            "kernels_per_step_in_graph": "replayed, not relaunched: eda_launch_count delta = %d" % launches_delta}
+        out["dropout_0.1"] = {"error": repr(e)[:200]}
+    if world > 1 and rank != 0:
+        return out
+
+    # ---- roofline of the dominant kernel family: the tcgen05 linear GEMM (q/k/v/out projections, FFNs, activation
+    # gradients: ~220 launches per step), heaviest shape = the 8192-row visual stream, 288 x 288 weights ----
+    lin = kn.linear_point(B_PER_GPU * 1024, 288, 288, dev)
+    out["roofline"] = {
+        "kernel": "linear_kernel (eda_linear_forward) R=8192 K=288 N=288, bias epilogue; timed alone, 30 launches",
+        "bound": "tensor", "achieved": lin["TFLOPs"], "peak": tf32, "unit": "TFLOP/s", "frac": lin["TFLOPs"] / tf32,
+        "traffic": traffic.get("linear_kernel_8192x288x288_dram_bytes_per_launch"), "peak_source": src + " burst",
+        "kernel_ms": lin["ms"], "algorithmic_flops_per_launch": lin["flops"], "min_bytes_per_launch": lin["min_bytes"],
+        "hbm_frac_at_min_bytes": lin["min_bytes"] / (lin["ms"] * 1e-3) / 1e9 / hbm,
+        "share_of_step": traffic.get("linear_kernel_share_of_step"),
+    }
+    if world > 1:
+        return out  # the remaining legs are single-GPU measurements (BENCH), not part of the scaling run
+    rl = {}
+    fps = kn.fps_point(B_PER_GPU, N_POINTS, 2048, dev, sm_mhz)
+    fps.update({"bound": "latency (serial arg-max chain); HBM by SURVEY 8d convention", "hbm_peak_GBps": hbm,
+                "frac_of_hbm_peak_algorithmic": fps["algorithmic_GBps"] / hbm,
+                "dram_bytes_per_launch_ncu": traffic.get("fps_cluster_kernel_dram_bytes_per_launch"),
+                "note": "points and running minima are register-resident: DRAM traffic is the compulsory read only, so "
+                        "algorithmic GB/s says nothing about efficiency; the honest bound is cycles_per_iteration vs "
+                        "exchange_floor_cycles_per_iteration (measured here by eda_selftest_fps_exchange)"})
+    rl["fps_sa1"] = fps
+    bq = kn.ball_query_point(B_PER_GPU, N_POINTS, 2048, 0.2, 64, dev)
+    bq.update({"hbm_peak_GBps": hbm, "frac_of_hbm_peak_algorithmic": bq["algorithmic_GBps"] / hbm,
+               "dram_bytes_per_launch_ncu": traffic.get("ball_query_kernel_dram_bytes_per_launch")})
+    rl["ball_query_sa1"] = bq
+    for name, Nq, Nk in (("attention_vis_self", 1024, 1024), ("attention_cross_v", 256, 1024)):
+        a = kn.attention_point(B_PER_GPU, Nq, Nk, dev)
+        a.update({"tf32_peak_TFLOPs": tf32, "frac_of_tf32_peak": a["TFLOPs"] / tf32})
+        rl[name] = a
+    sa = kn.sa_mlp_point(B_PER_GPU, N_POINTS, 2048, 64, 3, [64, 64, 128], 0.2, dev)
+    sa.update({"tf32_peak_TFLOPs": tf32, "frac_of_tf32_peak": sa["TFLOPs"] / tf32})
+    rl["sa_mlp_sa1"] = sa
+    out["rooflines"] = rl
+
+    # ---- eval forward of the hot path (configs[2] shapes), ours graphed ----
+    from eda_b200 import hotpath as hp
+
+    torch.manual_seed(0)
+    model = hp.HotPath(dropout=0.0).to(dev).eval()
+    g = GraphedCallable(lambda *a: model(*a)[0], inputs)
+    ms = kn.time_ms(lambda: g(*inputs), 3, 20)
+    out["eval_forward"] = {"ms": ms, "value": B_PER_GPU / (ms * 1e-3), "unit": "scenes/s",
+                           "workload": "configs[2] shapes: hot-path forward, eval-mode BN, one CUDA graph"}
+
+    # ---- the reference CUDA build on this box (R-GPU, BASELINE.md section 2): its compiled `_ext` + its own Python
+    # modules, same parameters, same inputs; TEST/BASELINE infrastructure, never on the product path ----
+    try:
+        out["ref_cuda"] = ref_cuda_leg(dev, model, inputs, out["eval_forward"]["ms"], step_ms)
+    except Exception as e:  # noqa: BLE001
+        out["ref_cuda"] = {"unavailable": repr(e)[:300]}
+    del model, g
+
+    # ---- configs[1]: SA1 + SA2 forward through the module API (last round's headline) ----
+    try:
+        out["sa_forward"] = sa_forward_leg(dev, host[0])
+    except Exception as e:  # noqa: BLE001
+        out["sa_forward"] = {"error": repr(e)[:200]}
+    # ---- configs[4] sweep ----
+    try:
+        out["sweep"] = kn.sweep(dev, B_PER_GPU, quick=args.quick_sweep)
+    except Exception as e:  # noqa: BLE001
+        out["sweep"] = {"error": repr(e)[:200]}
+    return out
+
+
+def ref_cuda_leg(dev, ours_eval, inputs, ours_fwd_ms, ours_step_ms):
+    import torch
+
+    from benchmarks import kernels as kn
+    from eda_b200 import hotpath
+    from oracle import ref_hotpath, ref_loader
+
+    ext = ref_loader.load_reference_ext()
+    if ext is None:
+        return {"unavailable": "oracle/_ref/pointnet2/_ext*.so did not travel"}
+    ref = ref_hotpath.build(ext, dropout=0.0).to(dev)
+    ref.load_state_dict(ours_eval.state_dict(), strict=True)
+    res = {"what": "unmodified reference Python modules + the reference's own `_ext` compiled for sm_100a (oracle/_ref), "
+                   "eager PyTorch 2.11, same parameters and inputs"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for label, tf32 in (("fp32", False), ("tf32_allowed", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ref.eval()
+            with torch.no_grad():
+                fwd = kn.time_ms(lambda: ref(*inputs), 2, 5)
+            ref.train()
+
+            def train_step():
+                for p in ref.parameters():
+                    p.grad = None
+                hotpath.quadratic_loss(ref(*inputs)).backward()
+
+            trn = kn.time_ms(train_step, 2, 5)
+            res[label] = {"forward_ms": fwd, "forward_scenes_per_s": B_PER_GPU / (fwd * 1e-3), "fwd_bwd_ms": trn,
+                          "fwd_bwd_scenes_per_s": B_PER_GPU / (trn * 1e-3),
+                          "speedup_forward": fwd / ours_fwd_ms, "speedup_fwd_bwd": trn / ours_step_ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return res
+
+
+def sa_forward_leg(dev, pc_host):
+    """configs[1]: SA1 -> SA2 forward, eval-mode BN, FPS chain on a side stream, chunk-pipelined."""
+    import torch
+
+    from benchmarks import kernels as kn
+    from eda_b200.backbone_module import fps_chain
+    from eda_b200.pointnet2 import fused
+    from eda_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
+
+    torch.manual_seed(0)
+    sa1 = PointnetSAModuleVotes(use_xyz=True, normalize_xyz=True, npoint=2048, radius=0.2, nsample=64,
+                                mlp=[3, 64, 64, 128]).to(dev).eval()
+    sa2 = PointnetSAModuleVotes(use_xyz=True, normalize_xyz=True, npoint=1024, radius=0.4, nsample=32,
+                                mlp=[128, 128, 128, 256]).to(dev).eval()
+    pc = pc_host.to(dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def step():
+        xyz = pc[..., :3].contiguous()
+        feats = pc[..., 3:].transpose(1, 2).contiguous()
+        (fps1, _), (fps2, _) = fps_chain(xyz, [2048, 1024], side, pipeline_every=(512, 1024))
+        x1, f1, _, _ = fused.sa_forward_pipelined(sa1, xyz, feats, fps1)
+        return fused.sa_forward_pipelined(sa2, x1, f1, fps2)
+
+    with torch.no_grad():
+        ms = kn.time_ms(step, 3, 20)
+    return {"ms": ms, "value": B_PER_GPU / (ms * 1e-3), "unit": "scenes/s",
+            "workload": "configs[1]: SA1(2048,r.2,ns64,[6,64,64,128]) -> SA2(1024,r.4,ns32,[131,128,128,256]) forward, "
+                        "B=8, N=50000, eval-mode BN, device-resident"}
 
 
 def main():

@@ -24,6 +24,8 @@ PROTOTYPES = {
     "eda_furthest_point_sampling": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "eda_furthest_point_sampling_progress": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     "eda_stream_wait_value32": (_c_int, [_vp, _vp, _c_int]),
+    "eda_selftest_fps_exchange": (_c_int, [_c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_fps_plan": (_c_int, [_c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "eda_ball_query_range": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp]),
     "eda_sa_mlp_forward_range": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
                                           _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int,
@@ -43,6 +45,7 @@ PROTOTYPES = {
     "eda_bn_finalize": (_c_int, [_vp, ctypes.c_double, _vp, _vp, _c_float, _c_float, _vp, _vp, _c_int, _c_int, _vp,
                                  _vp, _vp, _vp, _vp]),
     "eda_transpose_last2": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_transpose_strided": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_linear_packed_floats": (_sz, [_c_int, _c_int]),
     "eda_linear_pack": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp]),
     "eda_linear_pack_batch": (_c_int, [_vp, _c_int, _c_int, _vp]),
@@ -64,6 +67,10 @@ PROTOTYPES = {
                                            _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, ctypes.c_uint,
                                            _vp, _vp, _vp, _vp, _vp]),
     "eda_wgrad": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp]),
+    "eda_wgrad_small": (_c_int, [_vp, _c_int, _vp, _c_int, ctypes.c_longlong, _c_int, _c_int, _vp, _c_int, _vp, _vp]),
+    "eda_fp_gather_rows": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp,
+                                    _vp]),
+    "eda_fp_scatter_rows": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_layernorm_backward": (_c_int, [_vp, _vp, _vp, _c_float, ctypes.c_longlong, _c_int, _vp, _vp, _vp, _vp, _c_float,
                                         ctypes.c_uint, _vp]),
     "eda_relu_backward": (_c_int, [_vp, _vp, _c_float, ctypes.c_longlong, _vp, _vp]),
@@ -91,7 +98,8 @@ PROTOTYPES = {
 class LinearProblem(ctypes.Structure):
     """struct eda_linear_problem (include/eda_b200.h)."""
     _fields_ = [("x", _vp), ("pos", _vp), ("w_packed", _vp), ("bias", _vp), ("residual", _vp), ("y", _vp),
-                ("rows", _c_int), ("y_batch_rows", _c_int), ("y_ld", _c_int), ("round_tf32", _c_int), ("pre_ln", _vp)]
+                ("rows", _c_int), ("y_batch_rows", _c_int), ("y_ld", _c_int), ("round_tf32", _c_int), ("pre_ln", _vp),
+                ("y_row_stride", _c_int), ("reserved", _c_int)]
 
 
 class WgradProblem(ctypes.Structure):

@@ -192,7 +192,13 @@ def linear_raw(problems, K, N, relu=False, ln=None, dropout=None):
         _require_cuda(x)
         assert x.dtype == torch.float32 and x.is_contiguous() and x.size(-1) == K
         R = x.numel() // K
-        y = torch.empty((R, N), dtype=torch.float32, device=dev)
+        into = pr.get("y_into")  # optional (R, N) column-block view of a wider row-major matrix: written in place
+        if into is not None:
+            assert into.shape == (R, N) and into.stride(1) == 1 and into.stride(0) % 4 == 0 and into.dtype == torch.float32
+            y = into
+            arr[i].y_row_stride = into.stride(0)
+        else:
+            y = torch.empty((R, N), dtype=torch.float32, device=dev)
         pos, res, bias = pr.get("pos"), pr.get("residual"), pr.get("bias")
         if pos is not None:
             assert pos.is_contiguous() and pos.numel() == x.numel()
@@ -338,6 +344,31 @@ def mark_side_pending(dev):
             _join_queued = True
         except RuntimeError:  # not inside a backward pass
             pass
+
+
+def _bucket_of(p):
+    ref = getattr(p, "_eda_fused_grad_owner", None) if p is not None else None
+    owner = ref() if ref is not None else None
+    return owner if (owner is not None and owner.regions is not None) else None
+
+
+def grads_expected(params):
+    """Forward-side half of the completion tracking below: one more fused backward will write into these parameters'
+    gradient buffers (a module evaluated twice in one forward writes twice)."""
+    for p in params:
+        owner = _bucket_of(p)
+        if owner is not None:
+            owner.expect(p)
+
+
+def grads_written(params):
+    """Tells the owning FlatGradients bucket that a fused backward has queued its contribution to the gradients of
+    `params` (fused accumulation bypasses autograd's AccumulateGrad, so its hooks never fire for them): drives the
+    overlapped, bucketed all-reduce.  A parameter counts as complete once every expected contribution is in."""
+    for p in params:
+        owner = _bucket_of(p)
+        if owner is not None:
+            owner.written(p)
 
 
 def fused_grad_enabled(p):
@@ -574,6 +605,8 @@ class _MHABlockFn(torch.autograd.Function):
         ctx.key = key
         ctx.cuda_bw = train
         ctx.gbufs = _grad_buffers((in_w, in_b, out_w, out_b, ln_w, ln_b)) if train else None
+        if train:
+            grads_expected((in_w, in_b, out_w, out_b, ln_w, ln_b))
         return y.view(B, Nq, E)
 
     @staticmethod
@@ -670,6 +703,8 @@ class _MHABlockFn(torch.autograd.Function):
             if k_pos is not None:
                 probs.append(dict(dy=dk, x=k_pos.contiguous(), dw=d_in_w[E:2 * E]))
             wgrad(probs, E, E)
+        if fused:
+            grads_written((in_w, in_b, out_w, out_b, ln_w, ln_b))
         dq_in = dq_in.view(B, Nq, E)
         dk_in = dk_in.view(B, Nk, E)
         dv_in = dv_in.view(B, Nk, E)
@@ -714,6 +749,8 @@ class _FFNBlockFn(torch.autograd.Function):
         ctx.key = key
         ctx.cuda_bw = train
         ctx.gbufs = _grad_buffers((w1, b1, w2, b2, ln_w, ln_b)) if train else None
+        if train:
+            grads_expected((w1, b1, w2, b2, ln_w, ln_b))
         return y.view(shape)
 
     @staticmethod
@@ -746,6 +783,7 @@ class _FFNBlockFn(torch.autograd.Function):
         (dx,) = linear_raw([dict(x=dz, w_packed=pack_weight_t(w1, cache_key=(key, "w1t")))], Fh, E)
         dx += du
         if fused:
+            grads_written((w1, b1, w2, b2, ln_w, ln_b))
             return (None, None, dx.view(x.shape), None, None, None, None, None, None, None)
         return (None, None, dx.view(x.shape), dw1, db1, dw2, db2, d_ln_w, d_ln_b, None)
 
@@ -798,13 +836,18 @@ class _LinearFn(torch.autograd.Function):
         if ctx.has_scale:
             raise RuntimeError("eda_b200.linear: the scale-folded variant is inference-only")
         x, w, y = ctx.saved_tensors
-        K = w.size(1)
-        g = grad.reshape(-1, w.size(0))
+        N, K = w.shape
+        g = grad.contiguous().view(-1, N)
         if ctx.relu:
-            g = g * (y > 0)
-        gx = (g @ w).view(x.shape) if ctx.needs_input_grad[2] else None
-        gw = g.t() @ x.reshape(-1, K) if ctx.needs_input_grad[3] else None
-        gb = g.sum(0) if ctx.needs_input_grad[4] else None
+            g = relu_backward(g, y.view(-1, N), 1.0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[2]:  # dX = dY W on the forward tcgen05 GEMM with the transposed packed weight
+            (gx,) = linear_raw([dict(x=g, w_packed=pack_weight_t(w))], N, K)
+            gx = gx.view(x.shape)
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            gw = torch.zeros((N, K), dtype=torch.float32, device=g.device)
+            gb = torch.zeros(N, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[4] else None
+            wgrad([dict(dy=g, x=x.contiguous().view(-1, K), dw=gw, db=gb)], N, K)
         return None, None, gx, gw, gb, None
 
 

@@ -283,6 +283,88 @@ fps_cluster_kernel(const float *__restrict__ xyz_all, int N, int m, Layout lay, 
   if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still address its smem
 }
 
+// Latency floor of the sampler's reduction / exchange chain (measurement aid behind eda_selftest_fps_exchange): the
+// loop of fps_cluster_kernel with the distance sweep and the per-thread tournament removed — per iteration one warp
+// arg-max (2 x redux.sync), the shared-memory stage + bar.sync, the CTA arg-max, the one-sided DSMEM exchange of the
+// CL winners (st.async + mbarrier complete_tx), the wake-up and the cluster arg-max.  Each iteration's keys depend
+// on the previous winner, so iterations serialise exactly as in the sampler.  cycles / iteration of THIS kernel is
+// what no amount of bandwidth or issue slots can remove from the sampler at this decomposition.
+template <int CL, int T>
+__global__ void __launch_bounds__(T, 1) fps_exchange_floor_kernel(int iters, unsigned *__restrict__ sink) {
+  constexpr int kWarps = T / 32;
+  __shared__ WarpCand s_warp[2][kWarps];
+  __shared__ Cand s_cta[2][CL];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const unsigned rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (CL > 1) {
+    if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      mbar_fence_init_cluster();
+    }
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
+  unsigned prev = 0x9E3779B9u * (blockIdx.x / CL + 1);
+  for (int it = 1; it < iters; ++it) {
+    const int buf = it & 1;
+    if (CL > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], CL * 20);
+    // a key that depends on the previous winner (one multiply-xor: the dependency, not the work)
+    const unsigned h = (prev ^ (rank * T + tid + 1)) * 0x85EBCA77u;
+    const int hi = (int)(h >> 2);
+    const unsigned lo = ~(rank * T + tid);
+    const Key wk = warp_argmax(hi, lo);
+    if (hi == wk.hi && lo == wk.lo) {
+      WarpCand c;
+      c.hi = hi; c.lo = lo; c.slot = tid; c.pad = 0;
+      s_warp[buf][warp] = c;
+    }
+    __syncthreads();
+    int hi2 = -0x7fffffff;
+    unsigned lo2 = 0;
+    if (lane < kWarps) { hi2 = s_warp[buf][lane].hi; lo2 = s_warp[buf][lane].lo; }
+    const Key ck = warp_argmax(hi2, lo2);
+    Key fk = ck;
+    if (CL > 1) {
+      if (warp == 0 && lane < CL) {
+        const uint32_t dst = mapa_u32(smem_u32(&s_cta[buf][rank]), lane);
+        const uint32_t rbar = mapa_u32(smem_u32(&s_bar[buf]), lane);
+        st_async_v4(dst, (uint32_t)ck.hi, ck.lo, 0u, 0u, rbar);
+        st_async_b32(dst + 16, 0u, rbar);
+      }
+      mbar_wait_cluster(&s_bar[buf], ((it - 1) >> 1) & 1);
+      int hi3 = -0x7fffffff;
+      unsigned lo3 = 0;
+      if (lane < CL) { hi3 = s_cta[buf][lane].hi; lo3 = s_cta[buf][lane].lo; }
+      fk = warp_argmax(hi3, lo3);
+    }
+    prev = (unsigned)fk.hi ^ fk.lo;
+  }
+  if (tid == 0 && rank == 0) sink[blockIdx.x / CL] = prev;
+  if (CL > 1) cluster_sync_all();
+}
+
+template <int CL, int T>
+int launch_exchange_floor(int B, int iters, unsigned *sink, cudaStream_t st) {
+  auto kern = fps_exchange_floor_kernel<CL, T>;
+  if (CL > 8) EDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "floor cluster attr");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CL));
+  cfg.blockDim = dim3(T);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, iters, sink), "fps_exchange_floor_kernel launch");
+  return check_launch("fps_exchange_floor_kernel");
+}
+
 // Generic fallback: any N, running minima in global scratch (the reference's layout), one
 // 1024-thread CTA per scene, same ordering rule.  Used only when the register variant does
 // not cover the shape or a cluster launch is not possible.
@@ -575,6 +657,16 @@ size_t eda_fps_scratch_bytes(int B, int N, int m) {
   return pl.cl == 0 ? (size_t)B * N * sizeof(float) : 0;
 }
 
+int eda_fps_plan(int B, int N, int m, int *cluster, int *threads, int *points_per_thread) {
+  (void)m;
+  if (B <= 0 || N <= 0) return EDA_ERR_INVALID_ARGUMENT;
+  const eda::FpsPlan pl = eda::plan_fps(B, N, eda::ref_log2_block(N));
+  if (cluster) *cluster = pl.cl;            // 0: the global-scratch fallback kernel
+  if (threads) *threads = pl.cl ? pl.t : eda::kGThreads;
+  if (points_per_thread) *points_per_thread = pl.cl ? 2 * pl.p2 : 0;
+  return EDA_OK;
+}
+
 static int fps_impl(const float *xyz, int B, int N, int m, void *scratch, int *idxs, int *progress, int every,
                     const int *not_identity,
                     void *stream) {
@@ -629,6 +721,28 @@ int eda_fps_identity_check(const float *xyz, int B, int n, int m, float *dsel, i
   fps_identity_pass1_kernel<<<g1, kIdThreads, smem1, st>>>(xyz, n, m, dsel, not_identity);
   fps_identity_pass2_kernel<<<g2, kIdThreads, smem2, st>>>(xyz, n, m, dsel, not_identity);
   return check_launch("fps_identity_kernels", 2);
+}
+
+int eda_selftest_fps_exchange(int B, int cluster, int threads, int iters, unsigned int *sink, void *stream) {
+  using namespace eda;
+  if (B <= 0 || iters < 2 || !sink) return EDA_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = as_stream(stream);
+  if (threads == 256) {
+    switch (cluster) {
+      case 1: return launch_exchange_floor<1, 256>(B, iters, sink, st);
+      case 2: return launch_exchange_floor<2, 256>(B, iters, sink, st);
+      case 4: return launch_exchange_floor<4, 256>(B, iters, sink, st);
+      case 8: return launch_exchange_floor<8, 256>(B, iters, sink, st);
+      case 16: return launch_exchange_floor<16, 256>(B, iters, sink, st);
+    }
+  } else if (threads == 512) {
+    switch (cluster) {
+      case 4: return launch_exchange_floor<4, 512>(B, iters, sink, st);
+      case 8: return launch_exchange_floor<8, 512>(B, iters, sink, st);
+      case 16: return launch_exchange_floor<16, 512>(B, iters, sink, st);
+    }
+  }
+  return EDA_ERR_UNSUPPORTED;
 }
 
 int eda_furthest_point_sampling_progress(const float *xyz, int B, int N, int m, void *scratch, int *idxs,

@@ -300,6 +300,32 @@ __global__ void relu_backward_kernel(const float4 *__restrict__ dy, const float4
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient for tiny K (the 3- or 6-channel input of PositionEmbeddingLearned's first 1x1 conv,
+// encoder_decoder_layers.py:24-28): dW[N x K] += dY^T X, db[N] += column sums of dY, K <= 8, plain fp32 FMAs.
+// Block = 32 output rows n x 8 k lanes over one 256-row chunk: dY reads are coalesced over n, X reads broadcast.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWsRows = 256;
+__global__ void __launch_bounds__(256)
+wgrad_small_kernel(const float *__restrict__ dy, int ldy, const float *__restrict__ x, int ldx, long long rows, int N,
+                   int K, float *__restrict__ dw, int ldw, float *__restrict__ db) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int k = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * kWsRows;
+  const long long r1 = (r0 + kWsRows < rows) ? r0 + kWsRows : rows;
+  if (n >= N) return;
+  float acc = 0.f, sum = 0.f;
+  const bool kk = k < K;
+  for (long long r = r0; r < r1; ++r) {
+    const float g = __ldg(dy + r * ldy + n);
+    if (kk) acc = fmaf(g, __ldg(x + r * ldx + k), acc);
+    sum += g;
+  }
+  if (kk) atomicAdd(dw + (long long)n * ldw + k, acc);
+  if (k == 0 && db) atomicAdd(db + n, sum);
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -374,6 +400,21 @@ int eda_relu_backward(const float *dy, const float *y, float scale, long long n,
   relu_backward_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4 *>(dy), reinterpret_cast<const float4 *>(y), scale, n4, reinterpret_cast<float4 *>(out));
   return check_launch("relu_backward_kernel");
+}
+
+
+int eda_wgrad_small(const float *dy, int ldy, const float *x, int ldx, long long rows, int N, int K, float *dw, int ldw,
+                    float *db, void *stream) {
+  using namespace eda;
+  if (rows < 0 || N < 1 || K < 1 || ldy < N || ldx < K || ldw < K) return EDA_ERR_INVALID_ARGUMENT;
+  if (K > 8) return EDA_ERR_UNSUPPORTED;
+  if (rows == 0) return EDA_OK;
+  if (!dy || !x || !dw) return EDA_ERR_INVALID_ARGUMENT;
+  const long long chunks = (rows + kWsRows - 1) / kWsRows;
+  if (chunks > 65535) return EDA_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)chunks);
+  wgrad_small_kernel<<<grid, 256, 0, as_stream(stream)>>>(dy, ldy, x, ldx, rows, N, K, dw, ldw, db);
+  return check_launch("wgrad_small_kernel");
 }
 
 }  // extern "C"

@@ -121,6 +121,95 @@ three_interpolate_grad_kernel(const float *__restrict__ grad_out, const int *__r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Feature propagation, row-major (PointnetFPModule.forward, pointnet2_modules.py:393-410, as ONE pass):
+//   weight_k = (1 / (sqrt(dist2_k) + 1e-8)) / sum_k(...)          pointnet2_utils.py:142, pointnet2_modules.py:395-397
+//   x0[row]  = [ w1 K[i1] + w2 K[i2] + w3 K[i3]  (C2 interpolated channels)  |  skip[row]  (C1 channels) ]
+// i.e. three_interpolate + torch.cat([interpolated, unknow_feats], 1), written straight in the (rows, C2 + C1) layout
+// the MLP's GEMM consumes.  known / skip features are POINT-major (one contiguous row per point).  Warp = one row,
+// lanes stride over channels; the interpolation keeps the reference's FMUL(p2,w2); FFMA(p1,w1,.); FFMA(p3,w3,.) order.
+constexpr int kFpWarps = 8;
+
+__device__ __forceinline__ void fp_weights(const float *__restrict__ d2, float &w1, float &w2, float &w3) {
+  // torch: dist = sqrt(dist2); r = 1.0 / (dist + 1e-8); w = r / sum(r)   — IEEE sqrt / divide, fp32 throughout
+  const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 0)), 1e-8f));
+  const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 1)), 1e-8f));
+  const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 2)), 1e-8f));
+  const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+  w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm); w3 = __fdiv_rn(r3, norm);
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kFpWarps * 32)
+fp_gather_rows_kernel(const float *__restrict__ known, int ldk, const float *__restrict__ skip, int lds,
+                      const int *__restrict__ idx, const float *__restrict__ dist2, long long rows, int n, int m,
+                      int C2, int C1, float *__restrict__ x0, float *__restrict__ weight) {
+  const long long row = (long long)blockIdx.x * kFpWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long b = row / n;
+  const int *I = idx + row * 3;
+  float w1, w2, w3;
+  fp_weights(dist2 + row * 3, w1, w2, w3);
+  if (lane == 0 && weight) {
+    weight[row * 3 + 0] = w1; weight[row * 3 + 1] = w2; weight[row * 3 + 2] = w3;
+  }
+  const float *__restrict__ k1 = known + (b * m + __ldg(I + 0)) * ldk;
+  const float *__restrict__ k2 = known + (b * m + __ldg(I + 1)) * ldk;
+  const float *__restrict__ k3 = known + (b * m + __ldg(I + 2)) * ldk;
+  float *__restrict__ out = x0 + row * (long long)(C2 + C1);
+  if (kVec) {
+    for (int c = lane * 4; c < C2; c += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(k1 + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4 *>(k2 + c));
+      const float4 cc = __ldg(reinterpret_cast<const float4 *>(k3 + c));
+      float4 o;
+      o.x = __fmaf_rn(cc.x, w3, __fmaf_rn(a.x, w1, __fmul_rn(bb.x, w2)));
+      o.y = __fmaf_rn(cc.y, w3, __fmaf_rn(a.y, w1, __fmul_rn(bb.y, w2)));
+      o.z = __fmaf_rn(cc.z, w3, __fmaf_rn(a.z, w1, __fmul_rn(bb.z, w2)));
+      o.w = __fmaf_rn(cc.w, w3, __fmaf_rn(a.w, w1, __fmul_rn(bb.w, w2)));
+      *reinterpret_cast<float4 *>(out + c) = o;
+    }
+    if (skip) {
+      const float *__restrict__ sr = skip + row * (long long)lds;
+      for (int c = lane * 4; c < C1; c += 128)
+        *reinterpret_cast<float4 *>(out + C2 + c) = __ldg(reinterpret_cast<const float4 *>(sr + c));
+    }
+  } else {
+    for (int c = lane; c < C2; c += 32)
+      out[c] = __fmaf_rn(__ldg(k3 + c), w3, __fmaf_rn(__ldg(k1 + c), w1, __fmul_rn(__ldg(k2 + c), w2)));
+    if (skip) {
+      const float *__restrict__ sr = skip + row * (long long)lds;
+      for (int c = lane; c < C1; c += 32) out[C2 + c] = __ldg(sr + c);
+    }
+  }
+}
+
+// backward of the interpolated half: dknown[b, i_k, c] += w_k * dx[row, c]  (three_interpolate_grad, point-major)
+__global__ void __launch_bounds__(kFpWarps * 32)
+fp_scatter_rows_kernel(const float *__restrict__ dx, int ldx, const int *__restrict__ idx,
+                       const float *__restrict__ weight, long long rows, int n, int m, int C2,
+                       float *__restrict__ dknown) {
+  const long long row = (long long)blockIdx.x * kFpWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long b = row / n;
+  const int *I = idx + row * 3;
+  const float *W = weight + row * 3;
+  const float w1 = __ldg(W), w2 = __ldg(W + 1), w3 = __ldg(W + 2);
+  float *__restrict__ g1 = dknown + (b * m + __ldg(I + 0)) * C2;
+  float *__restrict__ g2 = dknown + (b * m + __ldg(I + 1)) * C2;
+  float *__restrict__ g3 = dknown + (b * m + __ldg(I + 2)) * C2;
+  const float *__restrict__ src = dx + row * (long long)ldx;
+  for (int c = lane; c < C2; c += 32) {
+    const float g = __ldg(src + c);
+    atomicAdd(g1 + c, __fmul_rn(g, w1));
+    atomicAdd(g2 + c, __fmul_rn(g, w2));
+    atomicAdd(g3 + c, __fmul_rn(g, w3));
+  }
+}
+
 }  // namespace
 }  // namespace eda
 
@@ -166,6 +255,40 @@ int eda_three_interpolate_grad(const float *grad_out, const int *idx, const floa
   dim3 grid((unsigned)((n + kIpThreads - 1) / kIpThreads), (unsigned)(B * cchunks));
   three_interpolate_grad_kernel<<<grid, kIpThreads, 0, st>>>(grad_out, idx, weight, C, n, m, cchunks, grad_points);
   return check_launch("three_interpolate_grad_kernel");
+}
+
+
+int eda_fp_gather_rows(const float *known, int ldk, const float *skip, int lds, const int *idx, const float *dist2,
+                       int B, int n, int m, int C2, int C1, float *x0, float *weight, void *stream) {
+  using namespace eda;
+  if (B < 0 || n < 0 || m <= 0 || C2 <= 0 || C1 < 0 || ldk < C2 || (C1 > 0 && skip && lds < C1)) return EDA_ERR_INVALID_ARGUMENT;
+  if (B == 0 || n == 0) return EDA_OK;
+  if (!known || !idx || !dist2 || !x0 || (C1 > 0 && !skip)) return EDA_ERR_INVALID_ARGUMENT;
+  const long long rows = (long long)B * n;
+  const bool vec = !(C2 & 3) && !(C1 & 3) && !(ldk & 3) && !(lds & 3) && !(reinterpret_cast<uintptr_t>(known) & 15) &&
+                   !(reinterpret_cast<uintptr_t>(x0) & 15) && !(skip && (reinterpret_cast<uintptr_t>(skip) & 15));
+  const unsigned grid = (unsigned)((rows + kFpWarps - 1) / kFpWarps);
+  if (vec)
+    fp_gather_rows_kernel<true><<<grid, kFpWarps * 32, 0, as_stream(stream)>>>(known, ldk, C1 ? skip : nullptr, lds, idx, dist2, rows, n, m, C2, C1, x0, weight);
+  else
+    fp_gather_rows_kernel<false><<<grid, kFpWarps * 32, 0, as_stream(stream)>>>(known, ldk, C1 ? skip : nullptr, lds, idx, dist2, rows, n, m, C2, C1, x0, weight);
+  return check_launch("fp_gather_rows_kernel");
+}
+
+int eda_fp_scatter_rows(const float *dx, int ldx, const int *idx, const float *weight, int B, int n, int m, int C2,
+                        float *dknown, void *stream) {
+  using namespace eda;
+  if (B < 0 || n < 0 || m < 0 || C2 < 0 || ldx < C2) return EDA_ERR_INVALID_ARGUMENT;
+  if (B == 0 || m == 0 || C2 == 0) return EDA_OK;
+  if (!dknown) return EDA_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = as_stream(stream);
+  EDA_CUDA_TRY(cudaMemsetAsync(dknown, 0, (size_t)B * m * C2 * sizeof(float), st), "fp scatter memset");
+  if (n == 0) return EDA_OK;
+  if (!dx || !idx || !weight) return EDA_ERR_INVALID_ARGUMENT;
+  const long long rows = (long long)B * n;
+  fp_scatter_rows_kernel<<<(unsigned)((rows + kFpWarps - 1) / kFpWarps), kFpWarps * 32, 0, st>>>(dx, ldx, idx, weight, rows,
+                                                                                                 n, m, C2, dknown);
+  return check_launch("fp_scatter_rows_kernel");
 }
 
 }  // extern "C"

@@ -52,6 +52,7 @@ struct LinProblem {
   float *y;
   float *pre;  // optional (rows, N): the LayerNorm INPUT (residual + product), saved for the backward pass
   int rows, tile0;
+  int ldy;      // row stride of the row-major output (>= N): y may be a column block of a wider matrix
   int tb, ldt;  // tb > 0: channel-major output, y[((row / tb) * N + col) * ldt + row % tb]
   int round_out;  // round the outputs to tf32 (they feed tensor-core operands of the attention kernel directly)
 };
@@ -444,7 +445,7 @@ linear_kernel(const LinParams p) {
         const int rr = warp * kRowsPerWarp + i;
         if (rr >= nvalid) break;
         const float4 *src = reinterpret_cast<const float4 *>(tile_s + (size_t)rr * pitch);
-        float4 *dst = reinterpret_cast<float4 *>(pr.y + (row0 + rr) * Nf + n0);
+        float4 *dst = reinterpret_cast<float4 *>(pr.y + (row0 + rr) * (long long)pr.ldy + n0);
         const float mean = p.ln ? w_mean[i] : 0.f, rstd = p.ln ? w_rstd[i] : 1.f;
 #pragma unroll
         for (int j = 0; j < kMaxJ; ++j) {
@@ -639,6 +640,8 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
     p.pr[i].x = q.x; p.pr[i].pos = q.pos; p.pr[i].w = q.w_packed; p.pr[i].bias = q.bias;
     p.pr[i].residual = q.residual; p.pr[i].y = q.y; p.pr[i].pre = q.pre_ln; p.pr[i].rows = q.rows; p.pr[i].tile0 = tiles;
     p.pr[i].tb = q.y_batch_rows; p.pr[i].ldt = q.y_ld; p.pr[i].round_out = q.round_tf32;
+    if (q.y_row_stride != 0 && (q.y_row_stride < N || (q.y_row_stride & 3) || q.y_batch_rows > 0)) return EDA_ERR_INVALID_ARGUMENT;
+    p.pr[i].ldy = q.y_row_stride ? q.y_row_stride : N;
     tiles += (q.rows + kRows - 1) / kRows;
   }
   if (tiles == 0) return EDA_OK;

@@ -485,15 +485,16 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, double coun
 }
 
 // ---- (B, R, C) <-> (B, C, R) -----------------------------------------------------------------
-__global__ void transpose_kernel(const float *__restrict__ in, int R, int C, float *__restrict__ out) {
+// `in` rows may be wider than C (row stride ld, first column col0): a column slice of a row-major matrix
+__global__ void transpose_kernel(const float *__restrict__ in, int col0, int ld, int R, int C, float *__restrict__ out) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
-  const float *src = in + (size_t)b * R * C;
+  const float *src = in + (size_t)b * R * ld + col0;
   float *dst = out + (size_t)b * R * C;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    if (r < R && c < C) tile[i][threadIdx.x] = src[(size_t)r * C + c];
+    if (r < R && c < C) tile[i][threadIdx.x] = src[(size_t)r * ld + c];
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -631,7 +632,18 @@ int eda_transpose_last2(const float *in, int B, int R, int C, float *out, void *
   if (!in || !out) return EDA_ERR_INVALID_ARGUMENT;
   if (B > 65535 || (R + 31) / 32 > 65535) return EDA_ERR_UNSUPPORTED;
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
-  transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, R, C, out);
+  transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, 0, C, R, C, out);
+  return check_launch("transpose_kernel");
+}
+
+int eda_transpose_strided(const float *in, int col0, int ld, int B, int R, int C, float *out, void *stream) {
+  using namespace eda;
+  if (B < 0 || R < 0 || C < 0 || col0 < 0 || ld < col0 + C) return EDA_ERR_INVALID_ARGUMENT;
+  if (B == 0 || R == 0 || C == 0) return EDA_OK;
+  if (!in || !out) return EDA_ERR_INVALID_ARGUMENT;
+  if (B > 65535 || (R + 31) / 32 > 65535) return EDA_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
+  transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, col0, ld, R, C, out);
   return check_launch("transpose_kernel");
 }
 

@@ -15,9 +15,7 @@ disappear.
 """
 from copy import deepcopy
 
-import torch
 from torch import nn
-import torch.nn.functional as F
 
 from . import attn_ops as ops
 
@@ -38,29 +36,17 @@ class PositionEmbeddingLearned(nn.Module):
             nn.Conv1d(num_pos_feats, num_pos_feats, kernel_size=1))
 
     def forward_rows(self, xyz):
-        """xyz (B, N, 3 or 6) -> (B, N, F), batch-first rows (what the attention kernels consume)."""
+        """xyz (B, N, 3 or 6) -> (B, N, F), batch-first rows (what the attention kernels consume).  Both 1x1 convs are
+        tcgen05 GEMMs over the B*N rows; train-mode BatchNorm1d takes its batch statistics (synchronised across ranks
+        when the layer is a SyncBatchNorm) and its backward on this package's kernels (eda_b200/rows_mlp.py); in
+        inference the running statistics are folded into the first GEMM."""
+        from . import rows_mlp
+
         conv1, bn, _, conv2 = self.position_embedding_head
-        w1 = conv1.weight.squeeze(-1)
-        if bn.training:
-            # batch statistics over the B*N rows (biased variance to normalise, unbiased for the running estimate)
-            h = ops.linear(xyz, w1, conv1.bias, cache_key=(self, 1))
-            h = F.batch_norm(h.transpose(1, 2), bn.running_mean, bn.running_var, bn.weight, bn.bias, True,
-                             bn.momentum if bn.momentum is not None else 0.0, bn.eps).transpose(1, 2)
-            if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
-            h = F.relu(h)
-        elif torch.is_grad_enabled() and any(q.requires_grad for q in self.position_embedding_head.parameters()):
-            # eval-mode BatchNorm under autograd: keep the affine map differentiable
-            h = ops.linear(xyz, w1, conv1.bias, cache_key=(self, 1))
-            h = F.relu(F.batch_norm(h.transpose(1, 2), bn.running_mean, bn.running_var, bn.weight, bn.bias, False,
-                                    0.0, bn.eps).transpose(1, 2))
-        else:
-            # inference: fold the running statistics into the first GEMM (scale on W, shift into the bias)
-            scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-            shift = bn.bias.detach() - bn.running_mean * scale
-            bias = shift if conv1.bias is None else conv1.bias.detach() * scale + shift
-            h = ops.linear(xyz, w1.detach(), bias, relu=True, scale=scale.contiguous())
-        return ops.linear(h, conv2.weight.squeeze(-1), conv2.bias, cache_key=(self, 2))
+        layers = [rows_mlp.Layer(conv1.weight, conv1.bias, bn, True, conv1, "w"),
+                  rows_mlp.Layer(conv2.weight, conv2.bias, None, False, conv2, "w")]
+        B, N, C = xyz.shape
+        return rows_mlp.rows_mlp(xyz.reshape(B * N, C), layers).view(B, N, -1)
 
     def forward(self, xyz):
         """Forward pass, xyz is (B, N, 3or6), output (B, F, N)."""

@@ -98,6 +98,10 @@ class GraphedTrainStep:
         # refreshes at the start of every step, instead of ~370 pack launches spread over the step
         self.pack_registry = attn_ops.PackRegistry(self.device)
         registry = self.pack_registry
+        # FlatGradients.enable_overlap(): the bucketed gradient all-reduce is issued region by region DURING the
+        # backward pass on a communication stream and is therefore part of the captured step
+        self.overlapped_allreduce = flat_grads.regions is not None
+        overlapped = self.overlapped_allreduce
 
         def step():
             if epoch is not None:
@@ -107,6 +111,8 @@ class GraphedTrainStep:
             loss = loss_fn(model(*self.static_inputs))
             loss.backward()
             flat_grads.sync()  # side-stream weight-gradient kernels rejoin the (capturing) stream
+            if overlapped:
+                flat_grads.finish()  # ... and so does the communication stream: gradients are averaged over the ranks
             return loss.detach()
 
         registry.attach(model)  # per-model context: only THIS model's modules consult the registry

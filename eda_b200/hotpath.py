@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import encoder_decoder_layers as edl
+from . import rows_mlp
 from .backbone_module import Pointnet2Backbone
 
 D_MODEL, HEADS, FFN = 288, 8, 256
@@ -24,7 +25,10 @@ class HotPath(nn.Module):
 
     def forward(self, pc, pos, text, text_mask, det, det_mask, query, qpos):
         ep = self.backbone(pc)
-        vis = ep["fp2_features"].transpose(1, 2).contiguous()
+        # (B, 288, 1024) -> batch-first rows (B, 1024, 288) on the package's transpose kernel (models/bdetr.py:259 does
+        # `.transpose(1, 2).contiguous()`, an ATen copy)
+        vis = rows_mlp.transpose_last2(ep["fp2_features"]) if ep["fp2_features"].is_cuda \
+            else ep["fp2_features"].transpose(1, 2).contiguous()
         v, t = self.encoder(vis, pos, None, text, text_mask, {}, detected_feats=det, detected_mask=det_mask)
         q = query
         for d in self.decoder:

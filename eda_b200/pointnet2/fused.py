@@ -71,24 +71,14 @@ def fusable(C, widths, nsample):
 
 def _bn_scale_shift(lib, dev, stats, count, bn, conv_bias, C, training_update, want_stats=False):
     """scale/shift of one layer.  bn None: scale = None (1), shift = conv bias (or None).  want_stats: also returns
-    the (2, C) [mean, invstd] the scale/shift were built from (BatchNorm backward needs them)."""
+    the (2, C) [mean, invstd] the scale/shift were built from (BatchNorm backward needs them).  Batch statistics of a
+    synchronised layer (SyncBatchNorm semantics, eda_b200/syncbn.py) are summed over the ranks before they are finalised."""
     if bn is None:
         r = None, (conv_bias.detach().contiguous() if conv_bias is not None else None)
         return r + (None,) if want_stats else r
-    scale = torch.empty(C, dtype=torch.float32, device=dev)
-    shift = torch.empty(C, dtype=torch.float32, device=dev)
-    mean_invstd = torch.empty(2, C, dtype=torch.float32, device=dev) if want_stats else None
-    momentum = bn.momentum
-    if training_update:
-        bn.num_batches_tracked += 1
-        if momentum is None:
-            momentum = 1.0 / float(bn.num_batches_tracked.item())
-    rc = lib.eda_bn_finalize(_p(stats), float(count), _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps),
-                             float(momentum if momentum is not None else 0.0), _p(bn.running_mean),
-                             _p(bn.running_var), 1 if training_update else 0, C, _p(scale), _p(shift),
-                             _p(mean_invstd[0]) if want_stats else None, _p(mean_invstd[1]) if want_stats else None,
-                             _stream(dev))
-    _lib.check(rc, "bn_finalize")
+    from .. import rows_mlp
+
+    scale, shift, mean_invstd = rows_mlp.bn_scale_shift(dev, stats, count, bn, C, training_update, want_stats=want_stats)
     return (scale, shift, mean_invstd) if want_stats else (scale, shift)
 
 
@@ -249,12 +239,14 @@ class FusedSAFunction(torch.autograd.Function):
         ctx.running = [(bn.running_mean.clone(), bn.running_var.clone()) if (bn is not None and not training) else None
                        for _, bn in layers]
         ctx.cuda_bw = (any(ctx.needs_input_grad) and all(has_bn) and os.environ.get("EDA_BACKWARD", "cuda") != "torch")
+        ctx.bns = [bn for _, bn in layers]
         ctx.state = [] if ctx.cuda_bw else None
         if ctx.cuda_bw:
             from .. import attn_ops
             # conv weights of layers 2 / 3 whose gradient buffers exist: their wgrad kernels accumulate straight
             # into them from the side stream (attn_ops.fused_grad_enabled); layer 1 needs a column permutation, so it stays
             ctx.gbufs = attn_ops._grad_buffers((params[4], params[8], params[0]))
+            attn_ops.grads_expected([p for p, g in zip((params[4], params[8], params[0]), ctx.gbufs) if g is not None])
         ctx.rows = None
         if ctx.cuda_bw and training and os.environ.get("EDA_SA_RECOMPUTE", "0") != "1":
             # training mode: keep the row-major pre-activations for the backward pass (EDA_SA_RECOMPUTE=1, and eval mode
@@ -347,7 +339,10 @@ def _sa_backward_cuda(ctx, grad_out):
                     src.append((z[l], ctx.state[l][0], ctx.state[l][1]))
         # ---- layer 3: max-pool + ReLU + BatchNorm backward -----------------------------------------------------
         g_pm = transpose_last2(grad_out.contiguous())  # (B, M, C3)
+        from .. import rows_mlp
         stats = [torch.zeros(2 * widths[l], **f32) for l in range(3)]
+        local_stats = list(stats)  # per layer [sum dy, sum dy zhat] of THIS rank's rows = the BatchNorm affine gradients
+        bns = ctx.bns
         dWl = [torch.zeros((widths[l], Kin[l]), **f32) for l in range(3)]
         scale, shift, mi = ctx.state[2]
         if amax is not None:  # saved by the training forward: only the reductions are left to do
@@ -357,8 +352,11 @@ def _sa_backward_cuda(ctx, grad_out):
             amax = torch.empty((B * M, widths[2]), dtype=torch.int32, device=dev)
             chk(lib.eda_sa_pool_backward(_p(z[2]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), _p(g_pm), B * M, S,
                                          widths[2], _p(amax), _p(stats[2]), stream), "sa_pool_backward")
+        count = float(R)
+        if training:  # synchronised BatchNorm: the reductions (and the row count) cover all ranks
+            stats[2], count, local_stats[2] = rows_mlp.bn_backward_reduce(bns[2], stats[2], float(R))
         chk(lib.eda_sa_pool_backward_apply(_p(z[2]), _p(amax), _p(g_pm), _p(scale), _p(mi[0]), _p(mi[1]), _p(stats[2]),
-                                           float(R), 1 if training else 0, B * M, S, widths[2], stream),
+                                           count, 1 if training else 0, B * M, S, widths[2], stream),
             "sa_pool_backward_apply")
         dz = z[2]  # overwritten in place
         z[2] = None
@@ -389,8 +387,11 @@ def _sa_backward_cuda(ctx, grad_out):
             scale, shift, mi = ctx.state[l - 1]
             chk(lib.eda_bn_relu_backward_stats(_p(da), _p(z[l - 1]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]), R,
                                                widths[l - 1], _p(stats[l - 1]), stream), "bn_relu_backward_stats")
+            count = float(R)
+            if training:
+                stats[l - 1], count, local_stats[l - 1] = rows_mlp.bn_backward_reduce(bns[l - 1], stats[l - 1], float(R))
             chk(lib.eda_bn_relu_backward_apply(_p(da), _p(z[l - 1]), _p(scale), _p(shift), _p(mi[0]), _p(mi[1]),
-                                               _p(stats[l - 1]), float(R), 1 if training else 0, R, widths[l - 1], stream),
+                                               _p(stats[l - 1]), count, 1 if training else 0, R, widths[l - 1], stream),
                 "bn_relu_backward_apply")
             dz = da
         gf = None
@@ -399,6 +400,7 @@ def _sa_backward_cuda(ctx, grad_out):
             dfeat_pm = torch.zeros((B, N, C), **f32)
             chk(lib.eda_sa_scatter_rows(_p(dx0), _p(idx), B, N, M, S, C, K0pad, _p(dfeat_pm), stream), "sa_scatter_rows")
             gf = transpose_last2(dfeat_pm)
+    ops.grads_written([p for p, g in zip((params[4], params[8], params[0]), ctx.gbufs) if g is not None])
     gps = []
     for l in range(3):
         w = params[4 * l]
@@ -406,7 +408,7 @@ def _sa_backward_cuda(ctx, grad_out):
             dW = None if g1 is not None else torch.cat([dWl[0][:, C:C + 3], dWl[0][:, :C]], dim=1)
         else:
             dW = None if fused_w[l] is not None else dWl[l]
-        gps += [None if dW is None else dW.reshape(w.shape), None, stats[l][widths[l]:], stats[l][:widths[l]]]
+        gps += [None if dW is None else dW.reshape(w.shape), None, local_stats[l][widths[l]:], local_stats[l][:widths[l]]]
     return (None, None, None, gf, None, *gps)
 
 

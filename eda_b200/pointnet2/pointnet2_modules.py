@@ -100,15 +100,43 @@ class PointnetSAModuleVotes(nn.Module):
 
 
 class PointnetFPModule(nn.Module):
-    """Feature propagation: 3-NN inverse-distance interpolation + skip concat + SharedMLP."""
+    """Feature propagation: 3-NN inverse-distance interpolation + skip concat + SharedMLP
+    (pointnet2/pointnet2_modules.py:356-416).
+
+    On CUDA the whole module runs on this package's kernels: eda_three_nn -> eda_fp_gather_rows (weights +
+    interpolation + concat in one pass, row-major) -> per layer tcgen05 GEMM + BatchNorm statistics / apply kernels
+    (eda_b200/rows_mlp.py), forward and backward; the result returns to the reference's (B, C, n) layout through the
+    transpose kernel and carries its point-major copy along for the next consumer."""
 
     def __init__(self, *, mlp: List[int], bn: bool = True):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
+        self.fuse = True  # False: the reference's op-by-op composition on torch layers (tests compare the two)
+
+    def _rows_layers(self):
+        from .. import rows_mlp
+
+        layers = self.mlp.fusable_layers()
+        if layers is None or any(bn is None for _, bn in layers):
+            return None
+        if any(conv.out_channels % 16 or conv.out_channels > 320 or conv.in_channels % 16 for conv, _ in layers):
+            return None
+        return [rows_mlp.Layer(conv.weight, conv.bias, bn, True, conv, "w") for conv, bn in layers]
 
     def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
                 known_feats: torch.Tensor) -> torch.Tensor:
         """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m) -> (B,mlp[-1],n)."""
+        layers = self._rows_layers() if (self.fuse and known is not None and known_feats.is_cuda) else None
+        if layers is not None:
+            from .. import rows_mlp
+
+            B, n = unknown.size(0), unknown.size(1)
+            dist2, idx = pointnet2_utils.three_nn_squared(unknown, known)
+            x0 = rows_mlp.fp_rows(dist2, idx, known_feats, unknow_feats)
+            out_pm = rows_mlp.rows_mlp(x0, layers).view(B, n, -1)
+            new_features = rows_mlp.transpose_last2(out_pm)
+            fused.attach_point_major(new_features, out_pm.detach())
+            return new_features
         if known is not None:
             dist, idx = pointnet2_utils.three_nn(unknown, known)
             dist_recip = 1.0 / (dist + 1e-8)

@@ -59,6 +59,13 @@ class ThreeNN(Function):
 three_nn = ThreeNN.apply
 
 
+def three_nn_squared(unknown, known):
+    """The native op's own outputs (SQUARED distances, indices), non-differentiable like ThreeNN: what the fused
+    feature-propagation path consumes (the sqrt and the weight arithmetic happen inside eda_fp_gather_rows)."""
+    with torch.no_grad():
+        return _ext.three_nn(unknown.detach().contiguous(), known.detach().contiguous())
+
+
 class ThreeInterpolate(Function):
     @staticmethod
     def forward(ctx, features, idx, weight):

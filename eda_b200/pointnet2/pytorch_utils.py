@@ -10,14 +10,6 @@ the parameters out of them and runs the fused CUDA kernels (pointnet2_modules.py
 import torch.nn as nn
 
 
-def _wrap_bn(bn_cls, channels, name):
-    holder = nn.Sequential()
-    holder.add_module(name + "bn", bn_cls(channels))
-    nn.init.constant_(holder[0].weight, 1.0)
-    nn.init.constant_(holder[0].bias, 0.0)
-    return holder
-
-
 class BatchNorm1d(nn.Sequential):
     def __init__(self, in_size, *, name=""):
         super().__init__()

@@ -80,6 +80,13 @@ EDA_API int eda_furthest_point_sampling(const float *xyz, int B, int N, int m, v
  * the strictly serial sampling of the remaining ones continues on otherwise idle SMs.  every >= 2. */
 EDA_API int eda_furthest_point_sampling_progress(const float *xyz, int B, int N, int m, void *scratch, int *idxs,
                                                  int *progress, int every, void *stream);
+/* Measurement aid (no reference counterpart): the sampler's per-iteration reduction + cluster-exchange chain alone
+ * (warp arg-max, shared-memory stage, bar.sync, st.async/mbarrier exchange between the `cluster` CTAs of a scene,
+ * cluster arg-max) for `iters` dependent iterations on B clusters of `threads` threads — the latency floor bench.py
+ * quotes next to the sampler's cycles per iteration.  sink: B words (keeps the chain alive).  Also reports through
+ * eda_fps_plan which decomposition eda_furthest_point_sampling uses for (N). */
+EDA_API int eda_selftest_fps_exchange(int B, int cluster, int threads, int iters, unsigned int *sink, void *stream);
+EDA_API int eda_fps_plan(int B, int N, int m, int *cluster, int *threads, int *points_per_thread);
 /* Stream-ordered wait on a device word: work queued on `stream` after this call starts once
  * (int)(*addr - value) >= 0 (cuStreamWaitValue32; no SM is occupied while waiting). */
 EDA_API int eda_stream_wait_value32(void *stream, const int *addr, int value);
@@ -128,6 +135,20 @@ EDA_API int eda_three_interpolate(const float *points, const int *idx, const flo
 EDA_API int eda_three_interpolate_grad(const float *grad_out, const int *idx, const float *weight, int B,
                                int C, int n, int m, float *grad_points, void *stream);
 
+/* Feature propagation in the row-major layout its MLP consumes.  Replaces, as ONE pass, the weight arithmetic +
+ * three_interpolate + torch.cat of PointnetFPModule.forward (pointnet2/pointnet2_modules.py:393-410;
+ * pointnet2_utils.py:142 for the sqrt): with dist2 / idx (B,n,3) from eda_three_nn,
+ *   weight_k = (1 / (sqrt(dist2_k) + 1e-8)) / sum_k(1 / (sqrt(dist2_k) + 1e-8))        (written to `weight` (B,n,3), may be NULL)
+ *   x0[(b,j)] = [ sum_k weight_k * known[b, idx_k, :]  (C2) | skip[b, j, :]  (C1) ]       x0 is (B*n, C2 + C1)
+ * known (B,m,C2; row stride ldk) and skip (B,n,C1; row stride lds; NULL with C1 = 0) are POINT-major.
+ * eda_fp_scatter_rows is the backward of the interpolated half (three_interpolate_grad, interpolate_gpu.cu:121-148):
+ *   dknown (B,m,C2) point-major (zero-filled here) += weight_k * dx[(b,j), 0:C2] at idx_k. */
+EDA_API int eda_fp_gather_rows(const float *known, int ldk, const float *skip, int lds, const int *idx,
+                               const float *dist2, int B, int n, int m, int C2, int C1, float *x0, float *weight,
+                               void *stream);
+EDA_API int eda_fp_scatter_rows(const float *dx, int ldx, const int *idx, const float *weight, int B, int n, int m, int C2,
+                                float *dknown, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fused set-abstraction grouped MLP: neighbour gather + centre/normalise + concat + 3 x [1x1 conv ->
  * BatchNorm -> ReLU] + max over nsample, one kernel, tcgen05 kind::tf32 with fp32 accumulation.
@@ -174,6 +195,8 @@ EDA_API int eda_bn_finalize(const double *stats, double count, const float *gamm
                             float momentum, float *running_mean, float *running_var, int update_running, int C,
                             float *scale, float *shift, float *save_mean, float *save_invstd, void *stream);
 EDA_API int eda_transpose_last2(const float *in, int B, int R, int C, float *out, void *stream);
+/* Same for a column slice of wider rows: in is (B, R, ld) and columns col0 .. col0+C-1 become out (B, C, R). */
+EDA_API int eda_transpose_strided(const float *in, int col0, int ld, int B, int R, int C, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Cross-modal attention layers (models/encoder_decoder_layers.py).  All activations are row-major
@@ -213,6 +236,9 @@ typedef struct eda_linear_problem {
                             eda_attention_forward feeds to the tensor cores as they are */
   float *pre_ln;         /* optional (rows, N): receives the LayerNorm input (residual + product), which
                             eda_layernorm_backward needs; NULL = not stored */
+  int y_row_stride;      /* 0: rows of y are N floats apart.  > N (multiple of 4): y is a column block of a wider
+                            row-major matrix (row-major output only) */
+  int reserved;
 } eda_linear_problem;
 EDA_API size_t eda_linear_packed_floats(int N, int K);
 EDA_API int eda_linear_pack(const float *W, const float *scale, int N, int K, float *packed, void *stream);
@@ -292,6 +318,10 @@ EDA_API int eda_attention_backward_tc(const float *q, const float *k, const floa
                                       float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
                                       float *dk, float *dv, void *stream);
 EDA_API int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *stream);
+/* Same accumulation for a tiny contraction width the tensor-core kernel does not take (K <= 8, any alignment): the 3- /
+ * 6-channel first conv of PositionEmbeddingLearned (models/encoder_decoder_layers.py:24-28).  fp32 FMAs. */
+EDA_API int eda_wgrad_small(const float *dy, int ldy, const float *x, int ldx, long long rows, int N, int K, float *dw,
+                            int ldw, float *db, void *stream);
 EDA_API int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, float eps, long long rows, int N,
                                    float *du, float *dproj, float *dgamma, float *dbeta, float dropout_p,
                                    unsigned int dropout_seed, void *stream);

@@ -10,7 +10,13 @@ tensors, e.g. pointnet2/_ext_src/src/sampling.cpp:87).
 We do not run the reference's setup.py; this is a direct nvcc/g++ recipe with the same
 flags it passes (-O2 and the include dir, pointnet2/setup.py:24-27).
 
-Only tests/ and bench.py (R-GPU baseline leg) load the result.
+The reference's PYTHON side of the path (pointnet2/*.py, models/{bdetr,modules,backbone_module,
+encoder_decoder_layers}.py) is needed on the GPU box too (full-model parity tests, the R-GPU baseline leg of bench.py),
+and /root/reference does not exist there: `build_pyref` byte-compiles those files where they lie into
+oracle/_ref/pyref/{pointnet2,models}/*.pyc (sourceless bytecode, git-ignored, travels like the .so).  No reference
+source text enters the repository.
+
+Only tests/ and bench.py (R-GPU baseline leg / CPU reference arm) load the results.
 """
 import os
 import subprocess
@@ -18,7 +24,13 @@ import sys
 import sysconfig
 from concurrent.futures import ThreadPoolExecutor
 
+REF_ROOT = "/root/reference"
 REF_SRC = "/root/reference/pointnet2/_ext_src"
+PYREF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyref")
+PYREF_FILES = {
+    "pointnet2": ["pointnet2_modules.py", "pointnet2_utils.py", "pytorch_utils.py"],
+    "models": ["bdetr.py", "modules.py", "backbone_module.py", "encoder_decoder_layers.py"],
+}
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "_ref", "pointnet2")
 OBJ_DIR = os.path.join(HERE, "_ref", "obj")
@@ -73,6 +85,26 @@ def build(force=False, verbose=True):
     return out
 
 
+def build_pyref(force=False):
+    """Byte-compiles the reference's Python modules on the path into oracle/_ref/pyref (see the module docstring).
+    Returns the directory, or None when /root/reference is absent (GPU box: the prebuilt files are used)."""
+    import py_compile
+
+    if not os.path.isdir(os.path.join(REF_ROOT, "models")):
+        return PYREF_DIR if os.path.isdir(PYREF_DIR) else None
+    for sub, names in PYREF_FILES.items():
+        os.makedirs(os.path.join(PYREF_DIR, sub), exist_ok=True)
+        for name in names:
+            src = os.path.join(REF_ROOT, sub, name)
+            dst = os.path.join(PYREF_DIR, sub, name + "c")
+            if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+                # dfile: tracebacks name the reference file; UNCHECKED_HASH: valid without the source next to it
+                py_compile.compile(src, cfile=dst, dfile=f"<reference>/{sub}/{name}", doraise=True,
+                                   invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    return PYREF_DIR
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv)
     print("built" if p else "reference sources absent; nothing built", p)
+    print("pyref:", build_pyref(force="--force" in sys.argv))

@@ -84,5 +84,5 @@ def test_hand_built_abi_structs_match_the_header_layout():
     row = (ctypes.c_longlong * 6)(0x1000, 0x2000, 288, 1, 288 | (256 << 32), 256)
     d = Desc.from_buffer_copy(bytes(row))
     assert (d.w, d.dst, d.sn, d.sk, d.N, d.K, d.Kpad, d.reserved) == (0x1000, 0x2000, 288, 1, 288, 256, 256, 0)
-    assert ctypes.sizeof(_lib.LinearProblem) == 6 * 8 + 4 * 4 + 8      # 6 pointers, 4 ints, pre_ln
+    assert ctypes.sizeof(_lib.LinearProblem) == 6 * 8 + 4 * 4 + 8 + 2 * 4  # 6 pointers, 4 ints, pre_ln, y_row_stride + reserved
     assert ctypes.sizeof(_lib.WgradProblem) == 4 * 8 + 8 + 3 * 4 + 4 + 2 * 8  # 4 pointers, rows, 3 ints (+pad), 2 pointers
