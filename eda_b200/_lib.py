@@ -50,29 +50,28 @@ PROTOTYPES = {
     "eda_linear_pack": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp]),
     "eda_linear_pack_batch": (_c_int, [_vp, _c_int, _c_int, _vp]),
     "eda_linear_forward": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_float, _c_int, _c_float,
-                                    ctypes.c_uint, _vp]),
-    "eda_dropout_mask": (_c_int, [ctypes.c_uint, _c_float, ctypes.c_longlong, _c_int, ctypes.c_uint, ctypes.c_uint, _vp,
-                                  _vp]),
-    "eda_dropout_set_epoch": (_c_int, [_vp]),
+                                    ctypes.c_uint, _vp, _vp]),
+    "eda_dropout_mask": (_c_int, [ctypes.c_uint, _vp, _c_float, ctypes.c_longlong, _c_int, ctypes.c_uint, ctypes.c_uint,
+                                  _vp, _vp]),
     "eda_debug_timestamps": (_c_int, [_vp, _c_int]),
     "eda_debug_timestamps_attn": (_c_int, [_vp, _c_int]),
     "eda_attention_forward": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
-                                       _c_float, ctypes.c_uint, _vp, _vp]),
+                                       _c_float, ctypes.c_uint, _vp, _vp, _vp]),
     "eda_linear_pack_strided": (_c_int, [_vp, ctypes.c_longlong, ctypes.c_longlong, _c_int, _c_int, _vp, _vp]),
     "eda_attention_forward_lse": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
-                                           _c_float, ctypes.c_uint, _vp, _vp, _vp]),
+                                           _c_float, ctypes.c_uint, _vp, _vp, _vp, _vp]),
     "eda_attention_backward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
-                                        _c_int, _c_int, _c_float, _c_float, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp]),
+                                        _c_int, _c_int, _c_float, _c_float, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp, _vp]),
     "eda_attention_backward_tc": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp,
                                            _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, ctypes.c_uint,
-                                           _vp, _vp, _vp, _vp, _vp]),
+                                           _vp, _vp, _vp, _vp, _vp, _vp]),
     "eda_wgrad": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp]),
     "eda_wgrad_small": (_c_int, [_vp, _c_int, _vp, _c_int, ctypes.c_longlong, _c_int, _c_int, _vp, _c_int, _vp, _vp]),
     "eda_fp_gather_rows": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp,
                                     _vp]),
     "eda_fp_scatter_rows": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_layernorm_backward": (_c_int, [_vp, _vp, _vp, _c_float, ctypes.c_longlong, _c_int, _vp, _vp, _vp, _vp, _c_float,
-                                        ctypes.c_uint, _vp]),
+                                        ctypes.c_uint, _vp, _vp]),
     "eda_relu_backward": (_c_int, [_vp, _vp, _c_float, ctypes.c_longlong, _vp, _vp]),
     "eda_rows_gemm": (_c_int, [_vp, _c_int, _vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _c_int,
                                _c_int, _vp, _c_int, _vp]),
@@ -89,6 +88,10 @@ PROTOTYPES = {
     "eda_sa_pool_forward": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _c_int, _c_int, _vp, _vp, _vp]),
     "eda_sa_pool_backward_stats": (_c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _c_int, _c_int, _vp, _vp]),
     "eda_sa_scatter_rows": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_peer_buffer_bytes": (_sz, [_c_int, _c_int]),
+    "eda_peer_allreduce": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _c_int, _c_int, _vp]),
+    "eda_bn_finalize_peer": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, ctypes.c_double, _vp, _vp, _c_float, _c_float,
+                                      _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "eda_selftest_umma": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_selftest_umma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
 }

@@ -170,12 +170,28 @@ def new_seed():
     return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
 
 
-def dropout_mask(seed, p, rows, cols, a_mul, a_add, device):
-    """(rows, cols) f32 keep-mask (1 / 0) that a forward kernel seeded `seed` applied (see include/eda_b200.h)."""
+def epoch_of(module):
+    """The dropout epoch word (device int32 tensor) a GraphedTrainStep attached to `module`'s model, or None: every
+    dropout-applying kernel launched for this module adds its value to the host-drawn seed when it runs."""
+    return getattr(module, "__dict__", {}).get("_eda_dropout_epoch")
+
+
+def _drop(dropout):
+    """(p, seed[, epoch tensor]) or None -> (p, seed, epoch pointer) for the C ABI."""
+    if dropout is None:
+        return 0.0, 0, None
+    p, seed = dropout[0], dropout[1]
+    epoch = dropout[2] if len(dropout) > 2 else None
+    return float(p), int(seed), _p(epoch)
+
+
+def dropout_mask(seed, p, rows, cols, a_mul, a_add, device, epoch=None):
+    """(rows, cols) f32 keep-mask (1 / 0) that a forward kernel seeded `seed` (+ the current value of the `epoch` word)
+    applied (see include/eda_b200.h)."""
     out = torch.empty((rows, cols), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
-        rc = _lib.load().eda_dropout_mask(int(seed), float(p), int(rows), int(cols), int(a_mul), int(a_add), _p(out),
-                                          _stream(device))
+        rc = _lib.load().eda_dropout_mask(int(seed), _p(epoch), float(p), int(rows), int(cols), int(a_mul), int(a_add),
+                                          _p(out), _stream(device))
     _lib.check(rc, "dropout_mask")
     return out
 
@@ -231,9 +247,9 @@ def linear_raw(problems, K, N, relu=False, ln=None, dropout=None):
         g = g.detach().contiguous() if g is not None else None
         b = b.detach().contiguous() if b is not None else None
     with torch.cuda.device(dev):
-        dp, dseed = dropout if dropout is not None else (0.0, 0)
+        dp, dseed, depoch = _drop(dropout)
         rc = lib.eda_linear_forward(ctypes.cast(arr, ctypes.c_void_p), len(problems), K, N, 1 if relu else 0, _p(g),
-                                    _p(b), float(eps), 1 if ln is not None else 0, float(dp), int(dseed), _stream(dev))
+                                    _p(b), float(eps), 1 if ln is not None else 0, dp, dseed, depoch, _stream(dev))
     _lib.check(rc, "linear_forward")
     return outs
 
@@ -255,9 +271,9 @@ def attention_raw(q, k, vt, key_padding_mask, B, Nq, Nk, H, dropout=None, lse=No
         m = m.contiguous().view(torch.uint8)
         assert m.shape == (B, Nk)
     with torch.cuda.device(q.device):
-        dp, dseed = dropout if dropout is not None else (0.0, 0)
+        dp, dseed, depoch = _drop(dropout)
         rc = lib.eda_attention_forward_lse(_p(q), _p(k), _p(vt), ldv, _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D),
-                                           float(dp), int(dseed), _p(ctx), _p(lse), _stream(q.device))
+                                           dp, dseed, depoch, _p(ctx), _p(lse), _stream(q.device))
     _lib.check(rc, "attention_forward")
     return ctx
 
@@ -442,11 +458,11 @@ def layernorm_backward(dy, u, gamma, eps, dgamma, dbeta, dropout=None):
     N = u.size(-1)
     R = u.numel() // N
     du = torch.empty_like(u)
-    dp, dseed = dropout if dropout is not None else (0.0, 0)
+    dp, dseed, depoch = _drop(dropout)
     dproj = torch.empty_like(u) if dp > 0 else du
     with torch.cuda.device(u.device):
         rc = lib.eda_layernorm_backward(_p(dy), _p(u), _p(gamma.detach().contiguous()), float(eps), R, N, _p(du),
-                                        _p(dproj) if dp > 0 else None, _p(dgamma), _p(dbeta), float(dp), int(dseed),
+                                        _p(dproj) if dp > 0 else None, _p(dgamma), _p(dbeta), dp, dseed, depoch,
                                         _stream(u.device))
     _lib.check(rc, "layernorm_backward")
     return du, dproj
@@ -518,7 +534,7 @@ def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, 
         if m.dtype != torch.bool:
             m = m != 0
         m = m.contiguous().view(torch.uint8)
-    dp, dseed = dropout if dropout is not None else (0.0, 0)
+    dp, dseed, depoch = _drop(dropout)
     if impl == "tc":
         v = _transpose_last2(vt)  # (B, ld, E): row-major values, rows >= Nk are padding and never read
         kt, ldk = _channel_major(k, B, Nk, E)
@@ -526,15 +542,15 @@ def attention_backward_raw(q, k, vt, dctx, c, lse, key_padding_mask, B, Nq, Nk, 
         dot, _ = _channel_major(dctx, B, Nq, E)
         with torch.cuda.device(q.device):
             rc = lib.eda_attention_backward_tc(_p(q), _p(k), _p(v), ld * E, _p(kt), ldk, _p(qt), _p(dot), ldq, _p(dctx),
-                                               _p(c), _p(lse), _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), float(dp),
-                                               int(dseed), _p(delta), _p(dq), _p(dk), _p(dv), _stream(q.device))
+                                               _p(c), _p(lse), _p(m), B, Nq, Nk, H, D, 1.0 / math.sqrt(D), dp,
+                                               dseed, depoch, _p(delta), _p(dq), _p(dk), _p(dv), _stream(q.device))
         _lib.check(rc, "attention_backward_tc")
         return dq, dk, dv
     v_nat = _transpose_last2(vt) if impl == "mma_natural" else None  # the ABI's row-major-values variant (tests)
     with torch.cuda.device(q.device):  # the warp-level kernel reads the channel-major values as they are
         rc = lib.eda_attention_backward(_p(q), _p(k), _p(v_nat), ld * E if v_nat is not None else 0,
                                         None if v_nat is not None else _p(vt), ld, _p(dctx), _p(c), _p(lse), _p(m), B, Nq, Nk, H, D,
-                                        1.0 / math.sqrt(D), float(dp), int(dseed), _p(delta), _p(dq), _p(dk), _p(dv),
+                                        1.0 / math.sqrt(D), dp, dseed, depoch, _p(delta), _p(dq), _p(dk), _p(dv),
                                         _stream(q.device))
     _lib.check(rc, "attention_backward")
     return dq, dk, dv
@@ -567,7 +583,7 @@ def _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H
 class _MHABlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, H, eps, key, mask, q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b,
-                drop=(0.0, 0, 0.0, 0)):
+                drop=(0.0, 0, 0.0, 0, None)):
         E = q_in.size(-1)
         B, Nq, _ = q_in.shape
         Nk = k_in.size(1)
@@ -586,17 +602,17 @@ class _MHABlockFn(torch.autograd.Function):
             dict(x=k_in, pos=kp, w_packed=wk, bias=ib[E:2 * E], round_tf32=True),
             dict(x=v_in, w_packed=wv, bias=ib[2 * E:], y_batch_rows=Nk, round_tf32=True),
         ], E, E)
-        p_attn, seed_attn, p_out, seed_out = drop
+        p_attn, seed_attn, p_out, seed_out, epoch = drop
         # eda_attention_backward is instantiated for head dims 32 and 36 (the forward also takes 64): other sizes
         # differentiate through the torch restatement instead of failing at backward() time
         train = any(ctx.needs_input_grad) and use_cuda_backward() and (E // H) in CUDA_BACKWARD_HEAD_DIMS
         lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if train else None
-        c = attention_raw(q, k, v, mask, B, Nq, Nk, H, dropout=(p_attn, seed_attn) if p_attn > 0 else None, lse=lse)
+        c = attention_raw(q, k, v, mask, B, Nq, Nk, H, dropout=(p_attn, seed_attn, epoch) if p_attn > 0 else None, lse=lse)
         res = residual.contiguous() if residual is not None else None
         ln = (ln_w, ln_b, eps) if ln_w is not None else None
         u = torch.empty((B * Nq, E), dtype=torch.float32, device=q.device) if (train and ln is not None) else None
         (y,) = linear_raw([dict(x=c, w_packed=wo, bias=out_b, residual=res, pre_ln=u)], E, E, ln=ln,
-                          dropout=(p_out, seed_out) if p_out > 0 else None)
+                          dropout=(p_out, seed_out, epoch) if p_out > 0 else None)
         if ln is None and res is not None:
             y = y + res.view(-1, E)
         ctx.save_for_backward(q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b,
@@ -614,7 +630,7 @@ class _MHABlockFn(torch.autograd.Function):
         if ctx.cuda_bw:
             return _MHABlockFn._backward_cuda(ctx, grad)
         H, eps, mask, drop = ctx.meta
-        p_attn, seed_attn, p_out, seed_out = drop
+        p_attn, seed_attn, p_out, seed_out, epoch = drop
         saved = ctx.saved_tensors
         with torch.enable_grad():
             ts = [None if t is None else t.detach().requires_grad_(ctx.needs_input_grad[4 + i])
@@ -623,11 +639,11 @@ class _MHABlockFn(torch.autograd.Function):
             B_, Nq_, E_ = q_in.shape
             attn_keep = None
             if p_attn > 0:  # the exact keep-mask the forward kernel applied
-                attn_keep = dropout_mask(seed_attn, p_attn, B_ * H * Nq_, k_in.size(1), 1, 0, q_in.device)
+                attn_keep = dropout_mask(seed_attn, p_attn, B_ * H * Nq_, k_in.size(1), 1, 0, q_in.device, epoch)
             y = _mha_torch(q_in, q_pos, k_in, k_pos, v_in, mask, in_w, in_b, out_w, out_b, H, attn_keep,
                            1.0 / (1.0 - p_attn))
             if p_out > 0:
-                y = y * (dropout_mask(seed_out, p_out, B_ * Nq_, E_, 3, 0, q_in.device).view_as(y) * (1.0 / (1.0 - p_out)))
+                y = y * (dropout_mask(seed_out, p_out, B_ * Nq_, E_, 3, 0, q_in.device, epoch).view_as(y) * (1.0 / (1.0 - p_out)))
             if residual is not None:
                 y = residual + y
             if ln_w is not None:
@@ -642,7 +658,7 @@ class _MHABlockFn(torch.autograd.Function):
     @staticmethod
     def _backward_cuda(ctx, grad):
         H, eps, mask, drop = ctx.meta
-        p_attn, seed_attn, p_out, seed_out = drop
+        p_attn, seed_attn, p_out, seed_out, epoch = drop
         (q_in, q_pos, k_in, k_pos, v_in, residual, in_w, in_b, out_w, out_b, ln_w, ln_b, q, k, vt, c, lse, u) = \
             ctx.saved_tensors
         key = ctx.key
@@ -670,18 +686,18 @@ class _MHABlockFn(torch.autograd.Function):
         # 1. LayerNorm (+ output dropout)
         if has_ln:
             du, dproj = layernorm_backward(grad, u, ln_w, eps, d_ln_w, d_ln_b,
-                                           dropout=(p_out, seed_out) if p_out > 0 else None)
+                                           dropout=(p_out, seed_out, epoch) if p_out > 0 else None)
         else:
             du = grad
             dproj = grad
             if p_out > 0:
-                dproj = grad * (dropout_mask(seed_out, p_out, B * Nq, E, 3, 0, dev) * (1.0 / (1.0 - p_out)))
+                dproj = grad * (dropout_mask(seed_out, p_out, B * Nq, E, 3, 0, dev, epoch) * (1.0 / (1.0 - p_out)))
         # 2. out-projection: activation gradient (tcgen05 GEMM with the transposed weight) and weight gradient
         (dctx,) = linear_raw([dict(x=dproj, w_packed=pack_weight_t(out_w, cache_key=(key, "ot")))], E, E)
         run_wgrad([dict(dy=dproj, x=c, dw=d_out_w, db=d_out_b)], E, E)
         # 3. attention core
         dq, dk, dv = attention_backward_raw(q, k, vt, dctx, c, lse, mask, B, Nq, Nk, H,
-                                            dropout=(p_attn, seed_attn) if p_attn > 0 else None)
+                                            dropout=(p_attn, seed_attn, epoch) if p_attn > 0 else None)
         # 4. in-projections
         dq_in, dk_in, dv_in = linear_raw([
             dict(x=dq, w_packed=pack_weight_t(in_w[:E], cache_key=(key, "qt"))),
@@ -721,7 +737,7 @@ def mha_block(mha, q_in, k_in, v_in, q_pos=None, k_pos=None, key_padding_mask=No
     [+ residual]).  All activations batch-first (B, S, E)."""
     p_attn = float(mha.dropout) if mha.training else 0.0
     p_out = float(out_dropout.p) if (out_dropout is not None and out_dropout.training) else 0.0
-    drop = (p_attn, new_seed() if p_attn > 0 else 0, p_out, new_seed() if p_out > 0 else 0)
+    drop = (p_attn, new_seed() if p_attn > 0 else 0, p_out, new_seed() if p_out > 0 else 0, epoch_of(mha))
     return _MHABlockFn.apply(mha.num_heads, norm.eps if norm is not None else 0.0, mha, key_padding_mask, q_in,
                              q_pos, k_in, k_pos, v_in, residual, mha.in_proj_weight, mha.in_proj_bias,
                              mha.out_proj.weight, mha.out_proj.bias, norm.weight if norm is not None else None,
@@ -730,19 +746,19 @@ def mha_block(mha, q_in, k_in, v_in, q_pos=None, k_pos=None, key_padding_mask=No
 
 class _FFNBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eps, key, x, w1, b1, w2, b2, ln_w, ln_b, drop=(0.0, 0, 0.0, 0)):
+    def forward(ctx, eps, key, x, w1, b1, w2, b2, ln_w, ln_b, drop=(0.0, 0, 0.0, 0, None)):
         _require_cuda(x)
         shape = x.shape
         E, Fh = w1.size(1), w1.size(0)
         x2 = x.contiguous().view(-1, E)
         p1 = pack_weight(w1, cache_key=(key, "w1"))
         p2 = pack_weight(w2, cache_key=(key, "w2"))
-        pa, sa, pb, sb = drop
+        pa, sa, pb, sb, epoch = drop
         train = any(ctx.needs_input_grad) and use_cuda_backward()
-        (hdn,) = linear_raw([dict(x=x2, w_packed=p1, bias=b1)], E, Fh, relu=True, dropout=(pa, sa) if pa > 0 else None)
+        (hdn,) = linear_raw([dict(x=x2, w_packed=p1, bias=b1)], E, Fh, relu=True, dropout=(pa, sa, epoch) if pa > 0 else None)
         u = torch.empty_like(x2) if train else None
         (y,) = linear_raw([dict(x=hdn, w_packed=p2, bias=b2, residual=x2, pre_ln=u)], Fh, E, ln=(ln_w, ln_b, eps),
-                          dropout=(pb, sb) if pb > 0 else None)
+                          dropout=(pb, sb, epoch) if pb > 0 else None)
         ctx.save_for_backward(x, w1, b1, w2, b2, ln_w, ln_b, *((hdn, u) if train else ()))
         ctx.eps = eps
         ctx.drop = drop
@@ -756,7 +772,7 @@ class _FFNBlockFn(torch.autograd.Function):
     @staticmethod
     def _backward_cuda(ctx, grad):
         x, w1, b1, w2, b2, ln_w, ln_b, hdn, u = ctx.saved_tensors
-        pa, sa, pb, sb = ctx.drop
+        pa, sa, pb, sb, epoch = ctx.drop
         key = ctx.key
         E, Fh = w1.size(1), w1.size(0)
         dev = x.device
@@ -774,7 +790,7 @@ class _FFNBlockFn(torch.autograd.Function):
             d_ln_w = flat[o:o + E]; o += E
             d_ln_b = flat[o:o + E]
         run_wgrad = wgrad_side if fused else wgrad
-        du, dproj = layernorm_backward(grad, u, ln_w, ctx.eps, d_ln_w, d_ln_b, dropout=(pb, sb) if pb > 0 else None)
+        du, dproj = layernorm_backward(grad, u, ln_w, ctx.eps, d_ln_w, d_ln_b, dropout=(pb, sb, epoch) if pb > 0 else None)
         (dh,) = linear_raw([dict(x=dproj, w_packed=pack_weight_t(w2, cache_key=(key, "w2t")))], E, Fh)
         # hdn is the saved post-ReLU, post-dropout activation: > 0 exactly where the unit was active and kept
         dz = relu_backward(dh, hdn, 1.0 / (1.0 - pa) if pa > 0 else 1.0)
@@ -794,14 +810,14 @@ class _FFNBlockFn(torch.autograd.Function):
         with torch.enable_grad():
             ts = [t.detach().requires_grad_(ctx.needs_input_grad[2 + i]) for i, t in enumerate(ctx.saved_tensors)]
             x, w1, b1, w2, b2, ln_w, ln_b = ts
-            pa, sa, pb, sb = ctx.drop
+            pa, sa, pb, sb, epoch = ctx.drop
             hdn = F.relu(F.linear(x, w1, b1))
             R = hdn.numel() // hdn.size(-1)
             if pa > 0:
-                hdn = hdn * (dropout_mask(sa, pa, R, hdn.size(-1), 3, 0, x.device).view_as(hdn) * (1.0 / (1.0 - pa)))
+                hdn = hdn * (dropout_mask(sa, pa, R, hdn.size(-1), 3, 0, x.device, epoch).view_as(hdn) * (1.0 / (1.0 - pa)))
             o = F.linear(hdn, w2, b2)
             if pb > 0:
-                o = o * (dropout_mask(sb, pb, R, o.size(-1), 3, 0, x.device).view_as(o) * (1.0 / (1.0 - pb)))
+                o = o * (dropout_mask(sb, pb, R, o.size(-1), 3, 0, x.device, epoch).view_as(o) * (1.0 / (1.0 - pb)))
             y = F.layer_norm(x + o, (x.size(-1),), ln_w, ln_b, ctx.eps)
             wanted = [t for t in ts if t.requires_grad]
             grads = torch.autograd.grad(y, wanted, grad, allow_unused=True) if wanted else []
@@ -814,7 +830,7 @@ def ffn_block(ffn, x, norm):
     l1, l2 = ffn[0], ffn[3]
     pa = float(ffn[2].p) if ffn[2].training else 0.0
     pb = float(ffn[4].p) if ffn[4].training else 0.0
-    drop = (pa, new_seed() if pa > 0 else 0, pb, new_seed() if pb > 0 else 0)
+    drop = (pa, new_seed() if pa > 0 else 0, pb, new_seed() if pb > 0 else 0, epoch_of(ffn))
     return _FFNBlockFn.apply(norm.eps, ffn, x, l1.weight, l1.bias, l2.weight, l2.bias, norm.weight, norm.bias, drop)
 
 

@@ -8,10 +8,6 @@ static thread_local char g_last_err[256] = "";
 void set_last_cuda_error(cudaError_t e, const char *where) {
   snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
-// A launch attribute of the CALLING THREAD (like the current device / stream), not process state: two threads driving
-// two models or devices never see each other's epoch word.
-static thread_local const uint32_t *t_dropout_epoch = nullptr;
-const uint32_t *dropout_epoch_ptr() { return t_dropout_epoch; }
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -34,11 +30,6 @@ extern "C" {
 unsigned long long eda_launch_count(void) { return __atomic_load_n(&eda::g_launches, __ATOMIC_RELAXED); }
 
 int eda_version(void) { return 100; }
-
-int eda_dropout_set_epoch(const unsigned int *device_word) {
-  eda::t_dropout_epoch = reinterpret_cast<const uint32_t *>(device_word);
-  return EDA_OK;
-}
 
 const char *eda_error_string(int code) {
   switch (code) {

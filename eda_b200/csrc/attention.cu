@@ -371,7 +371,7 @@ extern "C" int eda_debug_timestamps_attn(long long *host_out, int n) {
 
 extern "C" int eda_attention_forward_lse(const float *q, const float *k, const float *v, int ldv,
                                          const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                         float scale, float dropout_p, unsigned int dropout_seed, float *ctx,
+                                         float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *ctx,
                                          float *lse, void *stream) {
   using namespace eda;
   if (B < 0 || Nq < 0 || Nk < 1 || H < 1 || D < 1) return EDA_ERR_INVALID_ARGUMENT;
@@ -387,7 +387,7 @@ extern "C" int eda_attention_forward_lse(const float *q, const float *k, const f
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.ldv = ldv; p.scale = scale;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
-  p.seed_epoch = dropout_epoch_ptr();
+  p.seed_epoch = reinterpret_cast<const uint32_t *>(dropout_epoch);
   cudaStream_t st = as_stream(stream);
   switch (D) {  // head dims the compiled template set covers (EDA: 288 / 8 = 36)
     case 32: return launch_attention<32>(p, B, st);
@@ -399,8 +399,8 @@ extern "C" int eda_attention_forward_lse(const float *q, const float *k, const f
 
 extern "C" int eda_attention_forward(const float *q, const float *k, const float *v, int ldv,
                                      const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                     float scale, float dropout_p, unsigned int dropout_seed, float *ctx,
+                                     float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *ctx,
                                      void *stream) {
-  return eda_attention_forward_lse(q, k, v, ldv, key_padding_mask, B, Nq, Nk, H, D, scale, dropout_p, dropout_seed, ctx,
-                                   nullptr, stream);
+  return eda_attention_forward_lse(q, k, v, ldv, key_padding_mask, B, Nq, Nk, H, D, scale, dropout_p, dropout_seed,
+                                   dropout_epoch, ctx, nullptr, stream);
 }

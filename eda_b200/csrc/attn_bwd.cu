@@ -311,7 +311,7 @@ int launch_attention_backward(const AttnBwdParams &p, int B, cudaStream_t st) {
 extern "C" int eda_attention_backward(const float *q, const float *k, const float *v, long long v_batch_stride,
                                       const float *vt, int ldv, const float *dctx, const float *ctx, const float *lse,
                                       const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                      float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
+                                      float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *delta, float *dq,
                                       float *dk, float *dv, void *stream) {
   using namespace eda;
   if (B < 0 || Nq < 0 || Nk < 1 || H < 1 || D < 1) return EDA_ERR_INVALID_ARGUMENT;
@@ -333,7 +333,7 @@ extern "C" int eda_attention_backward(const float *q, const float *k, const floa
   p.vt = vt; p.ldv = ldv;
   if (vt) p.v = vt;  // never dereferenced in that mode; keeps the pointer arithmetic defined
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
-  p.seed_epoch = dropout_epoch_ptr();
+  p.seed_epoch = reinterpret_cast<const uint32_t *>(dropout_epoch);
   cudaStream_t st = as_stream(stream);
   switch (D) {
     case 32: return launch_attention_backward<32>(p, B, st);

@@ -402,7 +402,7 @@ extern "C" int eda_attention_backward_tc(const float *q, const float *k, const f
                                          const float *kt, int ldk, const float *qt, const float *dctx_t, int ldq,
                                          const float *dctx, const float *ctx, const float *lse,
                                          const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                         float scale, float dropout_p, unsigned int dropout_seed, float *delta,
+                                         float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *delta,
                                          float *dq, float *dk, float *dv, void *stream) {
   using namespace eda;
   if (B < 0 || Nq < 0 || Nk < 1 || H < 1 || D < 1) return EDA_ERR_INVALID_ARGUMENT;
@@ -421,7 +421,7 @@ extern "C" int eda_attention_backward_tc(const float *q, const float *k, const f
   p.mask = key_padding_mask; p.delta = delta; p.dq = dq; p.dk = dk; p.dv = dv; p.v_batch_stride = v_batch_stride;
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.ldk = ldk; p.ldq = ldq; p.scale = scale;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
-  p.seed_epoch = dropout_epoch_ptr();
+  p.seed_epoch = reinterpret_cast<const uint32_t *>(dropout_epoch);
   cudaStream_t st = as_stream(stream);
   switch (D) {
     case 32: return launch_both<32>(p, B, st);

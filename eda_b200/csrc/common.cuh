@@ -143,9 +143,9 @@ inline uint32_t dropout_thresh(float p) {
   return t >= 16777216.0 ? 16777216u : (uint32_t)(t + 0.5);
 }
 
-// Optional device word added to every dropout seed at kernel run time (eda_dropout_set_epoch): lets a CUDA graph of a
-// training step draw fresh masks on every replay although the per-call seeds are frozen into the graph.
-const uint32_t *dropout_epoch_ptr();
+// Optional device word added to every dropout seed at kernel run time (the `dropout_epoch` argument of every
+// dropout-applying entry point): lets a CUDA graph of a training step draw fresh masks on every replay although the
+// per-call seeds are frozen into the graph.
 __device__ __forceinline__ uint32_t effective_seed(uint32_t seed, const uint32_t *epoch) {
   return epoch ? seed + __ldg(epoch) : seed;
 }

@@ -369,7 +369,7 @@ int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *st
 
 int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, float eps, long long rows, int N,
                            float *du, float *dproj, float *dgamma, float *dbeta, float dropout_p,
-                           unsigned int dropout_seed, void *stream) {
+                           unsigned int dropout_seed, const unsigned int *dropout_epoch, void *stream) {
   using namespace eda;
   if (rows < 0 || N < 4 || (N & 3) || N > kLnMaxN) return rows < 0 ? EDA_ERR_INVALID_ARGUMENT : EDA_ERR_UNSUPPORTED;
   if (rows == 0) return EDA_OK;
@@ -385,7 +385,7 @@ int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, 
   const uint32_t thresh = dropout_thresh(dropout_p);
   layernorm_backward_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(
       dy, u, gamma, eps, rows, N, du, thresh ? dproj : nullptr, dgamma, dbeta, thresh, dropout_seed,
-      1.0f / (1.0f - dropout_p), dropout_epoch_ptr());
+      1.0f / (1.0f - dropout_p), reinterpret_cast<const uint32_t *>(dropout_epoch));
   return check_launch("layernorm_backward_kernel");
 }
 

@@ -567,8 +567,8 @@ int eda_debug_timestamps(long long *host_out, int n) {
   return EDA_OK;
 }
 
-int eda_dropout_mask(unsigned int seed, float p, long long rows, int cols, unsigned int a_mul, unsigned int a_add,
-                     float *out, void *stream) {
+int eda_dropout_mask(unsigned int seed, const unsigned int *dropout_epoch, float p, long long rows, int cols,
+                     unsigned int a_mul, unsigned int a_add, float *out, void *stream) {
   using namespace eda;
   if (rows < 0 || cols < 0 || p < 0.f || p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   if (rows == 0 || cols == 0) return EDA_OK;
@@ -576,7 +576,7 @@ int eda_dropout_mask(unsigned int seed, float p, long long rows, int cols, unsig
   const long long total = rows * cols;
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   dropout_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(seed, dropout_thresh(p), rows, cols, a_mul, a_add, out,
-                                                           dropout_epoch_ptr());
+                                                           reinterpret_cast<const uint32_t *>(dropout_epoch));
   return check_launch("dropout_mask_kernel");
 }
 
@@ -620,7 +620,7 @@ int eda_linear_pack_batch(const void *descs_device, int count, int max_elements,
 }
 
 int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu, const float *ln_gamma,
-                       const float *ln_beta, float ln_eps, int layer_norm, float dropout_p, unsigned int dropout_seed,
+                       const float *ln_beta, float ln_eps, int layer_norm, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch,
                        void *stream) {
   using namespace eda;
   if (!probs || nprobs < 1 || nprobs > kMaxProbs) return EDA_ERR_INVALID_ARGUMENT;
@@ -649,7 +649,7 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   p.gamma = ln_gamma; p.beta = ln_beta; p.eps = ln_eps;
   if (dropout_p < 0.f || dropout_p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
   p.drop_thresh = dropout_thresh(dropout_p); p.drop_seed = dropout_seed; p.drop_scale = 1.0f / (1.0f - dropout_p);
-  p.seed_epoch = dropout_epoch_ptr();
+  p.seed_epoch = reinterpret_cast<const uint32_t *>(dropout_epoch);
   const int sms = sm_count();
   p.S = lin_splits(N, tiles, sms);
   p.NS = N / p.S;

@@ -80,7 +80,7 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep needs CUDA tensor inputs")
         # Dropout: the per-call seeds are drawn on the host while the step is recorded and are frozen into the graph.
         # A device "epoch" word that the graph itself increments at the start of every replay is added to every seed by
-        # the kernels (eda_dropout_set_epoch), so each replay draws fresh masks — the same ones in its forward and backward.
+        # the kernels (their `dropout_epoch` argument), so each replay draws fresh masks — the same ones in its forward and backward.
         has_dropout = False
         for m in model.modules():
             p = getattr(m, "p", None) if isinstance(m, torch.nn.Dropout) else getattr(m, "dropout", None) \
@@ -117,9 +117,13 @@ class GraphedTrainStep:
 
         registry.attach(model)  # per-model context: only THIS model's modules consult the registry
         registry.active = True
-        lib = _lib.load()
-        if epoch is not None:
-            lib.eda_dropout_set_epoch(ctypes.c_void_p(epoch.data_ptr()))
+        # the epoch word is a per-model context too: the modules of this model hand it to every dropout-applying kernel
+        # they launch (a plain argument of the C ABI: the library keeps no dropout state)
+        for m in model.modules():
+            if epoch is not None:
+                m.__dict__["_eda_dropout_epoch"] = epoch
+            else:
+                m.__dict__.pop("_eda_dropout_epoch", None)
         buffers = [(b, b.detach().clone()) for b in model.buffers()]
         try:
             side = torch.cuda.Stream(device=self.device)
@@ -140,7 +144,8 @@ class GraphedTrainStep:
                 flat_grads.zero()
         finally:
             registry.active = False  # eager calls on the model go back to the version-keyed caches
-            lib.eda_dropout_set_epoch(None)  # eager launches after this are unaffected; the graph keeps the baked pointer
+            for m in model.modules():  # eager launches after this are unaffected; the graph keeps the baked pointer
+                m.__dict__.pop("_eda_dropout_epoch", None)
 
     def __call__(self, *inputs):
         if len(inputs) != len(self.static_inputs):

@@ -56,13 +56,23 @@ def bn_scale_shift(dev, stats, count, bn, C, training_update, want_stats=False):
         bn.num_batches_tracked += 1
         if momentum is None:
             momentum = 1.0 / float(bn.num_batches_tracked.item())
-    if stats is not None:
-        red = syncbn.reducer_of(bn)
-        if red is not None:
-            red.all_reduce_sum_(stats)
-            count = red.total_count(count)
+    red = syncbn.reducer_of(bn) if stats is not None else None
+    mom = float(momentum if momentum is not None else 0.0)
+    if red is not None:
+        count = red.total_count(count)
+        if red.peer is not None and stats.is_cuda and 2 * C <= red.peer.max_elems:
+            # synchronised layer, NVLink peer path: exchange + ordered sum + finalisation in ONE launch
+            pr = red.peer
+            rc = lib.eda_bn_finalize_peer(_p(pr.ptrs), pr.world, pr.rank, pr.max_elems, _p(stats), float(count),
+                                          _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps), mom,
+                                          _p(bn.running_mean), _p(bn.running_var), 1 if training_update else 0, C,
+                                          _p(scale), _p(shift), _p(mean_invstd[0]) if want_stats else None,
+                                          _p(mean_invstd[1]) if want_stats else None, ops._stream(dev))
+            _chk(rc, "bn_finalize_peer")
+            return scale, shift, mean_invstd
+        red.all_reduce_sum_(stats)
     rc = lib.eda_bn_finalize(_p(stats), float(count), _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps),
-                             float(momentum if momentum is not None else 0.0), _p(bn.running_mean),
+                             mom, _p(bn.running_mean),
                              _p(bn.running_var), 1 if training_update else 0, C, _p(scale), _p(shift),
                              _p(mean_invstd[0]) if want_stats else None, _p(mean_invstd[1]) if want_stats else None,
                              ops._stream(dev))

@@ -259,17 +259,17 @@ typedef struct eda_linear_pack_desc {
 EDA_API int eda_linear_pack_batch(const void *descs_device, int count, int max_elements, void *stream);
 EDA_API int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu,
                                const float *ln_gamma, const float *ln_beta, float ln_eps, int layer_norm,
-                               float dropout_p, unsigned int dropout_seed, void *stream);
+                               float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, void *stream);
 /* Development aid: clock64() phase stamps of CTA 0 of the most recent eda_linear_forward launch (synchronises). */
 EDA_API int eda_debug_timestamps(long long *host_out, int n);
 EDA_API int eda_debug_timestamps_attn(long long *host_out, int n); /* same, attention kernel, key block 1 */
 EDA_API int eda_attention_forward(const float *q, const float *k, const float *vt, int ldv,
                                   const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                  float scale, float dropout_p, unsigned int dropout_seed, float *ctx, void *stream);
+                                  float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *ctx, void *stream);
 /* Training variant: also writes lse (B, H, Nq), the log-sum-exp of every query's masked, scaled scores (NULL = skip). */
 EDA_API int eda_attention_forward_lse(const float *q, const float *k, const float *vt, int ldv,
                                       const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                      float scale, float dropout_p, unsigned int dropout_seed, float *ctx, float *lse,
+                                      float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *ctx, float *lse,
                                       void *stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -305,7 +305,7 @@ typedef struct eda_wgrad_problem {
 EDA_API int eda_attention_backward(const float *q, const float *k, const float *v, long long v_batch_stride,
                                    const float *vt, int ldv, const float *dctx, const float *ctx, const float *lse,
                                    const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                   float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
+                                   float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *delta, float *dq,
                                    float *dk, float *dv, void *stream);
 /* Same result on the tcgen05 tensor cores (TMEM-resident score tiles; csrc/attn_bwd_tc.cu).  Additionally takes
  * channel-major copies kt (B, H*D, ldk) of k and qt, dctx_t (B, H*D, ldq) of q and dctx (ld >= N, multiple of 4; padding
@@ -315,7 +315,7 @@ EDA_API int eda_attention_backward_tc(const float *q, const float *k, const floa
                                       const float *kt, int ldk, const float *qt, const float *dctx_t, int ldq,
                                       const float *dctx, const float *ctx, const float *lse,
                                       const unsigned char *key_padding_mask, int B, int Nq, int Nk, int H, int D,
-                                      float scale, float dropout_p, unsigned int dropout_seed, float *delta, float *dq,
+                                      float scale, float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, float *delta, float *dq,
                                       float *dk, float *dv, void *stream);
 EDA_API int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *stream);
 /* Same accumulation for a tiny contraction width the tensor-core kernel does not take (K <= 8, any alignment): the 3- /
@@ -324,7 +324,7 @@ EDA_API int eda_wgrad_small(const float *dy, int ldy, const float *x, int ldx, l
                             int ldw, float *db, void *stream);
 EDA_API int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, float eps, long long rows, int N,
                                    float *du, float *dproj, float *dgamma, float *dbeta, float dropout_p,
-                                   unsigned int dropout_seed, void *stream);
+                                   unsigned int dropout_seed, const unsigned int *dropout_epoch, void *stream);
 EDA_API int eda_relu_backward(const float *dy, const float *y, float scale, long long n, float *out, void *stream);
 /* Train-mode dropout (nn.Dropout after attention / FFN blocks, attention-probability dropout of
  * nn.MultiheadAttention(dropout=p), encoder_decoder_layers.py:47-59,94,106,118 ...): dropout_p > 0 makes
@@ -335,16 +335,14 @@ EDA_API int eda_relu_backward(const float *dy, const float *y, float scale, long
  * keep-mask (1.0 / 0.0) a forward call applied, out[a * cols + b] for a < rows, b < cols, hashing
  * (a * a_mul + a_add, b):  linear problem i of a launch: a_mul = 3, a_add = i, rows = R, cols = N;
  * attention: a_mul = 1, a_add = 0, rows = B*H*Nq (row (b*H + h)*Nq + q), cols = Nk. */
-EDA_API int eda_dropout_mask(unsigned int seed, float p, long long rows, int cols, unsigned int a_mul,
-                             unsigned int a_add, float *out, void *stream);
-/* Optional dropout epoch: a device word whose value every dropout-applying kernel of this library (forward and
- * backward) adds to its dropout_seed when it RUNS.  A CUDA graph of a training step freezes the host-drawn seeds; with
- * an epoch word that a captured device op increments once per step, every replay still draws fresh masks, identical in
- * that step's forward and backward.  A launch attribute of the CALLING THREAD (thread-local, like the current device):
- * it applies to kernels this thread launches after the call; NULL = off (default).  Library state is therefore limited
- * to per-thread values (this pointer, the last error string), a launch counter, and per-device caches of function
- * attributes (thread-safe).  The word must stay allocated while kernels launched under it run. */
-EDA_API int eda_dropout_set_epoch(const unsigned int *device_word);
+EDA_API int eda_dropout_mask(unsigned int seed, const unsigned int *dropout_epoch, float p, long long rows, int cols,
+                             unsigned int a_mul, unsigned int a_add, float *out, void *stream);
+/* Dropout epoch: every dropout-applying entry point (forward and backward) takes `dropout_epoch`, an optional device
+ * word whose value the kernel adds to dropout_seed when it RUNS (NULL = off).  A CUDA graph of a training step freezes
+ * the host-drawn seeds; with an epoch word that a captured device op increments once per step, every replay still draws
+ * fresh masks, identical in that step's forward and backward.  It is a plain per-call argument: the library keeps no
+ * dropout state (its only state is the per-thread last-error string, a launch counter and thread-safe per-device
+ * caches of kernel attributes).  The word must stay allocated while kernels launched with it run. */
 
 /* ---------------------------------------------------------------------------------------
  * Backward pass of the fused set-abstraction stage (eda_sa_mlp_forward).  In the reference: autograd through
@@ -402,6 +400,29 @@ EDA_API int eda_sa_pool_backward_stats(const float *z3, const int *amax, const f
                                        void *stream);
 EDA_API int eda_sa_scatter_rows(const float *dx0, const int *idx, int B, int N, int M, int S, int C, int K0pad,
                                 float *dfeat, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Synchronised BatchNorm statistics over the GPUs of one node through NVLink peer memory (the reference converts every
+ * BatchNorm to nn.SyncBatchNorm when more than one GPU is used, main_utils.py:335-338; torch's implementation issues an
+ * NCCL all-gather per layer in the forward and an all-reduce per layer in the backward pass).
+ *
+ * peer_buffers_dev: DEVICE array of `world` pointers, entry r = rank r's exchange buffer as mapped into THIS process
+ * (symmetric memory / CUDA IPC; the host side obtains them from torch.distributed._symmetric_memory); every buffer holds
+ * eda_peer_buffer_bytes(world, max_elems) bytes and must be zero-filled once before first use.  All ranks must issue the
+ * same sequence of peer calls (like any collective).  world <= 16.
+ *   eda_peer_allreduce      data[0:n] <- sum over ranks, in place (fp32 when is_f64 == 0, else fp64; accumulation in
+ *                           fp64, ranks added in rank order: bit-identical results on every rank).  One single-CTA launch:
+ *                           remote stores of the local vector into every peer, release/acquire flags, ordered local sum.
+ *   eda_bn_finalize_peer    eda_bn_finalize with that exchange fused in front: stats = THIS rank's [sum z, sum z^2],
+ *                           count = rows of ALL ranks.
+ * A peer that never arrives turns into a non-zero error word in the buffer (bytes 4..7) after ~2 s instead of a hang. */
+EDA_API size_t eda_peer_buffer_bytes(int world, int max_elems);
+EDA_API int eda_peer_allreduce(void *const *peer_buffers_dev, int world, int rank, int max_elems, void *data, int n,
+                               int is_f64, void *stream);
+EDA_API int eda_bn_finalize_peer(void *const *peer_buffers_dev, int world, int rank, int max_elems, const double *stats,
+                                 double count, const float *gamma, const float *beta, float eps, float momentum,
+                                 float *running_mean, float *running_var, int update_running, int C, float *scale,
+                                 float *shift, float *save_mean, float *save_invstd, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05/TMEM building blocks the fused kernels rely on (no reference

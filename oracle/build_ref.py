@@ -13,8 +13,9 @@ flags it passes (-O2 and the include dir, pointnet2/setup.py:24-27).
 The reference's PYTHON side of the path (pointnet2/*.py, models/{bdetr,modules,backbone_module,
 encoder_decoder_layers}.py) is needed on the GPU box too (full-model parity tests, the R-GPU baseline leg of bench.py),
 and /root/reference does not exist there: `build_pyref` byte-compiles those files where they lie into
-oracle/_ref/pyref/{pointnet2,models}/*.pyc (sourceless bytecode, git-ignored, travels like the .so).  No reference
-source text enters the repository.
+oracle/_ref/pyref/{pointnet2,models}/*.pyc.bin (sourceless bytecode, git-ignored, travels like the .so; the suffix is
+not ".pyc" because the gpurun snapshot drops *.pyc files — oracle/ref_model.py materialises them as .pyc in a temporary
+directory before importing).  No reference source text enters the repository.
 
 Only tests/ and bench.py (R-GPU baseline leg / CPU reference arm) load the results.
 """
@@ -96,7 +97,7 @@ def build_pyref(force=False):
         os.makedirs(os.path.join(PYREF_DIR, sub), exist_ok=True)
         for name in names:
             src = os.path.join(REF_ROOT, sub, name)
-            dst = os.path.join(PYREF_DIR, sub, name + "c")
+            dst = os.path.join(PYREF_DIR, sub, name + "c.bin")
             if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
                 # dfile: tracebacks name the reference file; UNCHECKED_HASH: valid without the source next to it
                 py_compile.compile(src, cfile=dst, dfile=f"<reference>/{sub}/{name}", doraise=True,

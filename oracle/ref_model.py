@@ -33,11 +33,34 @@ _NAMES = ["pointnet2", "pointnet2._ext", "pointnet2.pointnet2_utils", "pointnet2
 _cache = {}
 
 
+_materialised = None
+
+
 def ref_dir():
+    """Directory holding models/ and pointnet2/ of the reference: the checkout itself in the build container, else a
+    temporary directory into which the shipped bytecode (oracle/_ref/pyref/*/*.pyc.bin) is copied as importable .pyc."""
+    global _materialised
     if os.path.isdir("/root/reference/models"):
         return "/root/reference"
+    if _materialised is not None:
+        return _materialised
     d = os.path.join(_HERE, "_ref", "pyref")
-    return d if os.path.isdir(os.path.join(d, "models")) else None
+    if not os.path.isdir(os.path.join(d, "models")):
+        return None
+    import glob
+    import shutil
+
+    tmp = tempfile.mkdtemp(prefix="eda_pyref_")
+    n = 0
+    for sub in ("models", "pointnet2"):
+        os.makedirs(os.path.join(tmp, sub))
+        for src in glob.glob(os.path.join(d, sub, "*.pyc.bin")):
+            shutil.copyfile(src, os.path.join(tmp, sub, os.path.basename(src)[:-4]))
+            n += 1
+    if n == 0:
+        return None
+    _materialised = tmp
+    return tmp
 
 
 def oracle_ext():
