@@ -41,7 +41,7 @@ constexpr int kThreads = 576;   // + warp 16 MMA issue, warp 17 weight producer
 constexpr int kStages = 4;  // ring slots allocated at most; p.nstages (3 or 4) are used
 constexpr int kKBlock = 32;                      // 32 fp32 = one 128-byte swizzle row
 constexpr int kTileBytes = kRows * kKBlock * 4;  // 16 KB
-constexpr int kABytes = 2 * kTileBytes;          // A tile + P ("+ pos") tile
+constexpr int kABytes = kTileBytes;              // A tile ("+ pos" is added from global memory during the fix-up pass)
 constexpr int kMaxN = 320;
 constexpr int kMaxProbs = 3;
 constexpr int kPrefetch = 1;  // blocks the staging warps run ahead (the slot it needs was released a whole
@@ -230,7 +230,6 @@ linear_kernel(const LinParams p) {
         if (lane == 0) mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);  // the MMAs that read this slot are done
         __syncwarp();
         unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
-        unsigned char *sP = sA + kTileBytes;
         const int k = kb * kKBlock + cj * 4;
 #pragma unroll
         for (int i = 0; i < kOwn; ++i) {
@@ -239,7 +238,6 @@ linear_kernel(const LinParams p) {
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cj ^ (r & 7)) << 4);
           const size_t g = (size_t)(row0 + r) * K + k;
           umma::cp_async16(sA + off, in ? pr.x + g : pr.x, in ? 16u : 0u);
-          if (pr.pos) umma::cp_async16(sP + off, in ? pr.pos + g : pr.pos, in ? 16u : 0u);
         }
       }
       umma::cp_async_commit();
@@ -249,11 +247,22 @@ linear_kernel(const LinParams p) {
     for (int kb = 0; kb < nkb; ++kb) {
       const int slot = kb % p.nstages;
       issue_block(kb + p.prefetch);
+      // "+ pos" for block kb comes straight from global memory (the same 16-byte chunks this thread copied of x): the
+      // loads are issued before the wait below, so their latency hides behind the cp.async of x
+      float4 pq[kOwn];
+      if (vec && pr.pos) {
+        const int k = kb * kKBlock + cj * 4;
+#pragma unroll
+        for (int i = 0; i < kOwn; ++i) {
+          const int r = i * kRowStep + cr0;
+          const bool in = (row0 + r < pr.rows) && k < K;
+          pq[i] = in ? __ldg(reinterpret_cast<const float4 *>(pr.pos + (size_t)(row0 + r) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       if (p.prefetch == 2) umma::cp_async_wait<2>(); else umma::cp_async_wait<1>();  // block kb has landed (own copies)
       unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
       if (vec) {
         // the chunks this thread copied: "+ pos", round to tf32 (round-to-nearest), in place
-        const unsigned char *sP = sA + kTileBytes;
         float4 v[kOwn];
 #pragma unroll
         for (int i = 0; i < kOwn; ++i) {
@@ -261,8 +270,7 @@ linear_kernel(const LinParams p) {
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cj ^ (r & 7)) << 4);
           v[i] = *reinterpret_cast<const float4 *>(sA + off);
           if (pr.pos) {
-            const float4 q = *reinterpret_cast<const float4 *>(sP + off);
-            v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+            v[i].x += pq[i].x; v[i].y += pq[i].y; v[i].z += pq[i].z; v[i].w += pq[i].w;
           }
         }
 #pragma unroll
@@ -655,9 +663,11 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   p.NS = N / p.S;
   const int NS = p.NS;
   p.tmem_cols = NS <= 32 ? 32u : NS <= 64 ? 64u : NS <= 128 ? 128u : NS <= 256 ? 256u : 512u;
-  // stage = A tile + P tile + W block, padded to 1024 bytes (SWIZZLE_128B atoms must stay 1024-aligned)
+  // stage = A tile + W block, padded to 1024 bytes (SWIZZLE_128B atoms must stay 1024-aligned).  Four stages (the
+  // staging warps then run two K blocks ahead of the MMAs) whenever they fit next to the ~5 KB of static shared memory:
+  // N = 288 -> 4 x 52 KB = 208 KB
   p.stage_bytes = (uint32_t)((kABytes + kKBlock * NS * 4 + 1023) & ~1023);
-  p.nstages = (size_t)4 * p.stage_bytes <= 200 * 1024 ? 4 : 3;
+  p.nstages = (size_t)4 * p.stage_bytes <= 216 * 1024 ? 4 : 3;
   p.prefetch = p.nstages - 2;
   size_t smem = (size_t)p.nstages * p.stage_bytes;
   const size_t out_tile = (size_t)kRows * (NS + 4) * sizeof(float);
