@@ -112,7 +112,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // Development aid: phase timestamps (clock64) of CTA 0 of the most recent launch (eda_debug_timestamps):
 // [0] entry, [1] setup done, [2] staging loop done, [3] accumulator complete, [16] epilogue done, [17] exit.
-__device__ long long g_lin_ts[32];
+__device__ long long g_lin_ts[128];
 #define LIN_TS(i) do { if (blockIdx.x == 0 && tid == 0) g_lin_ts[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -193,7 +193,9 @@ linear_kernel(const LinParams p) {
         const int kcnt = min(kKBlock, p.Kpad - kb * kKBlock);
         const uint32_t par = (kb / p.nstages) & 1;
         mbar_wait(&a_ready[slot], par);
+        if (blockIdx.x == 0 && kb < 10) g_lin_ts[32 + 3 * kb] = clock64();      // [32 + 3 kb] A block kb staged
         mbar_wait(&full_w[slot], par);
+        if (blockIdx.x == 0 && kb < 10) g_lin_ts[33 + 3 * kb] = clock64();      // [33 + 3 kb] W block kb landed
         umma::fence_after_thread_sync();
         const uint32_t abase = smem_u32(smem_raw + (size_t)slot * p.stage_bytes);
         const uint32_t wbase = abase + kABytes;
@@ -210,6 +212,7 @@ linear_kernel(const LinParams p) {
           }
         }
         umma::mma_commit(&empty[slot]);
+        if (blockIdx.x == 0 && kb < 10) g_lin_ts[34 + 3 * kb] = clock64();      // [34 + 3 kb] MMAs of block kb issued
         if (kb == nkb - 1) umma::mma_commit(&mma_done);
       }
     }
@@ -246,7 +249,10 @@ linear_kernel(const LinParams p) {
 
     for (int kb = 0; kb < nkb; ++kb) {
       const int slot = kb % p.nstages;
+#define STG_TS(j) do { if (blockIdx.x == 0 && tid == 0 && kb < 9) g_lin_ts[64 + 6 * kb + (j)] = clock64(); } while (0)
+      STG_TS(0);
       issue_block(kb + p.prefetch);
+      STG_TS(1);
       // "+ pos" for block kb comes straight from global memory (the same 16-byte chunks this thread copied of x): the
       // loads are issued before the wait below, so their latency hides behind the cp.async of x
       float4 pq[kOwn];
@@ -260,6 +266,7 @@ linear_kernel(const LinParams p) {
         }
       }
       if (p.prefetch == 2) umma::cp_async_wait<2>(); else umma::cp_async_wait<1>();  // block kb has landed (own copies)
+      STG_TS(2);
       unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
       if (vec) {
         // the chunks this thread copied: "+ pos", round to tf32 (round-to-nearest), in place
@@ -299,9 +306,12 @@ linear_kernel(const LinParams p) {
               make_float4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
         }
       }
+      STG_TS(3);
       umma::fence_proxy_async_smem();
+      STG_TS(4);
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_ready[slot]);
+      STG_TS(5);
     }
     LIN_TS(2);
     mbar_wait(&mma_done, 0);
@@ -570,7 +580,7 @@ inline bool lin_supported(int N, int K) { return N >= 16 && N <= kMaxN && (N & 1
 extern "C" {
 
 int eda_debug_timestamps(long long *host_out, int n) {
-  if (!host_out || n < 0 || n > 32) return EDA_ERR_INVALID_ARGUMENT;
+  if (!host_out || n < 0 || n > 128) return EDA_ERR_INVALID_ARGUMENT;
   EDA_CUDA_TRY(cudaMemcpyFromSymbol(host_out, eda::g_lin_ts, sizeof(long long) * n), "debug timestamps");
   return EDA_OK;
 }
