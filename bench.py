@@ -339,8 +339,18 @@ def gpu_arm(args):
                                         "sample": "failed: " + repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # CUDA graphs that captured NCCL collectives (synchronised BatchNorm, overlapped gradient all-reduce) must be
+        # released before the communicator goes away; the process then leaves without the NCCL teardown, which can
+        # block on captured work
+        st.clear()
+        del step
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def extra_legs(args, dev, world, rank, inputs, host, step_ms):

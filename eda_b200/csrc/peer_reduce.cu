@@ -16,7 +16,8 @@
 //        result is bit-identical everywhere — and write it over the input.
 // Double buffering by parity is enough: a rank can enter epoch e+2 (same parity as e) only after it has seen every
 // peer's flag for e+1, which a peer raises after its epoch-e kernel finished reading (stream order).
-// A bounded spin (about two seconds) turns a missing peer into an error word instead of a hung GPU.
+// A bounded wait (two seconds on the global timer, then sticky) turns a missing peer into an error word instead of
+// a hung GPU.
 //
 // eda_bn_finalize_peer fuses this exchange into the BatchNorm finalisation (sum -> scale / shift / running statistics):
 // one launch where the library path needs a collective plus a kernel.
@@ -36,6 +37,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ double ld_volatile_f64(const double *p) {
   double v;
@@ -72,11 +78,15 @@ __device__ bool peer_exchange_sum(char *const *__restrict__ bufs, int world, int
     unsigned *flag_there = reinterpret_cast<unsigned *>(bufs[r] + 64) + parity * kMaxWorld + rank;
     st_release_sys(flag_there, epoch);
     const unsigned *flag_here = reinterpret_cast<const unsigned *>(mine + 64) + parity * kMaxWorld + r;
-    long long spins = 0;
+    volatile unsigned *err = reinterpret_cast<volatile unsigned *>(mine) + 1;
+    const unsigned long long t0 = global_ns();
+    // the error word is sticky: once a peer has failed to arrive, later exchanges do not wait again (a broken run
+    // finishes with wrong statistics and a non-zero error word instead of stalling for a second per layer)
     while (ld_acquire_sys(flag_here) != epoch) {
-      __nanosleep(64);
-      if (++spins > (1LL << 24)) {  // ~2 s: a peer never arrived
-        reinterpret_cast<unsigned *>(mine)[1] = epoch;
+      if (*err != 0u) { s_ok = 0; break; }
+      __nanosleep(32);
+      if (global_ns() - t0 > 2000000000ull) {  // 2 s: a peer never arrived
+        *err = epoch;
         s_ok = 0;
         break;
       }

@@ -25,7 +25,15 @@ def rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
+def log(msg):
+    print(f"[mpcheck rank {os.environ.get('RANK')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
+    import faulthandler
+
+    # a stuck collective must become a traceback and a non-zero exit, never a hung GPU box
+    faulthandler.dump_traceback_later(int(os.environ.get("EDA_MPCHECK_TIMEOUT", "150")), exit=True)
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -61,6 +69,7 @@ def main():
         dist.all_reduce(gsum, op=dist.ReduceOp.MAX)
         res[tag + "_grads_identical_across_ranks"] = bool(torch.equal(gsum, fg.flat))
 
+    log("single-process reference done")
     # ---- 1. eager, NCCL reducer for the statistics, one flat all-reduce ----
     m = ddp.convert_sync_batchnorm(fresh())
     fg = ddp.FlatGradients(m)
@@ -70,9 +79,11 @@ def main():
     fg.all_reduce_mean()
     check("eager_nccl", m, fg, out, loss.item())
 
+    log("eager nccl done: " + json.dumps(res))
     # ---- 2. eager, peer-memory reducer, overlapped bucketed all-reduce ----
     peer_ok = syncbn.enable_peer_reduce(dev)
     res["peer_reduce_available"] = bool(peer_ok)
+    log(f"peer reduce available: {peer_ok}")
     if not peer_ok:
         res["peer_error"] = getattr(syncbn.default_reducer(), "peer_error", None)
     m = ddp.convert_sync_batchnorm(fresh())
@@ -88,10 +99,12 @@ def main():
     if peer_ok:
         res["peer_error_word"] = syncbn.default_reducer().peer.error_word()
 
+    log("eager peer + overlap done: " + json.dumps(res))
     # ---- 3. the same as ONE CUDA graph (statistics exchange and gradient all-reduce captured) ----
     m = ddp.convert_sync_batchnorm(fresh())
     fg = ddp.FlatGradients(m).enable_overlap()
     step = GraphedTrainStep(m, hotpath.quadratic_loss, mine, fg)
+    log("graph captured")
     loss = step(*mine)
     torch.cuda.synchronize()
     with torch.no_grad():
@@ -129,9 +142,17 @@ def main():
     if rank == 0:
         res["all_ranks_ok"] = bool(flag.item())
         print("MPCHECK " + json.dumps(res), flush=True)
+    log("done")
+    ok_all = bool(flag.item())
+    # CUDA graphs that captured NCCL collectives must be gone before the communicator is torn down
+    del step
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() else 1)
+    faulthandler.cancel_dump_traceback_later()
+    sys.stdout.flush()
+    os._exit(0 if ok_all else 1)  # skip the communicator teardown: nothing to save, and it may wait on captured work
 
 
 if __name__ == "__main__":
