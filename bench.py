@@ -200,11 +200,17 @@ def build_train_step(dev, world, rank, dropout, inputs):
     torch.manual_seed(0)
     model = hotpath.HotPath(dropout=dropout).to(dev).train()
     ddp.broadcast_parameters(model)
-    sync_bn = False
-    if world > 1 and hasattr(ddp, "convert_sync_batchnorm"):
+    sync_bn, peer = False, False
+    if world > 1:
+        from eda_b200 import syncbn
+
         ddp.convert_sync_batchnorm(model)  # what main_utils.py:335-338 does when more than one GPU is used
         sync_bn = True
+        # statistics exchange over NVLink peer memory, fused with the BatchNorm finalisation (falls back to NCCL)
+        peer = os.environ.get("EDA_PEER_REDUCE", "1") != "0" and syncbn.enable_peer_reduce(dev)
     fg = ddp.FlatGradients(model)
+    if world > 1 and os.environ.get("EDA_OVERLAP_ALLREDUCE", "1") != "0":
+        fg.enable_overlap()  # bucketed all-reduce issued during the backward pass (captured inside the graph)
     l0 = lib.eda_launch_count()
     warm = 3
     gstep = GraphedTrainStep(model, hotpath.quadratic_loss, inputs, fg, warmup=warm)
@@ -218,7 +224,7 @@ def build_train_step(dev, world, rank, dropout, inputs):
         return loss
 
     return step, dict(model=model, fg=fg, gstep=gstep, kernels_per_step=int(kernels_per_step), sync_bn=sync_bn,
-                      overlapped=overlapped)
+                      overlapped=overlapped, peer=bool(peer))
 
 
 def gpu_arm(args):
@@ -232,6 +238,11 @@ def gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    # the contract is ONE JSON line on stdout: libraries (NCCL's version banner, symmetric-memory setup) write to fd 1 at
+    # will, so fd 1 is pointed at stderr for the duration of the run and the line goes out through a saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -315,6 +326,9 @@ def gpu_arm(args):
                                "); NCCL all-reduce of the flat fp32 gradient bucket after it"),
                       "kernels_per_step": st["kernels_per_step"], "gradient_floats": int(st["fg"].flat.numel()),
                       "sync_batchnorm": st["sync_bn"], "loss": loss_value,
+                      "batchnorm_statistics_exchange": ("NVLink peer-memory kernel fused with the finalisation" if st["peer"]
+                                                        else "NCCL all-reduce") if st["sync_bn"] else None,
+                      "gradient_regions": st["fg"].regions,
                       "index_paths": "fp32, bit-exact", "contractions": "tcgen05 kind::tf32, fp32 accumulate"},
     }
     if True:
@@ -337,7 +351,8 @@ def gpu_arm(args):
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: " + repr(e)[:200]}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # CUDA graphs that captured NCCL collectives (synchronised BatchNorm, overlapped gradient all-reduce) must be
         # released before the communicator goes away; the process then leaves without the NCCL teardown, which can

@@ -338,8 +338,24 @@ def _wgrad_side(dev):
     return st
 
 
+_aux_pending = {}  # device key -> auxiliary streams (the encoder's language-branch stream) used since the last join
+
+
+def note_aux_stream(dev, stream):
+    """A forward pass put work on `stream` (encoder_decoder_layers.BRANCH_STREAMS): its backward kernels will run there
+    too, and whoever joins the gradient streams must wait for it as well."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    _aux_pending.setdefault(key, set()).add(stream)
+
+
+def _capturing(stream):
+    with torch.cuda.stream(stream):
+        return torch.cuda.is_current_stream_capturing()
+
+
 def join_wgrad():
-    """The current stream waits for every weight-gradient kernel issued on the side streams so far."""
+    """The current stream waits for every weight-gradient kernel issued on the side streams so far, and for the
+    auxiliary branch streams that carried part of the backward pass."""
     global _join_queued
     _join_queued = False
     # only streams with un-joined work: waiting on an idle side stream would, during CUDA-graph capture, make the
@@ -347,6 +363,14 @@ def join_wgrad():
     for key in list(_wgrad_pending):
         torch.cuda.current_stream(torch.device("cuda", key)).wait_stream(_wgrad_streams[key])
     _wgrad_pending.clear()
+    for key, streams in list(_aux_pending.items()):
+        cur = torch.cuda.current_stream(torch.device("cuda", key))
+        cap = torch.cuda.is_current_stream_capturing()
+        for st in streams:
+            if cap and not _capturing(st):
+                continue  # used by an earlier, un-captured forward: nothing of this capture runs there
+            cur.wait_stream(st)
+    _aux_pending.clear()
 
 
 def mark_side_pending(dev):

@@ -145,6 +145,7 @@ class FlatGradients:
         self._works = []
         self._flush_queued = False
         self._expected = {}   # parameter index -> fused backward contributions still to come (counted in the forward)
+        self._streams = [set() for _ in self.regions]  # streams on which a region's gradient kernels were queued
 
     def _mark(self, i):
         """Parameter i's gradient has been written (its kernels are queued on the current or the side stream)."""
@@ -153,6 +154,8 @@ class FlatGradients:
         self._done[i] = True
         r = self._region_of[i]
         self._pending[r] -= 1
+        if self._comm is not None:
+            self._streams[r].add(torch.cuda.current_stream(self.flat.device))
         if not self._flush_queued:
             try:  # regions still open at the end of this backward pass are flushed there
                 torch.autograd.Variable._execution_engine.queue_callback(self._flush)
@@ -190,13 +193,18 @@ class FlatGradients:
             view.mul_(1.0 / world)
             return
         dev = self.flat.device
-        cur = torch.cuda.current_stream(dev)
-        self._comm.wait_stream(cur)
-        if self.fused:  # weight-gradient kernels of this region may still be running on the side stream
+        # the collective must follow every stream that carries gradient kernels of this region: the streams the
+        # completion reports came from (main stream, the encoder's language-branch stream), the current one, and the
+        # side stream of the fused weight-gradient kernels
+        waits = set(self._streams[r])
+        waits.add(torch.cuda.current_stream(dev))
+        if self.fused:
             from . import attn_ops
             side = attn_ops._wgrad_streams.get(dev.index if dev.index is not None else torch.cuda.current_device())
             if side is not None:
-                self._comm.wait_stream(side)
+                waits.add(side)
+        for st in waits:
+            self._comm.wait_stream(st)
         with torch.cuda.stream(self._comm):
             if self._avg:
                 work = dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self._group, async_op=True)

@@ -24,6 +24,26 @@ def _get_clones(module, N):
     return nn.ModuleList([deepcopy(module) for _ in range(N)])
 
 
+# The language branch of an encoder layer (text self-attention, text <- vision cross-attention, its FFN: ~8 launches of
+# 640-row problems that occupy a handful of SMs) is independent of the vision branch between the two points where the
+# modalities exchange keys / values.  It runs on a second CUDA stream, so these latency-bound launches execute in the
+# shadow of the vision branch instead of in front of it; autograd replays the same stream assignment in the backward
+# pass, and inside a captured CUDA graph the two streams become parallel branches of the graph.  Results are identical
+# (same kernels, same order within each branch).  BRANCH_STREAMS = False restores the single-stream order.
+BRANCH_STREAMS = True
+_branch_streams = {}
+
+
+def _text_stream(device):
+    import torch
+
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _branch_streams.get(key)
+    if st is None:
+        st = _branch_streams[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class PositionEmbeddingLearned(nn.Module):
     """Absolute pos embedding, learned: Conv1d(C,F,1) -> BatchNorm1d -> ReLU -> Conv1d(F,F,1)."""
 
@@ -153,6 +173,9 @@ class BiEncoderLayer(nn.Module):
     def forward(self, vis_feats, pos_feats, padding_mask, text_feats, text_padding_mask, end_points={},
                 detected_feats=None, detected_mask=None):
         """Forward pass, feats (B, N, F), masks (B, N), diff N for V/L."""
+        if BRANCH_STREAMS and vis_feats.is_cuda:
+            return self._forward_two_streams(vis_feats, pos_feats, padding_mask, text_feats, text_padding_mask,
+                                             detected_feats, detected_mask)
         if self.self_attention_visual is not None:
             vis_feats = self.self_attention_visual.forward_rows(vis_feats, pos_feats, padding_mask)
         if self.self_attention_lang is not None:
@@ -160,6 +183,46 @@ class BiEncoderLayer(nn.Module):
         return self.cross_layer(vis_feats=vis_feats, vis_key_padding_mask=padding_mask, text_feats=text_feats,
                                 text_key_padding_mask=text_padding_mask, pos_feats=pos_feats,
                                 detected_feats=detected_feats, detected_mask=detected_mask)
+
+    def _forward_two_streams(self, vis_feats, pos_feats, padding_mask, text_feats, text_padding_mask, detected_feats,
+                             detected_mask):
+        """Same computation as `forward`, language branch on the side stream (see BRANCH_STREAMS)."""
+        import torch
+
+        dev = vis_feats.device
+        main, side = torch.cuda.current_stream(dev), _text_stream(dev)
+        if torch.is_grad_enabled():
+            ops.note_aux_stream(dev, side)  # the backward pass will use it too: joined with the gradient streams
+        cl = self.cross_layer
+        side.wait_stream(main)  # everything produced so far (inputs of this layer) is visible to the side stream
+        with torch.cuda.stream(side):
+            if self.self_attention_lang is not None:
+                text_sa = self.self_attention_lang.forward_rows(text_feats, text_padding_mask)
+            else:
+                text_sa = text_feats
+        vis_sa = vis_feats
+        if self.self_attention_visual is not None:
+            vis_sa = self.self_attention_visual.forward_rows(vis_feats, pos_feats, padding_mask)
+        # exchange point: each branch needs the other's self-attended features as keys / values
+        side.wait_stream(main)
+        main.wait_stream(side)
+        text_sa.record_stream(main)
+        vis_sa.record_stream(side)
+        with torch.cuda.stream(side):
+            text_new = ops.mha_block(cl.cross_lv, text_sa, vis_sa, vis_sa, key_padding_mask=padding_mask,
+                                     residual=text_sa, norm=cl.norm_lv, out_dropout=cl.dropout_lv)
+            text_new = ops.ffn_block(cl.ffn_lv, text_new, cl.norm_lv2)
+        vis_new = ops.mha_block(cl.cross_vl, vis_sa, text_sa, text_sa, q_pos=pos_feats,
+                                key_padding_mask=text_padding_mask, residual=vis_sa, norm=cl.norm_vl,
+                                out_dropout=cl.dropout_vl)
+        if detected_feats is not None and cl.use_butd_enc_attn:
+            vis_new = ops.mha_block(cl.cross_d, vis_new, detected_feats, detected_feats, key_padding_mask=detected_mask,
+                                    residual=vis_new, norm=cl.norm_d, out_dropout=cl.dropout_d)
+        vis_new = ops.ffn_block(cl.ffn_vl, vis_new, cl.norm_vl2)
+        # join: the caller (next layer, decoder, loss) may consume both on the current stream
+        main.wait_stream(side)
+        text_new.record_stream(main)
+        return vis_new, text_new
 
 
 class BiEncoder(nn.Module):
