@@ -93,6 +93,7 @@ PROTOTYPES = {
     "eda_bn_finalize_peer": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, ctypes.c_double, _vp, _vp, _c_float, _c_float,
                                       _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "eda_selftest_umma": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "eda_selftest_umma_rate": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "eda_selftest_umma_probe": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
 }
 

@@ -29,6 +29,7 @@
 // each other's TMEM latency: bias, ReLU, dropout, rounding.  Phase 2, warp = row: residual read with coalesced
 // 16-byte loads, LayerNorm statistics by warp shuffle, coalesced 16-byte stores.
 #include <stdlib.h>
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "umma.cuh"
 
 namespace eda {
@@ -48,6 +49,7 @@ constexpr int kPrefetch = 1;  // blocks the staging warps run ahead (the slot it
                               // iteration ago, so staging never waits for the MMAs it has just enabled)
 
 struct LinProblem {
+  int tma;  // A tiles arrive by 2-D TMA (tensor map LinParams::tmap[problem]) instead of per-thread cp.async
   const float *x, *pos, *w, *bias, *residual;
   float *y;
   float *pre;  // optional (rows, N): the LayerNorm INPUT (residual + product), saved for the backward pass
@@ -58,6 +60,10 @@ struct LinProblem {
 };
 
 struct LinParams {
+  // one tensor map per problem over x as a (rows, K) fp32 matrix: box = 32 columns x 128 rows, SWIZZLE_128B — the
+  // TMA engine writes exactly the K-major swizzled tile the tensor core reads (chunk j of row r at j ^ (r & 7)), rows /
+  // columns beyond the matrix are zero-filled
+  alignas(64) CUtensorMap tmap[kMaxProbs];
   LinProblem pr[kMaxProbs];
   int nprobs, K, Kpad, N, relu, ln;
   int S, NS;  // the N columns are split over S CTAs of NS columns each (a cluster when LayerNorm needs whole rows)
@@ -65,6 +71,7 @@ struct LinParams {
   float eps;
   uint32_t tmem_cols, stage_bytes;
   int nstages, prefetch;  // ring depth in use and how many blocks the staging warps run ahead (nstages - 2)
+  int ts_hack;            // timing experiment only (EDA_LIN_TSHACK=1): A operand read from TMEM (garbage values)
   uint32_t drop_thresh, drop_seed;  // output dropout (after bias / ReLU, before residual): thresh 0 = off
   const uint32_t *seed_epoch;       // optional device word added to drop_seed (eda_dropout_set_epoch)
   float drop_scale;                 // 1 / (1 - p)
@@ -97,6 +104,15 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// 2-D tiled TMA load global -> shared (tensor map in kernel-parameter space), completes on `bar` with the box bytes
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -116,11 +132,11 @@ __device__ long long g_lin_ts[128];
 #define LIN_TS(i) do { if (blockIdx.x == 0 && tid == 0) g_lin_ts[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
-linear_kernel(const LinParams p) {
+linear_kernel(const __grid_constant__ LinParams p) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B atoms are addressed by absolute shared-memory address bits: align the ring to 1024 bytes
   unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t full_w[kStages], a_ready[kStages], empty[kStages], mma_done, res_bar;
+  __shared__ __align__(8) uint64_t full_w[kStages], full_a[kStages], a_ready[kStages], empty[kStages], mma_done, res_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[kMaxN], s_gamma[kMaxN], s_beta[kMaxN];
   __shared__ __align__(8) float2 s_stat[kRows];  // per-row (sum, sum of squares) of this CTA's column slice
@@ -139,6 +155,7 @@ linear_kernel(const LinParams p) {
   if (tid == 32) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_w[s], 1);
+      mbar_init(&full_a[s], 1);
       mbar_init(&a_ready[s], kWorkerWarps);  // one arrival per staging warp
       mbar_init(&empty[s], 1);
     }
@@ -161,11 +178,23 @@ linear_kernel(const LinParams p) {
   if (warp == kWorkerWarps + 1) {
     // ---------------- weight producer ----------------------------------------------------------
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % p.nstages;
+      // ring position as running counters: kb % nstages / kb / nstages by a run-time divisor cost a few hundred cycles
+      // of dependent scalar code per K block on these single-thread control paths
+      int slot = 0;
+      uint32_t round = 0;
+      for (int kb = 0; kb < nkb; ++kb, slot = (slot + 1 == p.nstages) ? 0 : slot + 1, round ^= (slot == 0) ? 1u : 0u) {
         const int kcnt = min(kKBlock, p.Kpad - kb * kKBlock);
         const uint32_t bytes = (uint32_t)kcnt * (uint32_t)N * 4u;
-        mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);
+        mbar_wait(&empty[slot], round ^ 1u);
+        if (pr.tma) {  // A block kb: one box of 32 columns x 128 rows, out-of-range parts zero-filled
+          if (p.ts_hack & 2) {
+            mbar_arrive(&full_a[slot]);  // timing experiment: no A traffic
+          } else {
+            mbar_arrive_expect_tx(&full_a[slot], (uint32_t)kTileBytes);
+            tma_load_2d(smem_raw + (size_t)slot * p.stage_bytes, &p.tmap[pi], kb * kKBlock, tile * kRows, &full_a[slot]);
+          }
+        }
+        if (p.ts_hack & 4) { mbar_arrive(&full_w[slot]); continue; }  // timing experiment: no W traffic
         mbar_arrive_expect_tx(&full_w[slot], bytes);
         unsigned char *wdst = smem_raw + (size_t)slot * p.stage_bytes + kABytes;
         const float *wsrc = pr.w + (size_t)kb * kKBlock * Nf;  // packed: [k block][16-byte chunk][Nf columns] float4
@@ -188,30 +217,41 @@ linear_kernel(const LinParams p) {
       const uint32_t idesc_a = umma::idesc_tf32(kRows, n_a);
       const uint32_t idesc_b = umma::idesc_tf32(kRows, n_b > 0 ? n_b : 16);
       const uint32_t lbo_w = (uint32_t)N * 16u;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % p.nstages;
+      // The issue loop runs on ONE thread that shares its scheduler with staging warps: every scalar instruction in it
+      // costs tens of cycles of tensor-pipe idle time.  Descriptors are therefore built once per ring slot; a K step
+      // only adds constants to their (address >> 4) fields: A +32 bytes inside the swizzle atom, B two chunk rows.
+      uint64_t adesc0[kStages], bdesc0[kStages];
+#pragma unroll
+      for (int st = 0; st < kStages; ++st) {
+        const uint32_t ab = smem_u32(smem_raw + (size_t)st * p.stage_bytes);
+        adesc0[st] = umma::smem_desc_swizzled(ab, 16u, 1024u, 2u);
+        bdesc0[st] = umma::smem_desc_kmajor_noswizzle(ab + kABytes, lbo_w, 128u);
+      }
+      const uint64_t a_step = 32u >> 4, b_step = (uint64_t)((2u * lbo_w) >> 4), b_half = (uint64_t)(((uint32_t)n_a * 16u) >> 4);
+      int slot = 0;
+      uint32_t par = 0;
+      for (int kb = 0; kb < nkb; ++kb, slot = (slot + 1 == p.nstages) ? 0 : slot + 1, par ^= (slot == 0) ? 1u : 0u) {
         const int kcnt = min(kKBlock, p.Kpad - kb * kKBlock);
-        const uint32_t par = (kb / p.nstages) & 1;
         mbar_wait(&a_ready[slot], par);
         if (blockIdx.x == 0 && kb < 10) g_lin_ts[32 + 3 * kb] = clock64();      // [32 + 3 kb] A block kb staged
         mbar_wait(&full_w[slot], par);
         if (blockIdx.x == 0 && kb < 10) g_lin_ts[33 + 3 * kb] = clock64();      // [33 + 3 kb] W block kb landed
         umma::fence_after_thread_sync();
-        const uint32_t abase = smem_u32(smem_raw + (size_t)slot * p.stage_bytes);
-        const uint32_t wbase = abase + kABytes;
-        for (int ks = 0; ks < kcnt / 8; ++ks) {
-          // A: K-major SWIZZLE_128B (rows of 128 B, 8-row atoms 1024 B apart); +32 B per 8-wide k step
-          const uint64_t adesc = umma::smem_desc_swizzled(abase + (uint32_t)ks * 32u, 16u, 1024u, 2u);
+        // A: K-major SWIZZLE_128B (rows of 128 B, 8-row atoms 1024 B apart); +32 B per 8-wide k step
+        uint64_t adesc = adesc0[slot], b0 = bdesc0[slot];
+        const int nks = kcnt / 8;
+        const bool dbg = blockIdx.x == 0 && kb == 3;
+        if (dbg) g_lin_ts[120] = clock64();  // after the fence
+        for (int ks = 0; ks < nks; ++ks) {
           const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-          const uint64_t b0 = umma::smem_desc_kmajor_noswizzle(wbase + (uint32_t)ks * 2u * lbo_w, lbo_w, 128u);
           umma::mma_tf32_ss(tbase, adesc, b0, idesc_a, acc);
-          if (n_b > 0) {
-            const uint64_t b1 =
-                umma::smem_desc_kmajor_noswizzle(wbase + (uint32_t)ks * 2u * lbo_w + (uint32_t)n_a * 16u, lbo_w, 128u);
-            umma::mma_tf32_ss(tbase + (uint32_t)n_a, adesc, b1, idesc_b, acc);
-          }
+          if (n_b > 0) umma::mma_tf32_ss(tbase + (uint32_t)n_a, adesc, b0 + b_half, idesc_b, acc);
+          adesc += a_step;
+          b0 += b_step;
+          if (dbg && ks < 4) g_lin_ts[121 + ks] = clock64();  // after K step ks
         }
         umma::mma_commit(&empty[slot]);
+        if (dbg) g_lin_ts[125] = clock64();  // after the commit
         if (blockIdx.x == 0 && kb < 10) g_lin_ts[34 + 3 * kb] = clock64();      // [34 + 3 kb] MMAs of block kb issued
         if (kb == nkb - 1) umma::mma_commit(&mma_done);
       }
@@ -227,10 +267,13 @@ linear_kernel(const LinParams p) {
     constexpr int kRowStep = kWorkers / 8;
     const int cj = tid & 7, cr0 = tid >> 3;
 
+    const bool tma = pr.tma != 0;
     auto issue_block = [&](int kb) {
+      if (tma) return;  // the producer warp's TMA copies fill the A tiles
       if (vec && kb < nkb) {
-        const int slot = kb % p.nstages;
-        if (lane == 0) mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);  // the MMAs that read this slot are done
+        const int slot = p.nstages == 4 ? (kb & 3) : kb % 3;
+        const int rnd = p.nstages == 4 ? (kb >> 2) : kb / 3;
+        if (lane == 0) mbar_wait(&empty[slot], (uint32_t)((rnd & 1) ^ 1));  // the MMAs that read this slot are done
         __syncwarp();
         unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
         const int k = kb * kKBlock + cj * 4;
@@ -247,8 +290,9 @@ linear_kernel(const LinParams p) {
     };
     for (int i = 0; i < p.prefetch; ++i) issue_block(i);
 
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int slot = kb % p.nstages;
+    int slot = 0;
+    uint32_t spar = 0;
+    for (int kb = 0; kb < nkb; ++kb, slot = (slot + 1 == p.nstages) ? 0 : slot + 1, spar ^= (slot == 0) ? 1u : 0u) {
 #define STG_TS(j) do { if (blockIdx.x == 0 && tid == 0 && kb < 9) g_lin_ts[64 + 6 * kb + (j)] = clock64(); } while (0)
       STG_TS(0);
       issue_block(kb + p.prefetch);
@@ -265,10 +309,16 @@ linear_kernel(const LinParams p) {
           pq[i] = in ? __ldg(reinterpret_cast<const float4 *>(pr.pos + (size_t)(row0 + r) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      if (p.prefetch == 2) umma::cp_async_wait<2>(); else umma::cp_async_wait<1>();  // block kb has landed (own copies)
+      if (tma) {
+        mbar_wait(&full_a[slot], spar);  // block kb has landed (TMA)
+      } else {
+        if (p.prefetch == 2) umma::cp_async_wait<2>(); else umma::cp_async_wait<1>();  // block kb has landed (own copies)
+      }
       STG_TS(2);
       unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
-      if (vec) {
+      if (vec && (p.ts_hack & 8)) {
+        // timing experiment: no fix-up pass
+      } else if (vec) {
         // the chunks this thread copied: "+ pos", round to tf32 (round-to-nearest), in place
         float4 v[kOwn];
 #pragma unroll
@@ -288,7 +338,7 @@ linear_kernel(const LinParams p) {
         }
       } else {
         // rows that are not 16-byte aligned (K = 3 or 6: xyz / box inputs of the position embedding): thread = row
-        mbar_wait(&empty[slot], ((kb / p.nstages) & 1) ^ 1);
+        mbar_wait(&empty[slot], spar ^ 1u);
         const long long row = row0 + tid;
         const bool valid = row < pr.rows;
         const float *xrow = pr.x + row * K;
@@ -572,6 +622,35 @@ __global__ void dropout_mask_kernel(uint32_t seed_base, uint32_t thresh, long lo
 }
 
 inline int kpad_of(int K) { return (K + 7) & ~7; }
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    if (const char *e = getenv("EDA_LINEAR_TMA")) if (e[0] == '0') return nullptr;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(sym);
+  }();
+  return fn;
+}
+// Tensor map over x (rows, K) fp32 row-major for 32-column x 128-row boxes, SWIZZLE_128B.  false = use cp.async staging.
+inline bool make_a_tensor_map(CUtensorMap *map, const float *x, long long rows, int K) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || (K & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || rows <= 0) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)kRows};
+  const cuuint32_t estride[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), gdim, gstride, box, estride,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline bool lin_supported(int N, int K) { return N >= 16 && N <= kMaxN && (N & 15) == 0 && K >= 1 && K <= 4096; }
 
 }  // namespace
@@ -658,6 +737,8 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
     p.pr[i].x = q.x; p.pr[i].pos = q.pos; p.pr[i].w = q.w_packed; p.pr[i].bias = q.bias;
     p.pr[i].residual = q.residual; p.pr[i].y = q.y; p.pr[i].pre = q.pre_ln; p.pr[i].rows = q.rows; p.pr[i].tile0 = tiles;
     p.pr[i].tb = q.y_batch_rows; p.pr[i].ldt = q.y_ld; p.pr[i].round_out = q.round_tf32;
+    p.pr[i].tma = (q.rows > 0 && (!q.pos || !(reinterpret_cast<uintptr_t>(q.pos) & 15)) &&
+                   make_a_tensor_map(&p.tmap[i], q.x, q.rows, K)) ? 1 : 0;
     if (q.y_row_stride != 0 && (q.y_row_stride < N || (q.y_row_stride & 3) || q.y_batch_rows > 0)) return EDA_ERR_INVALID_ARGUMENT;
     p.pr[i].ldy = q.y_row_stride ? q.y_row_stride : N;
     tiles += (q.rows + kRows - 1) / kRows;
@@ -679,6 +760,11 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   p.stage_bytes = (uint32_t)((kABytes + kKBlock * NS * 4 + 1023) & ~1023);
   p.nstages = (size_t)4 * p.stage_bytes <= 216 * 1024 ? 4 : 3;
   p.prefetch = p.nstages - 2;
+  {
+    const char *e = getenv("EDA_LIN_TSHACK");
+    p.ts_hack = e ? atoi(e) : 0;
+    if ((p.ts_hack & 1) && p.tmem_cols != 512u) p.ts_hack &= ~1;
+  }
   size_t smem = (size_t)p.nstages * p.stage_bytes;
   const size_t out_tile = (size_t)kRows * (NS + 4) * sizeof(float);
   if (smem < out_tile) smem = out_tile;

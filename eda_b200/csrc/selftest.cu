@@ -134,6 +134,72 @@ umma_probe_kernel(int N, int lbo, int sbo, int b_mn, int layout, int start_off, 
   if (warp == 0) umma::tmem_dealloc(tbase, 256);
 }
 
+
+// MMA issue / execution rate probe (measurement aid): one CTA per block of the grid issues `iters` kind::tf32 MMAs of
+// shape 128 x N x 8 back to back from one thread (fixed operand addresses, accumulate on) and reports the cycles
+// between the first issue and the completion of the last one (clock64).  a_mode 0: A from shared memory (K-major,
+// no swizzle), 1: A from tensor memory, 2: A from shared memory in the SWIZZLE_128B layout the linear kernel stages.
+// b_swz != 0: B in SWIZZLE_128B too (rows of 128 bytes), else the chunk-major no-swizzle layout of the packed weights.
+// precomputed != 0: descriptors built once outside the loop (isolates the instruction overhead of the issue loop).
+__global__ void __launch_bounds__(1024, 1)
+umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed, int iters, long long *__restrict__ cycles) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bar, spin_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&spin_bar, 1);
+    mbar_fence_init_cluster();
+  }
+  float *f = reinterpret_cast<float *>(base);
+  for (int i = tid; i < 16384; i += blockDim.x) f[i] = 0.f;  // 64 KB of zeros: operands (values do not matter for timing)
+  umma::fence_proxy_async_smem();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tbase = tmem_base_slot;
+  if (tid == 0) {
+    const uint32_t idesc = umma::idesc_tf32(128, N);
+    const uint32_t a_addr = smem_u32(base), b_addr = smem_u32(base) + 16384u;
+    const uint32_t lbo_w = (uint32_t)N * 16u;
+    const uint64_t a0 = a_mode == 2 ? umma::smem_desc_swizzled(a_addr, 16u, 1024u, 2u)
+                                    : umma::smem_desc_kmajor_noswizzle(a_addr, 128u * 16u, 128u);
+    const uint64_t b0 = b_swz ? umma::smem_desc_swizzled(b_addr, 16u, 1024u, 2u)
+                              : umma::smem_desc_kmajor_noswizzle(b_addr, lbo_w, 128u);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t ks = (uint32_t)(i & 3);
+      uint64_t ad = a0, bd = b0;
+      if (!precomputed) {  // what the production loops do: rebuild both descriptors per K step
+        ad = a_mode == 2 ? umma::smem_desc_swizzled(a_addr + ks * 32u, 16u, 1024u, 2u)
+                         : umma::smem_desc_kmajor_noswizzle(a_addr + ks * 2u * 2048u, 128u * 16u, 128u);
+        bd = b_swz ? umma::smem_desc_swizzled(b_addr + ks * 32u, 16u, 1024u, 2u)
+                   : umma::smem_desc_kmajor_noswizzle(b_addr + ks * 2u * lbo_w, lbo_w, 128u);
+      }
+      if (a_mode == 1) umma::mma_tf32_ts(tbase, tbase + 288u + ks * 8u, bd, idesc, 1u);
+      else umma::mma_tf32_ss(tbase, ad, bd, idesc, 1u);
+    }
+    const long long t1 = clock64();
+    umma::mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    cycles[2 * blockIdx.x] = t1 - t0;      // issue loop
+    cycles[2 * blockIdx.x + 1] = t2 - t0;  // until the last MMA has completed
+    mbar_arrive_expect_tx(&spin_bar, 0);   // releases the spinner warps
+  } else if (warp >= 4) {
+    // extra warps (blockDim > 128): wait on a shared-memory barrier for the whole measurement, like the staging /
+    // producer warps of the GEMM kernels do while the issuer thread works
+    mbar_wait(&spin_bar, 0);
+  }
+  __syncthreads();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace
 }  // namespace eda
 
@@ -155,4 +221,18 @@ extern "C" int eda_selftest_umma(const float *A, const float *W, int N, int K, i
                "selftest smem attr");
   umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(A, W, N, K, mode, D);
   return check_launch("umma_selftest_kernel");
+}
+
+extern "C" int eda_selftest_umma_rate(int N, int a_mode, int b_swizzled, int precomputed, int iters, int ctas,
+                                      int waiting_warps, long long *cycles_device, void *stream) {
+  using namespace eda;
+  if (!cycles_device || N < 16 || N > 256 || N % 16 || iters < 1 || ctas < 1 || a_mode < 0 || a_mode > 2 ||
+      waiting_warps < 0 || waiting_warps > 28)
+    return EDA_ERR_INVALID_ARGUMENT;
+  const size_t smem = 65536 + 1024;
+  EDA_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "umma rate smem attr");
+  umma_rate_kernel<<<ctas, 128 + 32 * waiting_warps, smem, as_stream(stream)>>>(N, a_mode, b_swizzled, precomputed, iters,
+                                                                               cycles_device);
+  return check_launch("umma_rate_kernel");
 }

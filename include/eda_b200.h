@@ -437,6 +437,14 @@ EDA_API int eda_selftest_umma(const float *A, const float *W, int N, int K, int 
 EDA_API int eda_selftest_umma_probe(int N, int lbo_bytes, int sbo_bytes, int b_mn_major, int layout_type,
                                     int start_offset_bytes, float *D, void *stream);
 
+/* Tensor-pipe rate probe (measurement aid, bench / DESIGN numbers): every CTA issues `iters` kind::tf32 MMAs of shape
+ * 128 x N x 8 from one thread and writes [issue-loop cycles, cycles until completion] to cycles_device[2 * cta].
+ * a_mode 0 / 1 / 2: A from shared memory (no swizzle) / tensor memory / shared memory SWIZZLE_128B; b_swizzled: B in
+ * SWIZZLE_128B instead of the packed chunk-major layout; precomputed: descriptors hoisted out of the issue loop;
+ * waiting_warps: extra warps of the CTA that sit in an mbarrier wait for the duration (as producer / staging warps do). */
+EDA_API int eda_selftest_umma_rate(int N, int a_mode, int b_swizzled, int precomputed, int iters, int ctas,
+                                   int waiting_warps, long long *cycles_device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
