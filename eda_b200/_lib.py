@@ -75,6 +75,8 @@ PROTOTYPES = {
     "eda_relu_backward": (_c_int, [_vp, _vp, _c_float, ctypes.c_longlong, _vp, _vp]),
     "eda_rows_gemm": (_c_int, [_vp, _c_int, _vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _c_int,
                                _c_int, _vp, _c_int, _vp]),
+    "eda_rows_gemm_stats": (_c_int, [_vp, _c_int, _vp, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                                     _c_int, _c_int, _vp, _c_int, _vp, _vp]),
     "eda_sa_gather_rows": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                                     _c_int, _vp, _vp]),
     "eda_bn_relu_apply": (_c_int, [_vp, _vp, _vp, ctypes.c_longlong, _c_int, _vp, _vp]),

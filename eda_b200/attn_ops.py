@@ -492,9 +492,10 @@ def layernorm_backward(dy, u, gamma, eps, dgamma, dbeta, dropout=None):
     return du, dproj
 
 
-def rows_gemm(x, W, transpose=False, in_scale=None, in_shift=None):
+def rows_gemm(x, W, transpose=False, in_scale=None, in_shift=None, stats=None):
     """y = f(x) W^T (transpose=False, W (N,K)) or f(x) W (transpose=True, W (K,N): the activation gradient of a layer
-    y = a W^T), f = relu(x * in_scale + in_shift) when given.  x (R,K) contiguous; W any 2-D strided view."""
+    y = a W^T), f = relu(x * in_scale + in_shift) when given.  x (R,K) contiguous; W any 2-D strided view.
+    stats: optional zeroed (2N,) float64 tensor that receives [column sums, column sums of squares] of y."""
     lib = _lib.load()
     R, K = x.shape
     if transpose:
@@ -505,8 +506,8 @@ def rows_gemm(x, W, transpose=False, in_scale=None, in_shift=None):
         N, sn, sk = W.size(0), W.stride(0), W.stride(1)
     y = torch.empty((R, N), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        rc = lib.eda_rows_gemm(_p(x), K, _p(in_scale), _p(in_shift), _p(W), int(sn), int(sk), R, K, N, _p(y), N,
-                               _stream(x.device))
+        rc = lib.eda_rows_gemm_stats(_p(x), K, _p(in_scale), _p(in_shift), _p(W), int(sn), int(sk), R, K, N, _p(y), N,
+                                     _p(stats), _stream(x.device))
     _lib.check(rc, "rows_gemm")
     return y
 

@@ -23,6 +23,8 @@ constexpr int kRgMaxK = 288;
 struct RowsGemmParams {
   const float *x, *in_scale, *in_shift, *w;
   float *y;
+  double *stats;  // optional [sum_r y[r][n] (N), sum_r y[r][n]^2 (N)], accumulated (fp64 atomics): the BatchNorm batch
+                  // statistics of the layer this GEMM evaluates, taken in the epilogue instead of by a second pass over y
   long long rows, w_sn, w_sk;
   int ldx, ldy, K, N, ntiles;
 };
@@ -43,7 +45,7 @@ __device__ __forceinline__ void rg_cp16(void *smem_dst, const void *gsrc, uint32
                : "memory");
 }
 
-template <bool kPrologue>
+template <bool kPrologue, bool kStats>
 __global__ void __launch_bounds__(kRgThreads, 1)
 rows_gemm_kernel(const RowsGemmParams p) {
   extern __shared__ __align__(16) unsigned char rg_smem[];
@@ -94,6 +96,13 @@ rows_gemm_kernel(const RowsGemmParams p) {
   constexpr int kMaxNT = kRgNc / 8;
   const int nnt = Nc >> 3;
   float acc[kMaxNT][4];
+  // column statistics (kStats): this thread's running partial sums over all the rows it produces, for its columns
+  // j * 8 + 2 t and + 1 — fixed order, fp32; reduced over the CTA at the end and added to p.stats in fp64
+  float csum[kStats ? kMaxNT : 1][2], csq[kStats ? kMaxNT : 1][2];
+  if (kStats) {
+#pragma unroll
+    for (int j = 0; j < kMaxNT; ++j) csum[j][0] = csum[j][1] = csq[j][0] = csq[j][1] = 0.f;
+  }
   const int r0 = warp * 16;
   for (long long item = 0; item < total; ++item) {
     const int ti = (int)(item / nkc), kc = (int)(item - (long long)ti * nkc);
@@ -130,20 +139,66 @@ rows_gemm_kernel(const RowsGemmParams p) {
           const int n = n0 + j * 8 + 2 * t;
           if (ra < p.rows) *reinterpret_cast<float2 *>(p.y + ra * p.ldy + n) = make_float2(acc[j][0], acc[j][1]);
           if (rb < p.rows) *reinterpret_cast<float2 *>(p.y + rb * p.ldy + n) = make_float2(acc[j][2], acc[j][3]);
+          if (kStats) {  // rows beyond p.rows were zero-filled on the way in: they add exactly 0
+            csum[j][0] += acc[j][0] + acc[j][2];
+            csum[j][1] += acc[j][1] + acc[j][3];
+            csq[j][0] = fmaf(acc[j][0], acc[j][0], fmaf(acc[j][2], acc[j][2], csq[j][0]));
+            csq[j][1] = fmaf(acc[j][1], acc[j][1], fmaf(acc[j][3], acc[j][3], csq[j][1]));
+          }
         }
       }
     }
     __syncthreads();  // the stage read here is refilled by the next iteration's prefetch
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (kStats) {
+    // lanes with the same t hold the same columns: butterfly over g (lane bits 2..4), then the 8 warps through shared
+    // memory (the X ring is idle now), then ONE fp64 atomic per column and CTA
+    __syncthreads();
+    float *red = sX;  // [8 warps][2 * kRgNc]
+#pragma unroll
+    for (int j = 0; j < kMaxNT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = csum[j][e], b = csq[j][e];
+#pragma unroll
+        for (int d = 4; d < 32; d <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, d);
+          b += __shfl_xor_sync(0xffffffffu, b, d);
+        }
+        if (g == 0 && j < nnt) {
+          red[warp * 2 * kRgNc + j * 8 + 2 * t + e] = a;
+          red[warp * 2 * kRgNc + kRgNc + j * 8 + 2 * t + e] = b;
+        }
+      }
+    }
+    __syncthreads();
+    for (int c = tid; c < 2 * Nc; c += kRgThreads) {
+      const int col = c < Nc ? c : c - Nc, half = c < Nc ? 0 : 1;
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kRgThreads / 32; ++w) v += (double)red[w * 2 * kRgNc + half * kRgNc + col];
+      atomicAdd(p.stats + (size_t)half * p.N + n0 + col, v);
+    }
+  }
 }
 
 }  // namespace
 }  // namespace eda
 
+extern "C" int eda_rows_gemm_stats(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
+                                   long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y,
+                                   int ldy, double *stats, void *stream);
+
 extern "C" int eda_rows_gemm(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
                              long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y, int ldy,
                              void *stream) {
+  return eda_rows_gemm_stats(x, ldx, in_scale, in_shift, w, w_stride_n, w_stride_k, rows, K, N, y, ldy, nullptr, stream);
+}
+
+extern "C" int eda_rows_gemm_stats(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
+                                   long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y,
+                                   int ldy, double *stats, void *stream) {
   using namespace eda;
   if (rows < 0 || K < 8 || N < 8) return EDA_ERR_INVALID_ARGUMENT;
   if ((K & 7) || (N & 7) || K > kRgMaxK) return EDA_ERR_UNSUPPORTED;
@@ -155,23 +210,27 @@ extern "C" int eda_rows_gemm(const float *x, int ldx, const float *in_scale, con
   if (ntiles > 0x7fffffffLL) return EDA_ERR_UNSUPPORTED;
   RowsGemmParams p = {};
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.y = y; p.rows = rows; p.w_sn = w_stride_n;
-  p.w_sk = w_stride_k; p.ldx = ldx; p.ldy = ldy; p.K = K; p.N = N; p.ntiles = (int)ntiles;
+  p.w_sk = w_stride_k; p.ldx = ldx; p.ldy = ldy; p.K = K; p.N = N; p.ntiles = (int)ntiles; p.stats = stats;
   const size_t smem = (size_t)kRgNc * (K + 4) * 4 + (size_t)kRgStages * kRgRows * kRgPx * 4 + 2 * kRgMaxK * 4;
-  static SmemAttr attr[2];
-  const int which = in_scale ? 1 : 0;
-  if (which)
-    EDA_CUDA_TRY(attr[1].ensure(rows_gemm_kernel<true>, smem), "rows_gemm smem attr");
-  else
-    EDA_CUDA_TRY(attr[0].ensure(rows_gemm_kernel<false>, smem), "rows_gemm smem attr");
+  static SmemAttr attr[4];
+  const int which = (in_scale ? 1 : 0) | (stats ? 2 : 0);
+  switch (which) {
+    case 0: EDA_CUDA_TRY(attr[0].ensure(rows_gemm_kernel<false, false>, smem), "rows_gemm smem attr"); break;
+    case 1: EDA_CUDA_TRY(attr[1].ensure(rows_gemm_kernel<true, false>, smem), "rows_gemm smem attr"); break;
+    case 2: EDA_CUDA_TRY(attr[2].ensure(rows_gemm_kernel<false, true>, smem), "rows_gemm smem attr"); break;
+    default: EDA_CUDA_TRY(attr[3].ensure(rows_gemm_kernel<true, true>, smem), "rows_gemm smem attr"); break;
+  }
   const int sms = sm_count();
   const int ny = (N + kRgNc - 1) / kRgNc;
   long long gx = sms / ny;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   dim3 grid((unsigned)gx, (unsigned)ny);
-  if (which)
-    rows_gemm_kernel<true><<<grid, kRgThreads, smem, as_stream(stream)>>>(p);
-  else
-    rows_gemm_kernel<false><<<grid, kRgThreads, smem, as_stream(stream)>>>(p);
+  switch (which) {
+    case 0: rows_gemm_kernel<false, false><<<grid, kRgThreads, smem, as_stream(stream)>>>(p); break;
+    case 1: rows_gemm_kernel<true, false><<<grid, kRgThreads, smem, as_stream(stream)>>>(p); break;
+    case 2: rows_gemm_kernel<false, true><<<grid, kRgThreads, smem, as_stream(stream)>>>(p); break;
+    default: rows_gemm_kernel<true, true><<<grid, kRgThreads, smem, as_stream(stream)>>>(p); break;
+  }
   return check_launch("rows_gemm_kernel");
 }

@@ -185,12 +185,13 @@ def sa_forward_rows(xyz, new_xyz, feat_pm, idx, layers, radius, normalize_xyz, t
         _lib.check(rc, "sa_gather_rows")
         zs, xin, sc, sh = [], x0, None, None
         for l, (conv, bn) in enumerate(layers):
-            z = ops.rows_gemm(xin, Wl[l], in_scale=sc, in_shift=sh)
             if training:
+                # batch statistics of this layer's output are taken in the GEMM epilogue (no second pass over z)
                 stats = torch.zeros(2 * widths[l], dtype=torch.float64, device=dev)
-                _lib.check(lib.eda_col_stats(_p(z), R, widths[l], _p(stats), stream), "col_stats")
+                z = ops.rows_gemm(xin, Wl[l], in_scale=sc, in_shift=sh, stats=stats)
                 sc, sh, mi = _bn_scale_shift(lib, dev, stats, float(R), bn, conv.bias, widths[l], True, want_stats=True)
             else:
+                z = ops.rows_gemm(xin, Wl[l], in_scale=sc, in_shift=sh)
                 sc, sh, mi = _bn_scale_shift(lib, dev, None, 0.0, bn, conv.bias, widths[l], False, want_stats=True)
             state.append((sc, sh, mi))
             zs.append(z)

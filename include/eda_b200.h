@@ -369,6 +369,12 @@ EDA_API int eda_dropout_mask(unsigned int seed, const unsigned int *dropout_epoc
 EDA_API int eda_rows_gemm(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
                           long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y, int ldy,
                           void *stream);
+/* Same GEMM, additionally accumulating the column statistics of its OUTPUT into stats (2N doubles: [sum_r y[r][n],
+ * sum_r y[r][n]^2], zero first): the BatchNorm batch statistics of the layer, taken in the epilogue while the tile is
+ * still in registers instead of by a second pass over y (eda_col_stats).  stats NULL = plain eda_rows_gemm. */
+EDA_API int eda_rows_gemm_stats(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
+                                long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y,
+                                int ldy, double *stats, void *stream);
 EDA_API int eda_sa_gather_rows(const float *xyz, const float *new_xyz, const float *feat, int feat_stride,
                                const int *idx, int B, int N, int M, int S, int C, int K0pad, float radius,
                                int normalize_xyz, float *x0, void *stream);

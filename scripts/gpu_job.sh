@@ -27,11 +27,21 @@ for step in "$@"; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches_train.csv python benchmarks/train_once.py 1 > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "launch list rc=$?"
       python scripts/ncu_csv_summary.py gpurun_out/${TAG}_launches_train.csv gpurun_out/${TAG}_launches_train_summary.json ;;
     metrics)
-      timeout 1200 ncu --metrics $M --clock-control none -k regex:"eda::" -c 1500 --csv --log-file gpurun_out/${TAG}_kernel_metrics.csv python benchmarks/train_once.py 1 > gpurun_out/${TAG}_ncu_metrics.log 2>&1; echo "metrics rc=$?"
+      timeout 1200 ncu --metrics $M --clock-control none -k regex:"_kernel" -c 1500 --csv --log-file gpurun_out/${TAG}_kernel_metrics.csv python benchmarks/train_once.py 1 > gpurun_out/${TAG}_ncu_metrics.log 2>&1; echo "metrics rc=$?"
       python scripts/ncu_csv_summary.py gpurun_out/${TAG}_kernel_metrics.csv gpurun_out/${TAG}_kernel_metrics.json ;;
     sweepncu)
       timeout 1200 ncu --metrics $M --clock-control none -k regex:"fps_cluster|ball_query|attention_kernel" -c 400 --csv --log-file gpurun_out/${TAG}_sweep_ncu.csv python benchmarks/kernels.py > gpurun_out/${TAG}_sweep_under_ncu.log 2>&1; echo "sweep ncu rc=$?"
       python scripts/ncu_csv_summary.py gpurun_out/${TAG}_sweep_ncu.csv gpurun_out/${TAG}_sweep_ncu.json ;;
+    full)
+      # one `--set full` capture per roofline kernel (the dominant launch of each), source-correlated
+      for k in linear fps ballq attention sa_mlp; do
+        case $k in linear) re=linear_kernel;; fps) re=fps_cluster_kernel;; ballq) re=ball_query_kernel;; attention) re=attention_kernel;; sa_mlp) re=sa_mlp_kernel;; esac
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:$re -s 3 -c 1 -f -o gpurun_out/${TAG}_full_$k python scripts/kernels_once.py $k > gpurun_out/${TAG}_full_$k.log 2>&1; echo "full $k rc=$?"
+      done ;;
+    benchlaunches)
+      # launch list of the bench command itself (graph replays show up as their kernels)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "bench launch list rc=$?"
+      python scripts/ncu_csv_summary.py gpurun_out/${TAG}_launches_bench.csv gpurun_out/${TAG}_launches_bench_summary.json ;;
     *) echo "unknown step $step" ;;
   esac
 done
