@@ -84,6 +84,8 @@ __device__ long long g_attn_ts[32];
 template <int D, bool kDrop>
 __global__ void __launch_bounds__(kThreads, 2)
 attention_kernel(const AttnParams p) {
+  pdl_launch_dependents();  // a PDL-launched successor may be scheduled now (it waits for this grid's completion itself)
+  pdl_wait();               // launched with the PDL attribute: q / k / v come from the GEMM just before
   using DM = Dims<D>;
   constexpr int DC = DM::DC, QC = DM::QC, Dn = DM::Dn, VP = DM::VP, VG = DM::VG;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -354,9 +356,9 @@ int launch_attention(const AttnParams &p, int B, cudaStream_t st) {
     EDA_CUDA_TRY(attr_plain.ensure(attention_kernel<D, false>, smem), "attention smem attr");
   dim3 grid((unsigned)((p.Nq + kRows - 1) / kRows), (unsigned)p.H, (unsigned)B);
   if (p.drop_thresh)
-    attention_kernel<D, true><<<grid, kThreads, smem, st>>>(p);
+    EDA_CUDA_TRY(launch_pdl(attention_kernel<D, true>, grid, dim3(kThreads), smem, st, p), "attention_kernel launch");
   else
-    attention_kernel<D, false><<<grid, kThreads, smem, st>>>(p);
+    EDA_CUDA_TRY(launch_pdl(attention_kernel<D, false>, grid, dim3(kThreads), smem, st, p), "attention_kernel launch");
   return check_launch("attention_kernel");
 }
 

@@ -74,6 +74,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int D, bool kKeyRows, bool kDrop>
 __global__ void __launch_bounds__(kBwThreads)
 attention_backward_kernel(const AttnBwdParams p) {
+  pdl_launch_dependents();  // a PDL-launched successor may be scheduled now (it waits for this grid's completion itself)
+  pdl_wait();               // launched with the PDL attribute: dctx comes from the GEMM just before, delta from the first pass
   constexpr int DP = (D + 7) & ~7;   // padded depth
   constexpr int KS = DP / 8;         // k-steps over the depth / n-tiles of the outputs
   constexpr int DC = D / 4;          // 16-byte chunks of real data per row
@@ -296,11 +298,11 @@ int launch_attention_backward(const AttnBwdParams &p, int B, cudaStream_t st) {
   dim3 gq((unsigned)((p.Nq + kBwRows - 1) / kBwRows), (unsigned)p.H, (unsigned)B);
   dim3 gk((unsigned)((p.Nk + kBwRows - 1) / kBwRows), (unsigned)p.H, (unsigned)B);
   if (p.drop_thresh) {
-    attention_backward_kernel<D, false, true><<<gq, kBwThreads, 0, st>>>(p);
-    attention_backward_kernel<D, true, true><<<gk, kBwThreads, 0, st>>>(p);
+    EDA_CUDA_TRY(launch_pdl(attention_backward_kernel<D, false, true>, gq, dim3(kBwThreads), 0, st, p), "attention backward launch");
+    EDA_CUDA_TRY(launch_pdl(attention_backward_kernel<D, true, true>, gk, dim3(kBwThreads), 0, st, p), "attention backward launch");
   } else {
-    attention_backward_kernel<D, false, false><<<gq, kBwThreads, 0, st>>>(p);
-    attention_backward_kernel<D, true, false><<<gk, kBwThreads, 0, st>>>(p);
+    EDA_CUDA_TRY(launch_pdl(attention_backward_kernel<D, false, false>, gq, dim3(kBwThreads), 0, st, p), "attention backward launch");
+    EDA_CUDA_TRY(launch_pdl(attention_backward_kernel<D, true, false>, gk, dim3(kBwThreads), 0, st, p), "attention backward launch");
   }
   return check_launch("attention_backward_kernel", 2);
 }

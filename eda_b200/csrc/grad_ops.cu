@@ -186,6 +186,8 @@ layernorm_backward_kernel(const float *__restrict__ dy, const float *__restrict_
                           float eps, long long rows, int N, float *__restrict__ du, float *__restrict__ dproj,
                           float *__restrict__ dgamma, float *__restrict__ dbeta, uint32_t drop_thresh,
                           uint32_t drop_seed_base, float drop_scale, const uint32_t *seed_epoch) {
+  pdl_launch_dependents();  // a PDL-launched successor may be scheduled now (it waits for this grid's completion itself)
+  pdl_wait();               // launched with the PDL attribute: dy comes from the kernel just before
   __shared__ float s_acc[2][kLnMaxN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n4 = N >> 2;
@@ -293,6 +295,7 @@ layernorm_backward_kernel(const float *__restrict__ dy, const float *__restrict_
 
 __global__ void relu_backward_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ y, float scale,
                                      long long n4, float4 *__restrict__ out) {
+  pdl_launch_dependents();  // a PDL-launched successor may be scheduled now (it waits for this grid's completion itself)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 d = __ldg(dy + i), a = __ldg(y + i);
     out[i] = make_float4(a.x > 0.f ? d.x * scale : 0.f, a.y > 0.f ? d.y * scale : 0.f, a.z > 0.f ? d.z * scale : 0.f,
@@ -383,9 +386,10 @@ int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, 
   if (blocks > sms) blocks = sms;
   if (blocks < 1) blocks = 1;
   const uint32_t thresh = dropout_thresh(dropout_p);
-  layernorm_backward_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(
-      dy, u, gamma, eps, rows, N, du, thresh ? dproj : nullptr, dgamma, dbeta, thresh, dropout_seed,
-      1.0f / (1.0f - dropout_p), reinterpret_cast<const uint32_t *>(dropout_epoch));
+  EDA_CUDA_TRY(launch_pdl(layernorm_backward_kernel, dim3((unsigned)blocks), dim3(kLnWarps * 32), 0, as_stream(stream), dy, u,
+                          gamma, eps, rows, N, du, thresh ? dproj : nullptr, dgamma, dbeta, thresh, dropout_seed,
+                          1.0f / (1.0f - dropout_p), reinterpret_cast<const uint32_t *>(dropout_epoch)),
+               "layernorm_backward_kernel launch");
   return check_launch("layernorm_backward_kernel");
 }
 

@@ -163,6 +163,11 @@ linear_kernel(const __grid_constant__ LinParams p) {
     mbar_init(&res_bar, 1);
     mbar_fence_init_cluster();
   }
+  // everything above is private set-up (tensor-memory allocation, barrier initialisation); from here on memory that the
+  // predecessor in the stream may have written is read (bias / shift vectors can come straight out of a BatchNorm
+  // finalisation, activations and packed weights anyway)
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = tid; i < N; i += kThreads) {
     s_bias[i] = pr.bias ? __ldg(pr.bias + n0 + i) : 0.f;
     s_gamma[i] = (p.ln && p.gamma) ? __ldg(p.gamma + n0 + i) : 1.f;
@@ -779,16 +784,28 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)p.S;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, linear_kernel, p), "linear_kernel cluster launch");
   } else {
-    linear_kernel<<<tiles * p.S, kThreads, smem, as_stream(stream)>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * p.S));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    EDA_CUDA_TRY(cudaLaunchKernelEx(&cfg, linear_kernel, p), "linear_kernel launch");
   }
   return check_launch("linear_kernel");
 }
