@@ -18,6 +18,20 @@ import torch
 from . import _lib
 
 
+_capture_streams = {}
+
+
+def _capture_stream(device):
+    """ONE warm-up / capture side stream per device for every graph this module records: autograd's AccumulateGrad nodes
+    remember the stream they first ran on, and a later capture (another length bucket, a re-capture) that warmed up on
+    a different stream would trip over that."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _capture_streams.get(key)
+    if st is None:
+        st = _capture_streams[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class GraphedCallable:
     """graphed = GraphedCallable(fn, example_inputs); out = graphed(*inputs)
 
@@ -126,7 +140,7 @@ class GraphedTrainStep:
                 m.__dict__.pop("_eda_dropout_epoch", None)
         buffers = [(b, b.detach().clone()) for b in model.buffers()]
         try:
-            side = torch.cuda.Stream(device=self.device)
+            side = _capture_stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(max(1, warmup)):
@@ -134,7 +148,7 @@ class GraphedTrainStep:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=side):
                 self.loss = step()
             with torch.no_grad():  # undo the warm-up's side effects (capture itself executes nothing)
                 for b, saved in buffers:
@@ -157,3 +171,60 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+
+class BucketedTrainStep:
+    """GraphedTrainStep for batches whose sequence length varies from step to step.
+
+    The reference pads every text batch to ITS longest sentence (`padding="longest"`, models/bdetr.py:170), so the token
+    dimension L changes per batch while CUDA graphs need fixed shapes.  This wrapper keeps one captured step per LENGTH
+    BUCKET (L rounded up to a multiple of `multiple`, default 16: 32, 48, 64, 80, ...), captured lazily on first use, and
+    pads the listed inputs up to the bucket before every replay:
+
+        step = BucketedTrainStep(model, loss_fn, fg, pad={2: (1, 0.0), 3: (1, True)})   # input 2: text (B, L, E) padded
+        loss = step(*inputs)                                                           # with zeros, input 3: its
+                                                                                       # key-padding mask padded with True
+
+    `pad` maps input index -> (dimension that carries L, fill value).  Padded positions must be marked as padding in the
+    mask the model already takes (fill value True above), so they are ignored as attention keys; what the model outputs
+    AT padded positions is garbage by construction (as for the reference's own padded tokens) and `loss_fn` must not
+    read it — the reference's losses mask by the same attention mask.  All buckets share the model, the FlatGradients
+    bucket and therefore the parameters; BatchNorm buffers and the dropout epoch are protected from the warm-up steps of
+    a late capture exactly as in GraphedTrainStep."""
+
+    def __init__(self, model, loss_fn, flat_grads, pad, multiple=16, max_buckets=8):
+        self.model, self.loss_fn, self.flat_grads = model, loss_fn, flat_grads
+        self.pad = dict(pad)
+        self.multiple = int(multiple)
+        self.max_buckets = int(max_buckets)
+        self.steps = {}  # bucket length -> GraphedTrainStep
+
+    def bucket_of(self, length):
+        return ((int(length) + self.multiple - 1) // self.multiple) * self.multiple
+
+    def _padded(self, inputs, bucket):
+        out = list(inputs)
+        for i, (dim, fill) in self.pad.items():
+            t = out[i]
+            cur = t.size(dim)
+            if cur == bucket:
+                continue
+            shape = list(t.shape)
+            shape[dim] = bucket
+            p = torch.full(shape, fill, dtype=t.dtype, device=t.device)
+            p.narrow(dim, 0, cur).copy_(t)
+            out[i] = p
+        return out
+
+    def __call__(self, *inputs):
+        lengths = {inputs[i].size(dim) for i, (dim, _) in self.pad.items()}
+        if len(lengths) != 1:
+            raise RuntimeError("BucketedTrainStep: the padded inputs disagree on the sequence length")
+        bucket = self.bucket_of(lengths.pop())
+        padded = self._padded(inputs, bucket)
+        step = self.steps.get(bucket)
+        if step is None:
+            if len(self.steps) >= self.max_buckets:
+                raise RuntimeError(f"BucketedTrainStep: more than {self.max_buckets} length buckets in use")
+            step = self.steps[bucket] = GraphedTrainStep(self.model, self.loss_fn, padded, self.flat_grads)
+        return step(*padded)
