@@ -396,6 +396,20 @@ def extra_legs(args, dev, world, rank, inputs, host, step_ms):
         del step_d, st_d
     except Exception as e:  # noqa: BLE001
         out["dropout_0.1"] = {"error": repr(e)[:200]}
+    # ---- the reference's published operating point is batch 12 per GPU (scripts/train_scanrefer.sh:7): the same step
+    # at B = 12 with its peak memory (the SA stage keeps its pre-activations for the backward pass: 1.9 GB at B = 8) ----
+    if world == 1:
+        try:
+            torch.cuda.reset_peak_memory_stats(dev)
+            in12 = [t.to(dev) for t in hotpath.synthetic_inputs(12, N_POINTS, L_TEXT, D_BOXES, K_QUERIES, seed=100)]
+            step12, st12 = build_train_step(dev, world, rank, 0.0, in12)
+            ms = kn.time_ms(step12, 3, max(5, args.steps // 2))
+            out["batch_12"] = {"ms_per_step": ms, "value": 12 / (ms * 1e-3), "unit": "scenes/s",
+                               "peak_memory_GB": torch.cuda.max_memory_allocated(dev) / 1e9}
+            st12.clear()
+            del step12, st12, in12
+        except Exception as e:  # noqa: BLE001
+            out["batch_12"] = {"error": repr(e)[:200]}
     if world > 1 and rank != 0:
         return out
 

@@ -53,6 +53,8 @@ PROTOTYPES = {
                                     ctypes.c_uint, _vp, _vp]),
     "eda_dropout_mask": (_c_int, [ctypes.c_uint, _vp, _c_float, ctypes.c_longlong, _c_int, ctypes.c_uint, ctypes.c_uint,
                                   _vp, _vp]),
+    "eda_dropout_apply": (_c_int, [_vp, ctypes.c_uint, _vp, _c_float, ctypes.c_longlong, _c_int, ctypes.c_uint, ctypes.c_uint,
+                                   _vp, _vp]),
     "eda_debug_timestamps": (_c_int, [_vp, _c_int]),
     "eda_debug_timestamps_attn": (_c_int, [_vp, _c_int]),
     "eda_attention_forward": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,

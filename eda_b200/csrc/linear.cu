@@ -626,6 +626,20 @@ __global__ void dropout_mask_kernel(uint32_t seed_base, uint32_t thresh, long lo
   }
 }
 
+// nn.Dropout as its own pass (after a BatchNorm + ReLU apply, where no GEMM epilogue is available to carry it): same
+// counter-based decision as above, out = keep ? x / (1 - p) : 0
+__global__ void dropout_apply_kernel(const float *__restrict__ x, uint32_t seed_base, uint32_t thresh, float scale,
+                                     long long rows, int cols, uint32_t a_mul, uint32_t a_add, float *__restrict__ out,
+                                     const uint32_t *seed_epoch) {
+  const uint32_t seed = effective_seed(seed_base, seed_epoch);
+  const long long total = rows * cols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long a = e / cols;
+    const int b = (int)(e - a * cols);
+    out[e] = dropout_keep(seed, (uint32_t)a * a_mul + a_add, (uint32_t)b, thresh) ? __ldg(x + e) * scale : 0.f;
+  }
+}
+
 inline int kpad_of(int K) { return (K + 7) & ~7; }
 // cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -680,6 +694,19 @@ int eda_dropout_mask(unsigned int seed, const unsigned int *dropout_epoch, float
   dropout_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(seed, dropout_thresh(p), rows, cols, a_mul, a_add, out,
                                                            reinterpret_cast<const uint32_t *>(dropout_epoch));
   return check_launch("dropout_mask_kernel");
+}
+
+int eda_dropout_apply(const float *x, unsigned int seed, const unsigned int *dropout_epoch, float p, long long rows, int cols,
+                      unsigned int a_mul, unsigned int a_add, float *out, void *stream) {
+  using namespace eda;
+  if (rows < 0 || cols < 0 || p < 0.f || p >= 1.f) return EDA_ERR_INVALID_ARGUMENT;
+  if (rows == 0 || cols == 0) return EDA_OK;
+  if (!x || !out) return EDA_ERR_INVALID_ARGUMENT;
+  const long long total = rows * cols;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  dropout_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, seed, dropout_thresh(p), 1.0f / (1.0f - p), rows, cols, a_mul,
+                                                            a_add, out, reinterpret_cast<const uint32_t *>(dropout_epoch));
+  return check_launch("dropout_apply_kernel");
 }
 
 size_t eda_linear_packed_floats(int N, int K) {

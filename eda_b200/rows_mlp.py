@@ -32,10 +32,15 @@ class Layer:
     """One layer of the chain: `weight` (N, K[, 1[, 1]]) and optional `bias` parameters, optional BatchNorm module
     (`bn`), optional ReLU.  `owner` / `name` key the packed-weight cache."""
 
-    def __init__(self, weight, bias, bn, relu, owner, name):
+    def __init__(self, weight, bias, bn, relu, owner, name, dropout=None):
         self.weight, self.bias, self.bn, self.relu, self.owner, self.name = weight, bias, bn, relu, owner, name
+        self.dropout = dropout  # nn.Dropout applied to this layer's output (after the ReLU), or None
         if bn is not None and not relu:
             raise RuntimeError("eda_b200.rows_mlp: BatchNorm without ReLU is not on the path")
+
+    def drop_p(self):
+        d = self.dropout
+        return float(d.p) if (d is not None and d.training and d.p > 0) else 0.0
 
 
 def _w2d(w):
@@ -92,11 +97,34 @@ def bn_backward_reduce(bn, stats, count):
     return stats, red.total_count(count), local
 
 
-def _linear(x, W, bias, relu, owner, name, scale=None):
+def _linear(x, W, bias, relu, owner, name, scale=None, dropout=None):
     N, K = W.shape
     packed = ops.pack_weight(W, scale=scale, cache_key=(owner, name) if owner is not None else None)
-    (y,) = ops.linear_raw([dict(x=x, w_packed=packed, bias=bias)], K, N, relu=relu)
+    (y,) = ops.linear_raw([dict(x=x, w_packed=packed, bias=bias)], K, N, relu=relu, dropout=dropout)
     return y
+
+
+def _padded(L, W, bias):
+    """Output widths the tcgen05 GEMM does not take (not a multiple of 16: the 3-channel centre / size heads, the
+    1-channel objectness logit) run zero-padded to the next multiple of 16; the extra columns are dropped again."""
+    N, K = W.shape
+    N16 = (N + 15) // 16 * 16
+    Wp = torch.zeros((N16, K), dtype=torch.float32, device=W.device)
+    Wp[:N] = W
+    bp = None
+    if bias is not None:
+        bp = torch.zeros(N16, dtype=torch.float32, device=W.device)
+        bp[:N] = bias
+    return Wp, bp
+
+
+def _dropout_apply(y, p, seed, epoch):
+    out = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        rc = _lib.load().eda_dropout_apply(_p(y), int(seed), _p(epoch), float(p), y.size(0), y.size(1), 1, 0, _p(out),
+                                           ops._stream(y.device))
+    _chk(rc, "dropout_apply")
+    return out
 
 
 def _dgrad(dz, W, owner, name):
@@ -153,15 +181,21 @@ class _RowsMLPFn(torch.autograd.Function):
                 N = W.size(0)
                 bias = L.bias.detach() if L.bias is not None else None
                 bn = L.bn
+                pdrop = L.drop_p()
+                drop = (pdrop, ops.new_seed(), ops.epoch_of(L.owner)) if pdrop > 0 else None
                 if bn is None:
-                    y = _linear(a, W, bias, L.relu, L.owner, L.name)
-                    saved.append((a, None, y if L.relu else None, None))
+                    if N % 16:
+                        Wp, bp = _padded(L, W, bias)
+                        y = _linear(a, Wp, bp, L.relu, None, None, dropout=drop)[:, :N].contiguous()
+                    else:
+                        y = _linear(a, W, bias, L.relu, L.owner, L.name, dropout=drop)
+                    saved.append((a, None, y if L.relu else None, None, drop))
                     a = y
                     continue
                 if not bn.training and not need_grad:
                     # inference: running statistics folded into the GEMM (scale into the packed weight, shift as bias)
                     packed, shift = _folded(L, W, bias, bn, dev)
-                    (a,) = ops.linear_raw([dict(x=a, w_packed=packed, bias=shift)], W.size(1), N, relu=True)
+                    (a,) = ops.linear_raw([dict(x=a, w_packed=packed, bias=shift)], W.size(1), N, relu=True, dropout=drop)
                     saved.append(None)
                     continue
                 z = _linear(a, W, bias, False, L.owner, L.name)
@@ -173,7 +207,9 @@ class _RowsMLPFn(torch.autograd.Function):
                     scale, shift, mi = bn_scale_shift(dev, None, 0.0, bn, N, False, want_stats=True)
                 y = torch.empty_like(z)
                 _chk(lib.eda_bn_relu_apply(_p(z), _p(scale), _p(shift), R, N, _p(y), ops._stream(dev)), "bn_relu_apply")
-                saved.append((a, z, None, (scale, shift, mi, bool(bn.training))))
+                if drop is not None:
+                    y = _dropout_apply(y, *drop)  # post-dropout activation: > 0 exactly where the unit was active and kept
+                saved.append((a, z, y if drop is not None else None, (scale, shift, mi, bool(bn.training)), drop))
                 a = y
         ctx.layers = layers
         ctx.saved = saved if need_grad else None
@@ -199,12 +235,21 @@ class _RowsMLPFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             for li in range(len(layers) - 1, -1, -1):
                 L = layers[li]
-                a_in, z, y, bnstate = saved[li]
+                a_in, z, y, bnstate, drop = saved[li]
                 W = _w2d(L.weight.detach())
                 N, K = W.shape
                 R = g.size(0)
+                pad = bnstate is None and N % 16 != 0
+                if pad:  # zero-padded output columns (see _padded): their gradient is zero
+                    Wp, _ = _padded(L, W, None)
+                    g16 = torch.zeros((R, Wp.size(0)), dtype=torch.float32, device=dev)
+                    g16[:, :N] = g
+                    g, own = g16, True
                 if bnstate is not None:
                     scale, shift, mi, batch = bnstate
+                    if drop is not None:  # gradient through dropout o ReLU from the saved post-dropout activation
+                        g = ops.relu_backward(g, y, 1.0 / (1.0 - drop[0]))
+                        own = True
                     if not own:
                         g = g.clone()
                     stats = torch.zeros(2 * N, dtype=torch.float32, device=dev)
@@ -219,7 +264,7 @@ class _RowsMLPFn(torch.autograd.Function):
                     dz = g
                     grads[4 * li + 2], grads[4 * li + 3] = local[N:], local[:N]   # d gamma = sum dy zhat, d beta = sum dy
                 elif L.relu:
-                    dz = ops.relu_backward(g, y, 1.0)
+                    dz = ops.relu_backward(g, y, 1.0 / (1.0 - drop[0]) if drop is not None else 1.0)
                 else:
                     dz = g
                 # weight / bias gradients: straight into the parameters' own buffers when a FlatGradients bucket owns
@@ -227,7 +272,13 @@ class _RowsMLPFn(torch.autograd.Function):
                 gw, gb = ctx.gbufs[4 * li], ctx.gbufs[4 * li + 1]
                 has_b = L.bias is not None
                 wants_w, wants_b = ctx.needs_input_grad[2 + 4 * li], has_b and ctx.needs_input_grad[3 + 4 * li]
-                if wants_w or wants_b:
+                if pad and (wants_w or wants_b):
+                    dW16 = torch.zeros(tuple(Wp.shape), dtype=torch.float32, device=dev)
+                    db16 = torch.zeros(Wp.size(0), dtype=torch.float32, device=dev) if has_b else None
+                    _wgrad(dz, a_in, Wp, dW16, db16)
+                    grads[4 * li] = dW16[:N].reshape(L.weight.shape)
+                    grads[4 * li + 1] = db16[:N] if has_b else None
+                elif wants_w or wants_b:
                     fused = gw is not None and (not has_b or gb is not None) and K % 4 == 0 and N % 4 == 0
                     if fused:
                         ops.wgrad_side([dict(dy=dz, x=a_in, dw=_w2d(gw), db=gb if has_b else None)], N, K)
@@ -239,7 +290,7 @@ class _RowsMLPFn(torch.autograd.Function):
                         grads[4 * li] = dW.view(L.weight.shape)
                         grads[4 * li + 1] = db
                 if li > 0 or ctx.needs_input_grad[1]:
-                    g = _dgrad(dz, W, L.owner, L.name)
+                    g = _dgrad(dz, Wp, None, None) if pad else _dgrad(dz, W, L.owner, L.name)
                     own = True
                     if li == 0:
                         dx = g

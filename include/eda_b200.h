@@ -337,6 +337,11 @@ EDA_API int eda_relu_backward(const float *dy, const float *y, float scale, long
  * attention: a_mul = 1, a_add = 0, rows = B*H*Nq (row (b*H + h)*Nq + q), cols = Nk. */
 EDA_API int eda_dropout_mask(unsigned int seed, const unsigned int *dropout_epoch, float p, long long rows, int cols,
                              unsigned int a_mul, unsigned int a_add, float *out, void *stream);
+/* nn.Dropout as a stand-alone pass with the same decision function (used after a BatchNorm + ReLU apply, where no GEMM
+ * epilogue carries it: ThreeLayerMLP of the prediction heads, models/modules.py:88-106): out = keep ? x / (1 - p) : 0,
+ * element (a, b) hashed as (a * a_mul + a_add, b) like eda_dropout_mask. */
+EDA_API int eda_dropout_apply(const float *x, unsigned int seed, const unsigned int *dropout_epoch, float p, long long rows,
+                              int cols, unsigned int a_mul, unsigned int a_add, float *out, void *stream);
 /* Dropout epoch: every dropout-applying entry point (forward and backward) takes `dropout_epoch`, an optional device
  * word whose value the kernel adds to dropout_seed when it RUNS (NULL = off).  A CUDA graph of a training step freezes
  * the host-drawn seeds; with an epoch word that a captured device op increments once per step, every replay still draws

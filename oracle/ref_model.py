@@ -8,9 +8,10 @@ Two "flavours" of the same, unmodified reference files can live side by side in 
                            `pointnet2._ext` bound to `ext`: the reference's compiled CUDA extension (oracle/_ref, the
                            R-GPU baseline) or the C port (oracle/pointnet2_oracle, the CPU baseline — the reference has
                            no CPU implementation of `_ext`, pointnet2/_ext_src/src/sampling.cpp:87)
-  load("eda")              the SAME unmodified models/bdetr.py and models/modules.py, with this repo's modules swapped in
-                           for pointnet2/* , models/backbone_module.py and models/encoder_decoder_layers.py exactly as
-                           INTEGRATION.md sections 2-3 describe (the drop-in)
+  load("eda")              the SAME unmodified models/bdetr.py, with this repo's modules swapped in for pointnet2/*,
+                           models/backbone_module.py, models/encoder_decoder_layers.py and (heads=True) models/modules.py
+                           exactly as INTEGRATION.md sections 2-3 describe (the drop-in); heads=False keeps the
+                           reference's own models/modules.py
 
 Files come from /root/reference when it exists (build container), else from the sourceless bytecode
 oracle/build_ref.py left in oracle/_ref/pyref (GPU box).  models/__init__.py is deliberately not executed (it pulls in
@@ -78,8 +79,8 @@ class Flavour:
     """Attribute bag: bdetr, modules, backbone_module, encoder_decoder_layers, pointnet2_modules, pointnet2_utils."""
 
 
-def load(flavour, ext=None):
-    key = (flavour, id(ext))
+def load(flavour, ext=None, heads=True):
+    key = (flavour, id(ext), bool(heads))
     if key in _cache:
         return _cache[key]
     rd = ref_dir()
@@ -116,6 +117,9 @@ def load(flavour, ext=None):
                 sys.modules[f"pointnet2.{name}"] = mod
             sys.modules["models.backbone_module"] = eda_b200.backbone_module
             sys.modules["models.encoder_decoder_layers"] = eda_b200.encoder_decoder_layers
+            if heads:  # the query-generation / prediction-head modules as well
+                import eda_b200.modules
+                sys.modules["models.modules"] = eda_b200.modules
         else:
             raise ValueError(flavour)
         bdetr = importlib.import_module("models.bdetr")
