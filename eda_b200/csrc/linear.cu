@@ -71,6 +71,11 @@ struct LinParams {
   float eps;
   uint32_t tmem_cols, stage_bytes;
   int nstages, prefetch;  // ring depth in use and how many blocks the staging warps run ahead (nstages - 2)
+  int sub;                // 32-wide K sub-blocks per ring stage (1..3; > 1 only when every problem's A tiles come by TMA): a
+                          // stage then carries 8 - 24 MMAs per commit instead of 4 - 8 — the tensor pipe needs ~400 cycles
+                          // to fill and drain around every commit (eda_selftest_umma_rate), so few fat stages beat many
+                          // thin ones
+  uint32_t a_bytes;       // sub * 16 KB: offset of the W block inside a stage
   int ts_hack;            // timing experiment only (EDA_LIN_TSHACK=1): A operand read from TMEM (garbage values)
   uint32_t drop_thresh, drop_seed;  // output dropout (after bias / ReLU, before residual): thresh 0 = off
   const uint32_t *seed_epoch;       // optional device word added to drop_seed (eda_dropout_set_epoch)
@@ -177,7 +182,8 @@ linear_kernel(const __grid_constant__ LinParams p) {
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tbase = tmem_slot;
-  const int nkb = (p.Kpad + kKBlock - 1) / kKBlock;
+  const int KB = kKBlock * p.sub;                 // K columns per ring stage
+  const int nkb = (p.Kpad + KB - 1) / KB;
   LIN_TS(1);
 
   if (warp == kWorkerWarps + 1) {
@@ -188,21 +194,24 @@ linear_kernel(const __grid_constant__ LinParams p) {
       int slot = 0;
       uint32_t round = 0;
       for (int kb = 0; kb < nkb; ++kb, slot = (slot + 1 == p.nstages) ? 0 : slot + 1, round ^= (slot == 0) ? 1u : 0u) {
-        const int kcnt = min(kKBlock, p.Kpad - kb * kKBlock);
+        const int kcnt = min(KB, p.Kpad - kb * KB);
         const uint32_t bytes = (uint32_t)kcnt * (uint32_t)N * 4u;
         mbar_wait(&empty[slot], round ^ 1u);
-        if (pr.tma) {  // A block kb: one box of 32 columns x 128 rows, out-of-range parts zero-filled
+        if (pr.tma) {  // A: one box of 32 columns x 128 rows per sub-block, out-of-range parts zero-filled
           if (p.ts_hack & 2) {
             mbar_arrive(&full_a[slot]);  // timing experiment: no A traffic
           } else {
-            mbar_arrive_expect_tx(&full_a[slot], (uint32_t)kTileBytes);
-            tma_load_2d(smem_raw + (size_t)slot * p.stage_bytes, &p.tmap[pi], kb * kKBlock, tile * kRows, &full_a[slot]);
+            const int nsub = (kcnt + kKBlock - 1) / kKBlock;
+            mbar_arrive_expect_tx(&full_a[slot], (uint32_t)(nsub * kTileBytes));
+            for (int j = 0; j < nsub; ++j)
+              tma_load_2d(smem_raw + (size_t)slot * p.stage_bytes + (size_t)j * kTileBytes, &p.tmap[pi],
+                          kb * KB + j * kKBlock, tile * kRows, &full_a[slot]);
           }
         }
         if (p.ts_hack & 4) { mbar_arrive(&full_w[slot]); continue; }  // timing experiment: no W traffic
         mbar_arrive_expect_tx(&full_w[slot], bytes);
-        unsigned char *wdst = smem_raw + (size_t)slot * p.stage_bytes + kABytes;
-        const float *wsrc = pr.w + (size_t)kb * kKBlock * Nf;  // packed: [k block][16-byte chunk][Nf columns] float4
+        unsigned char *wdst = smem_raw + (size_t)slot * p.stage_bytes + p.a_bytes;
+        const float *wsrc = pr.w + (size_t)kb * KB * Nf;  // packed: [16-byte chunk of K][Nf columns] float4, K ascending
         if (p.S == 1) {
           bulk_g2s(wdst, wsrc, bytes, &full_w[slot]);
         } else {
@@ -230,30 +239,34 @@ linear_kernel(const __grid_constant__ LinParams p) {
       for (int st = 0; st < kStages; ++st) {
         const uint32_t ab = smem_u32(smem_raw + (size_t)st * p.stage_bytes);
         adesc0[st] = umma::smem_desc_swizzled(ab, 16u, 1024u, 2u);
-        bdesc0[st] = umma::smem_desc_kmajor_noswizzle(ab + kABytes, lbo_w, 128u);
+        bdesc0[st] = umma::smem_desc_kmajor_noswizzle(ab + p.a_bytes, lbo_w, 128u);
       }
       const uint64_t a_step = 32u >> 4, b_step = (uint64_t)((2u * lbo_w) >> 4), b_half = (uint64_t)(((uint32_t)n_a * 16u) >> 4);
+      const uint64_t a_sub = (uint64_t)kTileBytes >> 4;  // next 32-wide sub-block of A inside the stage
       int slot = 0;
       uint32_t par = 0;
       for (int kb = 0; kb < nkb; ++kb, slot = (slot + 1 == p.nstages) ? 0 : slot + 1, par ^= (slot == 0) ? 1u : 0u) {
-        const int kcnt = min(kKBlock, p.Kpad - kb * kKBlock);
-        mbar_wait(&a_ready[slot], par);
+        const int kcnt = min(KB, p.Kpad - kb * KB);
+        if (!(p.ts_hack & 16)) mbar_wait(&a_ready[slot], par);  // (timing experiment 16: issue without waiting)
         if (blockIdx.x == 0 && kb < 10) g_lin_ts[32 + 3 * kb] = clock64();      // [32 + 3 kb] A block kb staged
-        mbar_wait(&full_w[slot], par);
+        if (!(p.ts_hack & 16)) mbar_wait(&full_w[slot], par);
         if (blockIdx.x == 0 && kb < 10) g_lin_ts[33 + 3 * kb] = clock64();      // [33 + 3 kb] W block kb landed
         umma::fence_after_thread_sync();
         // A: K-major SWIZZLE_128B (rows of 128 B, 8-row atoms 1024 B apart); +32 B per 8-wide k step
-        uint64_t adesc = adesc0[slot], b0 = bdesc0[slot];
-        const int nks = kcnt / 8;
-        const bool dbg = blockIdx.x == 0 && kb == 3;
+        uint64_t b0 = bdesc0[slot];
+        const bool dbg = blockIdx.x == 0 && kb == 1;
         if (dbg) g_lin_ts[120] = clock64();  // after the fence
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-          umma::mma_tf32_ss(tbase, adesc, b0, idesc_a, acc);
-          if (n_b > 0) umma::mma_tf32_ss(tbase + (uint32_t)n_a, adesc, b0 + b_half, idesc_b, acc);
-          adesc += a_step;
-          b0 += b_step;
-          if (dbg && ks < 4) g_lin_ts[121 + ks] = clock64();  // after K step ks
+        for (int k0 = 0, j = 0; k0 < kcnt; k0 += kKBlock, ++j) {  // sub-blocks of the stage
+          uint64_t adesc = adesc0[slot] + (uint64_t)j * a_sub;
+          const int nks = min(kKBlock, kcnt - k0) / 8;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t acc = (kb > 0 || k0 > 0 || ks > 0) ? 1u : 0u;
+            umma::mma_tf32_ss(tbase, adesc, b0, idesc_a, acc);
+            if (n_b > 0) umma::mma_tf32_ss(tbase + (uint32_t)n_a, adesc, b0 + b_half, idesc_b, acc);
+            adesc += a_step;
+            b0 += b_step;
+            if (dbg && j == 0 && ks < 4) g_lin_ts[121 + ks] = clock64();  // after K step ks
+          }
         }
         umma::mma_commit(&empty[slot]);
         if (dbg) g_lin_ts[125] = clock64();  // after the commit
@@ -300,6 +313,63 @@ linear_kernel(const __grid_constant__ LinParams p) {
     for (int kb = 0; kb < nkb; ++kb, slot = (slot + 1 == p.nstages) ? 0 : slot + 1, spar ^= (slot == 0) ? 1u : 0u) {
 #define STG_TS(j) do { if (blockIdx.x == 0 && tid == 0 && kb < 9) g_lin_ts[64 + 6 * kb + (j)] = clock64(); } while (0)
       STG_TS(0);
+      if (tma) {
+        // ---- TMA-fed stage (one to three 32-wide sub-blocks): wait for the boxes, then "+ pos" and tf32 rounding of
+        // the chunks this thread owns in every sub-block, in place
+        const int kcnt = min(KB, p.Kpad - kb * KB);
+        const int nsub = (kcnt + kKBlock - 1) / kKBlock;
+        float4 pq[3][kOwn];
+        if (pr.pos) {  // issued before the wait: their latency hides behind the TMA transfer
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (j < nsub) {
+              const int k = kb * KB + j * kKBlock + cj * 4;
+#pragma unroll
+              for (int i = 0; i < kOwn; ++i) {
+                const int r = i * kRowStep + cr0;
+                const bool in = (row0 + r < pr.rows) && k < K;
+                pq[j][i] = in ? __ldg(reinterpret_cast<const float4 *>(pr.pos + (size_t)(row0 + r) * K + k))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+          }
+        }
+        STG_TS(1);
+        mbar_wait(&full_a[slot], spar);
+        STG_TS(2);
+        if (!(p.ts_hack & 8)) {
+          unsigned char *sA0 = smem_raw + (size_t)slot * p.stage_bytes;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (j < nsub) {
+              unsigned char *sA = sA0 + (size_t)j * kTileBytes;
+              float4 v[kOwn];
+#pragma unroll
+              for (int i = 0; i < kOwn; ++i) {
+                const int r = i * kRowStep + cr0;
+                const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cj ^ (r & 7)) << 4);
+                v[i] = *reinterpret_cast<const float4 *>(sA + off);
+                if (pr.pos) {
+                  v[i].x += pq[j][i].x; v[i].y += pq[j][i].y; v[i].z += pq[j][i].z; v[i].w += pq[j][i].w;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < kOwn; ++i) {
+                const int r = i * kRowStep + cr0;
+                const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cj ^ (r & 7)) << 4);
+                *reinterpret_cast<float4 *>(sA + off) = tf32x4(v[i]);
+              }
+            }
+          }
+        }
+        STG_TS(3);
+        umma::fence_proxy_async_smem();
+        STG_TS(4);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[slot]);
+        STG_TS(5);
+        continue;
+      }
       issue_block(kb + p.prefetch);
       STG_TS(1);
       // "+ pos" for block kb comes straight from global memory (the same 16-byte chunks this thread copied of x): the
@@ -314,11 +384,7 @@ linear_kernel(const __grid_constant__ LinParams p) {
           pq[i] = in ? __ldg(reinterpret_cast<const float4 *>(pr.pos + (size_t)(row0 + r) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      if (tma) {
-        mbar_wait(&full_a[slot], spar);  // block kb has landed (TMA)
-      } else {
-        if (p.prefetch == 2) umma::cp_async_wait<2>(); else umma::cp_async_wait<1>();  // block kb has landed (own copies)
-      }
+      if (p.prefetch == 2) umma::cp_async_wait<2>(); else umma::cp_async_wait<1>();  // block kb has landed (own copies)
       STG_TS(2);
       unsigned char *sA = smem_raw + (size_t)slot * p.stage_bytes;
       if (vec && (p.ts_hack & 8)) {
@@ -789,9 +855,30 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   // stage = A tile + W block, padded to 1024 bytes (SWIZZLE_128B atoms must stay 1024-aligned).  Four stages (the
   // staging warps then run two K blocks ahead of the MMAs) whenever they fit next to the ~5 KB of static shared memory:
   // N = 288 -> 4 x 52 KB = 208 KB
-  p.stage_bytes = (uint32_t)((kABytes + kKBlock * NS * 4 + 1023) & ~1023);
-  p.nstages = (size_t)4 * p.stage_bytes <= 216 * 1024 ? 4 : 3;
-  p.prefetch = p.nstages - 2;
+  // Wide stages (sub > 1) need every problem's A tiles to come by TMA; the cp.async / unaligned staging paths keep the
+  // 32-wide stages of before.  EDA_LINEAR_SUB forces a width (tests / measurements).
+  bool all_tma = true;
+  for (int i = 0; i < nprobs; ++i) all_tma = all_tma && (p.pr[i].rows == 0 || p.pr[i].tma);
+  static const int sub_env = [] { const char *e = getenv("EDA_LINEAR_SUB"); return e ? atoi(e) : 0; }();
+  p.sub = 1;
+  if (all_tma) {
+    const int nkb32 = (p.Kpad + kKBlock - 1) / kKBlock;
+    for (int sub = 3; sub >= 2; --sub) {
+      if (sub_env && sub != sub_env) continue;
+      const size_t sb = ((size_t)sub * (kTileBytes + kKBlock * NS * 4) + 1023) & ~(size_t)1023;
+      if (2 * sb <= 216 * 1024 && nkb32 >= 2) { p.sub = sub; break; }
+    }
+    if (sub_env == 1) p.sub = 1;
+  }
+  p.a_bytes = (uint32_t)(p.sub * kTileBytes);
+  p.stage_bytes = (uint32_t)((p.a_bytes + p.sub * kKBlock * NS * 4 + 1023) & ~1023);
+  if (p.sub > 1) {
+    p.nstages = (size_t)3 * p.stage_bytes <= 216 * 1024 ? 3 : 2;
+    p.prefetch = 0;  // TMA-fed: the producer runs ahead as far as the ring allows
+  } else {
+    p.nstages = (size_t)4 * p.stage_bytes <= 216 * 1024 ? 4 : 3;
+    p.prefetch = p.nstages - 2;
+  }
   {
     const char *e = getenv("EDA_LIN_TSHACK");
     p.ts_hack = e ? atoi(e) : 0;
