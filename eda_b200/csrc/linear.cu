@@ -261,6 +261,10 @@ linear_kernel(const __grid_constant__ LinParams p) {
           const int nks = min(kKBlock, kcnt - k0) / 8;
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t acc = (kb > 0 || k0 > 0 || ks > 0) ? 1u : 0u;
+            if (p.ts_hack & 32) {  // timing experiment: every MMA reads the same operand addresses
+              umma::mma_tf32_ss(tbase, adesc0[0], bdesc0[0], idesc_a, acc);
+              continue;
+            }
             umma::mma_tf32_ss(tbase, adesc, b0, idesc_a, acc);
             if (n_b > 0) umma::mma_tf32_ss(tbase + (uint32_t)n_a, adesc, b0 + b_half, idesc_b, acc);
             adesc += a_step;

@@ -142,11 +142,18 @@ umma_probe_kernel(int N, int lbo, int sbo, int b_mn, int layout, int start_off, 
 // b_swz != 0: B in SWIZZLE_128B too (rows of 128 bytes), else the chunk-major no-swizzle layout of the packed weights.
 // precomputed != 0: descriptors built once outside the loop (isolates the instruction overhead of the issue loop).
 __global__ void __launch_bounds__(1024, 1)
-umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed, int iters, long long *__restrict__ cycles) {
+umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed_arg, int iters, long long *__restrict__ cycles) {
+  // precomputed_arg: bits 0-7 the mode below; bits 8-19 a second accumulator's column offset (0 = one accumulator):
+  // MMAs then go in pairs sharing A, alternating accumulators and B halves, as the linear kernel does for N > 256;
+  // bits 20-30 the row count of the B tile the MMA's N rows are cut from (LBO = rows * 16 bytes; 0 = N)
+  const int precomputed = precomputed_arg & 255;
+  const uint32_t acc_off = (uint32_t)(precomputed_arg >> 8) & 4095u;
+  const uint32_t b_rows = ((uint32_t)precomputed_arg >> 20) ? ((uint32_t)precomputed_arg >> 20) : (uint32_t)N;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t bar, spin_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ uint64_t adesc_tab[16], bdesc_tab[16];
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) umma::tmem_alloc(&tmem_base_slot, 512);
   if (tid == 0) {
@@ -155,7 +162,7 @@ umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed, int iters, long 
     mbar_fence_init_cluster();
   }
   float *f = reinterpret_cast<float *>(base);
-  for (int i = tid; i < 16384; i += blockDim.x) f[i] = 0.f;  // 64 KB of zeros: operands (values do not matter for timing)
+  for (int i = tid; i < 32768; i += blockDim.x) f[i] = 0.f;  // 128 KB of zeros: operands (values do not matter for timing)
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -163,12 +170,43 @@ umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed, int iters, long 
   const uint32_t tbase = tmem_base_slot;
   if (tid == 0) {
     const uint32_t idesc = umma::idesc_tf32(128, N);
-    const uint32_t a_addr = smem_u32(base), b_addr = smem_u32(base) + 16384u;
-    const uint32_t lbo_w = (uint32_t)N * 16u;
+    // precomputed == 2: every MMA reads FRESH shared-memory addresses (16 distinct A K-steps over 64 KB, as many B
+    // K-steps as fit into 64 KB) — what a real K loop does; the other modes cycle through 4 K-steps of one tile
+    const bool fresh = precomputed == 2;
+    const uint32_t a_addr = smem_u32(base), b_addr = smem_u32(base) + (fresh ? 65536u : 16384u);
+    const uint32_t lbo_w = b_rows * 16u;
+    const uint32_t b_swz_tile = ((uint32_t)N * 128u + 1023u) & ~1023u;
+    const uint32_t b_steps = !fresh ? 4u : b_swz ? 4u * (65536u / b_swz_tile) : 65536u / (2u * lbo_w);
     const uint64_t a0 = a_mode == 2 ? umma::smem_desc_swizzled(a_addr, 16u, 1024u, 2u)
                                     : umma::smem_desc_kmajor_noswizzle(a_addr, 128u * 16u, 128u);
     const uint64_t b0 = b_swz ? umma::smem_desc_swizzled(b_addr, 16u, 1024u, 2u)
                               : umma::smem_desc_kmajor_noswizzle(b_addr, lbo_w, 128u);
+    if (fresh) {
+      // descriptor tables built outside the timed loop: the loop itself is two shared-memory loads and the MMA
+      for (uint32_t i = 0; i < 16u; ++i) {
+        const uint32_t ia = acc_off ? (i >> 1) : i, ib = (acc_off ? (i >> 1) : i) % b_steps;
+        const uint32_t half = acc_off ? (i & 1u) * (uint32_t)N * 16u : 0u;
+        adesc_tab[i] = a_mode == 2 ? umma::smem_desc_swizzled(a_addr + (ia >> 2) * 16384u + (ia & 3u) * 32u, 16u, 1024u, 2u)
+                                   : umma::smem_desc_kmajor_noswizzle(a_addr + ia * 2u * 2048u, 128u * 16u, 128u);
+        bdesc_tab[i] = b_swz ? umma::smem_desc_swizzled(b_addr + (ib >> 2) * (((uint32_t)N * 128u + 1023u) & ~1023u) + (ib & 3u) * 32u, 16u, 1024u, 2u)
+                             : umma::smem_desc_kmajor_noswizzle(b_addr + ib * 2u * lbo_w + half, lbo_w, 128u);
+      }
+      const long long t0 = clock64();
+#pragma unroll 4
+      for (int i = 0; i < iters; ++i) {
+        const uint64_t ad = adesc_tab[i & 15], bd = bdesc_tab[i & 15];
+        const uint32_t d = tbase + (uint32_t)(i & 1) * acc_off;
+        if (a_mode == 1) umma::mma_tf32_ts(d, tbase + 288u + (uint32_t)(i & 3) * 8u, bd, idesc, 1u);
+        else umma::mma_tf32_ss(d, ad, bd, idesc, 1u);
+      }
+      const long long t1 = clock64();
+      umma::mma_commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      cycles[2 * blockIdx.x] = t1 - t0;
+      cycles[2 * blockIdx.x + 1] = t2 - t0;
+      mbar_arrive_expect_tx(&spin_bar, 0);
+    } else {
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const uint32_t ks = (uint32_t)(i & 3);
@@ -189,6 +227,7 @@ umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed, int iters, long 
     cycles[2 * blockIdx.x] = t1 - t0;      // issue loop
     cycles[2 * blockIdx.x + 1] = t2 - t0;  // until the last MMA has completed
     mbar_arrive_expect_tx(&spin_bar, 0);   // releases the spinner warps
+    }
   } else if (warp >= 4) {
     // extra warps (blockDim > 128): wait on a shared-memory barrier for the whole measurement, like the staging /
     // producer warps of the GEMM kernels do while the issuer thread works
@@ -229,7 +268,7 @@ extern "C" int eda_selftest_umma_rate(int N, int a_mode, int b_swizzled, int pre
   if (!cycles_device || N < 16 || N > 256 || N % 16 || iters < 1 || ctas < 1 || a_mode < 0 || a_mode > 2 ||
       waiting_warps < 0 || waiting_warps > 28)
     return EDA_ERR_INVALID_ARGUMENT;
-  const size_t smem = 65536 + 1024;
+  const size_t smem = 131072 + 1024;
   EDA_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                "umma rate smem attr");
   umma_rate_kernel<<<ctas, 128 + 32 * waiting_warps, smem, as_stream(stream)>>>(N, a_mode, b_swizzled, precomputed, iters,
