@@ -98,6 +98,7 @@ attention_kernel(const AttnParams p) {
   __shared__ float s_x[2][kRows];  // per-row exchange between the two column halves (max, then sum)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = umma::uniform_warp_index();  // == warp, known warp-uniform to the compiler (MMA issue branches)
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int HD = p.H * D;
   const int nblocks = (p.Nk + kKB - 1) / kKB;
@@ -211,16 +212,21 @@ attention_kernel(const AttnParams p) {
     umma::fence_after_thread_sync();
     ATT_TS(3);
     // ---- S = Q K^T --------------------------------------------------------------------------------
-    if (tid == 0) {
+    // (issue code: the whole of warp 0, converged, warp-uniform values — see umma::mma4_tf32_ss_w)
+    if (warp_u == 0) {
       const uint32_t idesc = umma::idesc_tf32(kRows, nkp);
-      const uint32_t qb = smem_u32(sQ), kb = smem_u32(sK + buf * QC * kKB);
+      const uint64_t ad = umma::smem_desc_kmajor_noswizzle(smem_u32(sQ), kRows * 16u, 128u);
+      const uint64_t bd = umma::smem_desc_kmajor_noswizzle(smem_u32(sK + buf * QC * kKB), kKB * 16u, 128u);
+      constexpr uint32_t a_step = (2u * kRows * 16u) >> 4, b_step = (2u * kKB * 16u) >> 4;
+      constexpr int kSteps = QC / 2, kGroups = kSteps / 4;
 #pragma unroll
-      for (int ks = 0; ks < QC / 2; ++ks) {
-        const uint64_t adesc = umma::smem_desc_kmajor_noswizzle(qb + (uint32_t)ks * 2u * kRows * 16u, kRows * 16u, 128u);
-        const uint64_t bdesc = umma::smem_desc_kmajor_noswizzle(kb + (uint32_t)ks * 2u * kKB * 16u, kKB * 16u, 128u);
-        umma::mma_tf32_ss(tbase, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
-      }
-      umma::mma_commit(&mma_done);
+      for (int g = 0; g < kGroups; ++g)
+        umma::mma4_tf32_ss_w(tbase, umma::desc_lo(ad) + (uint32_t)(4 * g) * a_step, umma::desc_hi(ad), a_step,
+                             umma::desc_lo(bd) + (uint32_t)(4 * g) * b_step, umma::desc_hi(bd), b_step, idesc, g > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 4 * kGroups; ks < kSteps; ++ks)
+        umma::mma_tf32_ss_w(tbase, ad + ks * a_step, bd + ks * b_step, idesc, ks > 0 ? 1u : 0u);
+      umma::mma_commit_w(&mma_done);
     }
     mbar_wait(&mma_done, phase);
     phase ^= 1u;
@@ -296,14 +302,19 @@ attention_kernel(const AttnParams p) {
     umma::fence_after_thread_sync();
     ATT_TS(10);
     // ---- O += P V  (B operand = V^T block, K-major: 4-key units VP*16 bytes apart, dims 16 bytes apart) -----
-    if (tid == 0) {
+    if (warp_u == 0) {
       const uint32_t idesc = umma::idesc_tf32(kRows, Dn);
-      const uint32_t vb = smem_u32(sV + buf * VG * VP);
-      for (int ks = 0; ks < nkp / 8; ++ks) {
-        const uint64_t bdesc = umma::smem_desc_kmajor_noswizzle(vb + (uint32_t)ks * 2u * VP * 16u, VP * 16u, 128u);
-        umma::mma_tf32_ts(tbase + 128u, tbase + (uint32_t)ks * 8u, bdesc, idesc, (blk > 0 || ks > 0) ? 1u : 0u);
-      }
-      umma::mma_commit(&mma_done);
+      const uint64_t bd = umma::smem_desc_kmajor_noswizzle(smem_u32(sV + buf * VG * VP), VP * 16u, 128u);
+      constexpr uint32_t b_step = (2u * VP * 16u) >> 4;
+      const int nsteps = nkp / 8;
+      int ks = 0;
+      for (; ks + 4 <= nsteps; ks += 4)
+        umma::mma4_tf32_ts_w(tbase + 128u, tbase + (uint32_t)ks * 8u, 8u, umma::desc_lo(bd) + (uint32_t)ks * b_step,
+                             umma::desc_hi(bd), b_step, idesc, (blk > 0 || ks > 0) ? 1u : 0u);
+      for (; ks < nsteps; ++ks)
+        umma::mma_tf32_ts_w(tbase + 128u, tbase + (uint32_t)ks * 8u, bd + (uint64_t)((uint32_t)ks * b_step), idesc,
+                            (blk > 0 || ks > 0) ? 1u : 0u);
+      umma::mma_commit_w(&mma_done);
     }
     mbar_wait(&mma_done, phase);
     phase ^= 1u;

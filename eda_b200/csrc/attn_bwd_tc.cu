@@ -90,6 +90,7 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
   __shared__ float s_delta[kRows];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = umma::uniform_warp_index();  // == warp, known warp-uniform to the compiler (MMA issue branches)
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int HD = p.H * D;
   const int Nrows = kKeyRows ? p.Nk : p.Nq, Ncols = kKeyRows ? p.Nq : p.Nk;
@@ -232,23 +233,30 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
     __syncthreads();
     umma::fence_after_thread_sync();
     // ---- S = X1 C1^T -> columns [0,128),  dP = X2 C2^T -> columns [128,256) ---------------------------------------------
-    if (tid == 0) {
+    // (issue code: the whole of warp 0, converged, warp-uniform values, four K steps per statement — umma::mma4_tf32_ss_w)
+    if (warp_u == 0) {
       const uint32_t idesc = umma::idesc_tf32(kRows, ncp);
-      const uint32_t a1 = smem_u32(sX1), a2 = smem_u32(sX2);
-      const uint32_t b1 = smem_u32(sC1 + buf * QC * kCB), b2 = smem_u32(sC2 + buf * QC * kCB);
+      const uint64_t a1 = umma::smem_desc_kmajor_noswizzle(smem_u32(sX1), kRows * 16u, 128u);
+      const uint64_t a2 = umma::smem_desc_kmajor_noswizzle(smem_u32(sX2), kRows * 16u, 128u);
+      const uint64_t b1 = umma::smem_desc_kmajor_noswizzle(smem_u32(sC1 + buf * QC * kCB), kCB * 16u, 128u);
+      const uint64_t b2 = umma::smem_desc_kmajor_noswizzle(smem_u32(sC2 + buf * QC * kCB), kCB * 16u, 128u);
+      constexpr uint32_t a_step = (2u * kRows * 16u) >> 4, b_step = (2u * kCB * 16u) >> 4;
+      constexpr int kSteps = QC / 2, kGroups = kSteps / 4;
 #pragma unroll
-      for (int ks = 0; ks < QC / 2; ++ks) {
-        const uint32_t off = (uint32_t)ks * 2u * kRows * 16u;
-        umma::mma_tf32_ss(tbase, umma::smem_desc_kmajor_noswizzle(a1 + off, kRows * 16u, 128u),
-                          umma::smem_desc_kmajor_noswizzle(b1 + off, kCB * 16u, 128u), idesc, ks > 0 ? 1u : 0u);
-      }
+      for (int g = 0; g < kGroups; ++g)
+        umma::mma4_tf32_ss_w(tbase, umma::desc_lo(a1) + (uint32_t)(4 * g) * a_step, umma::desc_hi(a1), a_step,
+                             umma::desc_lo(b1) + (uint32_t)(4 * g) * b_step, umma::desc_hi(b1), b_step, idesc, g > 0 ? 1u : 0u);
 #pragma unroll
-      for (int ks = 0; ks < QC / 2; ++ks) {
-        const uint32_t off = (uint32_t)ks * 2u * kRows * 16u;
-        umma::mma_tf32_ss(tbase + 128u, umma::smem_desc_kmajor_noswizzle(a2 + off, kRows * 16u, 128u),
-                          umma::smem_desc_kmajor_noswizzle(b2 + off, kCB * 16u, 128u), idesc, ks > 0 ? 1u : 0u);
-      }
-      umma::mma_commit(&mma_done);
+      for (int ks = 4 * kGroups; ks < kSteps; ++ks)
+        umma::mma_tf32_ss_w(tbase, a1 + ks * a_step, b1 + ks * b_step, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g)
+        umma::mma4_tf32_ss_w(tbase + 128u, umma::desc_lo(a2) + (uint32_t)(4 * g) * a_step, umma::desc_hi(a2), a_step,
+                             umma::desc_lo(b2) + (uint32_t)(4 * g) * b_step, umma::desc_hi(b2), b_step, idesc, g > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 4 * kGroups; ks < kSteps; ++ks)
+        umma::mma_tf32_ss_w(tbase + 128u, a2 + ks * a_step, b2 + ks * b_step, idesc, ks > 0 ? 1u : 0u);
+      umma::mma_commit_w(&mma_done);
     }
     mbar_wait(&mma_done, phase);
     phase ^= 1u;
@@ -311,24 +319,31 @@ attention_backward_tc_kernel(const AttnBwdTcParams p) {
     __syncthreads();
     umma::fence_after_thread_sync();
     // ---- second products: A from tensor memory, B = channel-major column blocks ----------------------------------------------
-    if (tid == 0) {
+    if (warp_u == 0) {
       const uint32_t idesc = umma::idesc_tf32(kRows, Dn);
-      const uint32_t tb1 = smem_u32(sT1 + buf * VG * VP), tb2 = smem_u32(sT2 + buf * VG * VP);
-      for (int ks = 0; ks < ncp / 8; ++ks) {
+      const uint64_t tb1 = umma::smem_desc_kmajor_noswizzle(smem_u32(sT1 + buf * VG * VP), VP * 16u, 128u);
+      const uint64_t tb2 = umma::smem_desc_kmajor_noswizzle(smem_u32(sT2 + buf * VG * VP), VP * 16u, 128u);
+      constexpr uint32_t b_step = (2u * VP * 16u) >> 4;
+      const int nsteps = ncp / 8;
+      // key rows:   dk += dS^T Q (A = columns [128,256)),  dv += P'^T dO (A = columns [0,128))
+      // query rows: dq += dS K   (A = columns [0,128))
+      const uint32_t a_first = kKeyRows ? tbase + 128u : tbase;
+      int ks = 0;
+      for (; ks + 4 <= nsteps; ks += 4) {
         const uint32_t acc = (blk > 0 || ks > 0) ? 1u : 0u;
-        const uint32_t off = (uint32_t)ks * 2u * VP * 16u;
-        if (kKeyRows) {
-          // dk += dS^T Q (A = columns [128,256)),  dv += P'^T dO (A = columns [0,128))
-          umma::mma_tf32_ts(tbase + kO1, tbase + 128u + (uint32_t)ks * 8u,
-                            umma::smem_desc_kmajor_noswizzle(tb1 + off, VP * 16u, 128u), idesc, acc);
-          umma::mma_tf32_ts(tbase + kO2, tbase + (uint32_t)ks * 8u,
-                            umma::smem_desc_kmajor_noswizzle(tb2 + off, VP * 16u, 128u), idesc, acc);
-        } else {
-          umma::mma_tf32_ts(tbase + kO1, tbase + (uint32_t)ks * 8u,
-                            umma::smem_desc_kmajor_noswizzle(tb1 + off, VP * 16u, 128u), idesc, acc);
-        }
+        umma::mma4_tf32_ts_w(tbase + kO1, a_first + (uint32_t)ks * 8u, 8u, umma::desc_lo(tb1) + (uint32_t)ks * b_step,
+                             umma::desc_hi(tb1), b_step, idesc, acc);
+        if (kKeyRows)
+          umma::mma4_tf32_ts_w(tbase + kO2, tbase + (uint32_t)ks * 8u, 8u, umma::desc_lo(tb2) + (uint32_t)ks * b_step,
+                               umma::desc_hi(tb2), b_step, idesc, acc);
       }
-      umma::mma_commit(&mma_done);
+      for (; ks < nsteps; ++ks) {
+        const uint32_t acc = (blk > 0 || ks > 0) ? 1u : 0u;
+        umma::mma_tf32_ts_w(tbase + kO1, a_first + (uint32_t)ks * 8u, tb1 + (uint64_t)((uint32_t)ks * b_step), idesc, acc);
+        if (kKeyRows)
+          umma::mma_tf32_ts_w(tbase + kO2, tbase + (uint32_t)ks * 8u, tb2 + (uint64_t)((uint32_t)ks * b_step), idesc, acc);
+      }
+      umma::mma_commit_w(&mma_done);
     }
     mbar_wait(&mma_done, phase);
     phase ^= 1u;

@@ -76,7 +76,8 @@ struct LinParams {
                           // to fill and drain around every commit (eda_selftest_umma_rate), so few fat stages beat many
                           // thin ones
   uint32_t a_bytes;       // sub * 16 KB: offset of the W block inside a stage
-  int ts_hack;            // timing experiment only (EDA_LIN_TSHACK=1): A operand read from TMEM (garbage values)
+  int ts_hack;            // timing experiments only (EDA_LIN_TSHACK bits: 2 no A traffic, 4 no W traffic, 8 no fix-up pass,
+                          // 16 MMAs issued without waiting for operands — results are garbage)
   uint32_t drop_thresh, drop_seed;  // output dropout (after bias / ReLU, before residual): thresh 0 = off
   const uint32_t *seed_epoch;       // optional device word added to drop_seed (eda_dropout_set_epoch)
   float drop_scale;                 // 1 / (1 - p)
@@ -147,6 +148,7 @@ linear_kernel(const __grid_constant__ LinParams p) {
   __shared__ __align__(8) float2 s_stat[kRows];  // per-row (sum, sum of squares) of this CTA's column slice
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = umma::uniform_warp_index();  // == warp, known warp-uniform to the compiler
   LIN_TS(0);
   const int gtile = (int)blockIdx.x / p.S, split = (int)blockIdx.x - gtile * p.S;
   int pi = 0;
@@ -186,7 +188,7 @@ linear_kernel(const __grid_constant__ LinParams p) {
   const int nkb = (p.Kpad + KB - 1) / KB;
   LIN_TS(1);
 
-  if (warp == kWorkerWarps + 1) {
+  if (warp_u == kWorkerWarps + 1) {
     // ---------------- weight producer ----------------------------------------------------------
     if (lane == 0) {
       // ring position as running counters: kb % nstages / kb / nstages by a run-time divisor cost a few hundred cycles
@@ -222,60 +224,58 @@ linear_kernel(const __grid_constant__ LinParams p) {
       }
     }
     if (clustered) cluster_sync_all();  // matches the workers' statistics exchange
-  } else if (warp == kWorkerWarps) {
+  } else if (warp_u == kWorkerWarps) {
     // ---------------- MMA issuer -----------------------------------------------------------------
-    if (lane == 0) {
+    // The WHOLE warp runs this loop, converged, with warp-uniform values (the role branch is on a shuffled warp index,
+    // so the compiler knows): descriptors stay in uniform registers and the four K steps of a 32-wide sub-block go out
+    // from one statement (umma::mma4_tf32_ss_w: one elected lane, two adds per MMA).  Written as `if (lane == 0)` with
+    // per-MMA descriptor arithmetic the same loop cost 160 - 330 cycles per MMA in scalar issue code (vector -> uniform
+    // register moves in an elect / branch "waterfall" around every tcgen05.mma) against 72 for the MMA itself
+    // (eda_selftest_umma_rate, scripts/umma_rate.py).
+    {
       // N split into MMA-sized pieces (multiples of 16, <= 256)
       const int n_a = N <= 256 ? N : ((N / 2 + 15) / 16) * 16;
       const int n_b = N - n_a;
       const uint32_t idesc_a = umma::idesc_tf32(kRows, n_a);
       const uint32_t idesc_b = umma::idesc_tf32(kRows, n_b > 0 ? n_b : 16);
       const uint32_t lbo_w = (uint32_t)N * 16u;
-      // The issue loop runs on ONE thread that shares its scheduler with staging warps: every scalar instruction in it
-      // costs tens of cycles of tensor-pipe idle time.  Descriptors are therefore built once per ring slot; a K step
-      // only adds constants to their (address >> 4) fields: A +32 bytes inside the swizzle atom, B two chunk rows.
-      uint64_t adesc0[kStages], bdesc0[kStages];
-#pragma unroll
-      for (int st = 0; st < kStages; ++st) {
-        const uint32_t ab = smem_u32(smem_raw + (size_t)st * p.stage_bytes);
-        adesc0[st] = umma::smem_desc_swizzled(ab, 16u, 1024u, 2u);
-        bdesc0[st] = umma::smem_desc_kmajor_noswizzle(ab + p.a_bytes, lbo_w, 128u);
-      }
-      const uint64_t a_step = 32u >> 4, b_step = (uint64_t)((2u * lbo_w) >> 4), b_half = (uint64_t)(((uint32_t)n_a * 16u) >> 4);
-      const uint64_t a_sub = (uint64_t)kTileBytes >> 4;  // next 32-wide sub-block of A inside the stage
+      const uint32_t ring0 = smem_u32(smem_raw);
+      const uint64_t ad0 = umma::smem_desc_swizzled(ring0, 16u, 1024u, 2u);
+      const uint64_t bd0 = umma::smem_desc_kmajor_noswizzle(ring0 + p.a_bytes, lbo_w, 128u);
+      const uint32_t a_hi = umma::desc_hi(ad0), b_hi = umma::desc_hi(bd0);
+      // descriptor low words count 16-byte units: a K step is +32 bytes inside A's swizzle atom and two chunk rows of B
+      const uint32_t a_step = 32u >> 4, b_step = (2u * lbo_w) >> 4, b_half = ((uint32_t)n_a * 16u) >> 4;
+      const uint32_t a_sub = (uint32_t)kTileBytes >> 4, stage_step = p.stage_bytes >> 4;
       int slot = 0;
       uint32_t par = 0;
       for (int kb = 0; kb < nkb; ++kb, slot = (slot + 1 == p.nstages) ? 0 : slot + 1, par ^= (slot == 0) ? 1u : 0u) {
         const int kcnt = min(KB, p.Kpad - kb * KB);
         if (!(p.ts_hack & 16)) mbar_wait(&a_ready[slot], par);  // (timing experiment 16: issue without waiting)
-        if (blockIdx.x == 0 && kb < 10) g_lin_ts[32 + 3 * kb] = clock64();      // [32 + 3 kb] A block kb staged
+        if (blockIdx.x == 0 && lane == 0 && kb < 10) g_lin_ts[32 + 3 * kb] = clock64();  // [32 + 3 kb] A block kb staged
         if (!(p.ts_hack & 16)) mbar_wait(&full_w[slot], par);
-        if (blockIdx.x == 0 && kb < 10) g_lin_ts[33 + 3 * kb] = clock64();      // [33 + 3 kb] W block kb landed
+        if (blockIdx.x == 0 && lane == 0 && kb < 10) g_lin_ts[33 + 3 * kb] = clock64();  // [33 + 3 kb] W block kb landed
         umma::fence_after_thread_sync();
-        // A: K-major SWIZZLE_128B (rows of 128 B, 8-row atoms 1024 B apart); +32 B per 8-wide k step
-        uint64_t b0 = bdesc0[slot];
-        const bool dbg = blockIdx.x == 0 && kb == 1;
-        if (dbg) g_lin_ts[120] = clock64();  // after the fence
-        for (int k0 = 0, j = 0; k0 < kcnt; k0 += kKBlock, ++j) {  // sub-blocks of the stage
-          uint64_t adesc = adesc0[slot] + (uint64_t)j * a_sub;
+        uint32_t a_lo = umma::desc_lo(ad0) + (uint32_t)slot * stage_step;
+        uint32_t b_lo = umma::desc_lo(bd0) + (uint32_t)slot * stage_step;
+        for (int k0 = 0; k0 < kcnt; k0 += kKBlock, a_lo += a_sub, b_lo += 4u * b_step) {  // sub-blocks of the stage
           const int nks = min(kKBlock, kcnt - k0) / 8;
-          for (int ks = 0; ks < nks; ++ks) {
-            const uint32_t acc = (kb > 0 || k0 > 0 || ks > 0) ? 1u : 0u;
-            if (p.ts_hack & 32) {  // timing experiment: every MMA reads the same operand addresses
-              umma::mma_tf32_ss(tbase, adesc0[0], bdesc0[0], idesc_a, acc);
-              continue;
+          const uint32_t acc = (kb > 0 || k0 > 0) ? 1u : 0u;
+          if (nks == 4) {
+            umma::mma4_tf32_ss_w(tbase, a_lo, a_hi, a_step, b_lo, b_hi, b_step, idesc_a, acc);
+            if (n_b > 0)
+              umma::mma4_tf32_ss_w(tbase + (uint32_t)n_a, a_lo, a_hi, a_step, b_lo + b_half, b_hi, b_step, idesc_b, acc);
+          } else {  // K tail (Kpad % 32 != 0: the 3- / 6- / 8-wide inputs of the position embeddings)
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)ks * a_step);
+              const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)ks * b_step);
+              umma::mma_tf32_ss_w(tbase, ad, bd, idesc_a, (acc || ks > 0) ? 1u : 0u);
+              if (n_b > 0) umma::mma_tf32_ss_w(tbase + (uint32_t)n_a, ad, bd + b_half, idesc_b, (acc || ks > 0) ? 1u : 0u);
             }
-            umma::mma_tf32_ss(tbase, adesc, b0, idesc_a, acc);
-            if (n_b > 0) umma::mma_tf32_ss(tbase + (uint32_t)n_a, adesc, b0 + b_half, idesc_b, acc);
-            adesc += a_step;
-            b0 += b_step;
-            if (dbg && j == 0 && ks < 4) g_lin_ts[121 + ks] = clock64();  // after K step ks
           }
         }
-        umma::mma_commit(&empty[slot]);
-        if (dbg) g_lin_ts[125] = clock64();  // after the commit
-        if (blockIdx.x == 0 && kb < 10) g_lin_ts[34 + 3 * kb] = clock64();      // [34 + 3 kb] MMAs of block kb issued
-        if (kb == nkb - 1) umma::mma_commit(&mma_done);
+        umma::mma_commit_w(&empty[slot]);
+        if (blockIdx.x == 0 && lane == 0 && kb < 10) g_lin_ts[34 + 3 * kb] = clock64();  // [34 + 3 kb] MMAs of block kb issued
+        if (kb == nkb - 1) umma::mma_commit_w(&mma_done);
       }
     }
     if (clustered) cluster_sync_all();  // matches the workers' statistics exchange
@@ -886,7 +886,6 @@ int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N
   {
     const char *e = getenv("EDA_LIN_TSHACK");
     p.ts_hack = e ? atoi(e) : 0;
-    if ((p.ts_hack & 1) && p.tmem_cols != 512u) p.ts_hack &= ~1;
   }
   size_t smem = (size_t)p.nstages * p.stage_bytes;
   const size_t out_tile = (size_t)kRows * (NS + 4) * sizeof(float);

@@ -126,6 +126,7 @@ sa_mlp_kernel(const SaParams p) {
   __shared__ float s_stat[4][2][kMaxC];  // per compute warp: this CTA's partial (sum, sum of squares) of the statistics pass
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = umma::uniform_warp_index();  // == warp, known warp-uniform to the compiler (MMA issue branches)
   const int nlayers_run = p.stats_layer == 0 ? 3 : p.stats_layer;
 
   // ---- one-time setup -----------------------------------------------------------------------
@@ -179,34 +180,40 @@ sa_mlp_kernel(const SaParams p) {
     }
   } else {
     // ================= compute warps: thread = row =================================================
-    uint32_t n = 0;           // ring position; only thread 0 consumes blocks, it persists across tiles
+    uint32_t n = 0;           // ring position; only warp 0 consumes blocks, it persists across tiles
     uint32_t done_phase = 0;  // parity of the next mma_done completion (same sequence in every thread)
     const uint32_t lane_base = (uint32_t)(warp * 32);
     const uint32_t t_r1 = umma::tmem_addr(tbase, lane_base, 0);    // region 1: columns [0,128)
     const uint32_t t_r2 = umma::tmem_addr(tbase, lane_base, 128);  // region 2: columns [128,256)
     const long long MS = (long long)p.M * p.S;
 
-    // Thread 0: D[128 x nblk] at column d_col (+)= A[128 x (k_hi-k_lo)] (TMEM columns a_col...) * W-blocks^T.
-    // `k_abs0` is the absolute k of the first column (accumulate unless it is the very first k-step).
+    // Warp 0 (all lanes, converged; one elected lane issues — umma::mma4_tf32_ts_w): D[128 x nblk] at column d_col (+)=
+    // A[128 x (k_hi-k_lo)] (TMEM columns a_col...) * W-blocks^T.  Accumulates unless it is the very first k-step.
     auto issue_blocks = [&](uint32_t d_col, uint32_t a_col, int k_lo, int k_hi, int nblk, bool commit_done) {
       umma::fence_after_thread_sync();
       const uint32_t idesc = umma::idesc_tf32(kRows, nblk);
       const uint32_t lbo = (uint32_t)nblk * 16u;
+      const uint32_t b_step = (2u * lbo) >> 4;
+      const uint64_t bd0 = umma::smem_desc_kmajor_noswizzle(smem_u32(ring), lbo, 128u);
       for (int k0 = k_lo; k0 < k_hi; k0 += kKBlock) {
         const int kcnt = min(kKBlock, k_hi - k0);
         const uint32_t slot = n % kRing;
         mbar_wait(&full_bar[slot], (n / kRing) & 1u);
         umma::fence_after_thread_sync();
-        const uint32_t wbase = smem_u32(reinterpret_cast<unsigned char *>(ring) + (size_t)slot * kSlotBytes);
-        for (int ks = 0; ks < kcnt / 8; ++ks) {
-          const uint64_t bdesc = umma::smem_desc_kmajor_noswizzle(wbase + (uint32_t)ks * 2u * lbo, lbo, 128u);
-          umma::mma_tf32_ts(tbase + d_col, tbase + a_col + (uint32_t)(k0 - k_lo + ks * 8), bdesc, idesc,
-                            (k0 > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma::mma_commit(&empty_bar[slot]);  // slot reusable once these MMAs have read it
+        const uint32_t b_lo = umma::desc_lo(bd0) + slot * (uint32_t)(kSlotBytes >> 4);
+        const uint32_t a_t = tbase + a_col + (uint32_t)(k0 - k_lo);
+        int ks = 0;
+        for (; ks + 4 <= kcnt / 8; ks += 4)
+          umma::mma4_tf32_ts_w(tbase + d_col, a_t + (uint32_t)ks * 8u, 8u, b_lo + (uint32_t)ks * b_step, umma::desc_hi(bd0),
+                               b_step, idesc, (k0 > 0 || ks > 0) ? 1u : 0u);
+        for (; ks < kcnt / 8; ++ks)
+          umma::mma_tf32_ts_w(tbase + d_col, a_t + (uint32_t)ks * 8u,
+                              ((uint64_t)umma::desc_hi(bd0) << 32) | (b_lo + (uint32_t)ks * b_step), idesc,
+                              (k0 > 0 || ks > 0) ? 1u : 0u);
+        umma::mma_commit_w(&empty_bar[slot]);  // slot reusable once these MMAs have read it
         ++n;
       }
-      if (commit_done) umma::mma_commit(&mma_done);
+      if (commit_done) umma::mma_commit_w(&mma_done);
     };
     auto wait_mma_done = [&]() {
       mbar_wait(&mma_done, done_phase);
@@ -326,7 +333,7 @@ sa_mlp_kernel(const SaParams p) {
         }
         umma::tmem_st_wait();
         phase_sync();
-        if (tid == 0) issue_blocks(0u, 128u, c_lo, c_hi, p.Cout[0], true);
+        if (warp_u == 0) issue_blocks(0u, 128u, c_lo, c_hi, p.Cout[0], true);
       }
       wait_mma_done();
 
@@ -336,7 +343,7 @@ sa_mlp_kernel(const SaParams p) {
         // ================= layer 2: A1 = relu(D1 + shift1) in region 1, D2 -> region 2 ===========
         relu_inplace(t_r1, p.Cout[0], s_shift);
         phase_sync();
-        if (tid == 0) issue_blocks(128u, 0u, 0, p.Cout[0], p.Cout[1], true);
+        if (warp_u == 0) issue_blocks(128u, 0u, 0, p.Cout[0], p.Cout[1], true);
         wait_mma_done();
         if (p.stats_layer == 2) {
           take_stats(t_r2, p.Cout[1], s_stat[warp][0], s_stat[warp][1], valid);
@@ -348,7 +355,7 @@ sa_mlp_kernel(const SaParams p) {
           const int halves = n_halves(C3);
           for (int h = 0; h < halves; ++h) {
             const int nblk = min(128, C3 - h * 128);
-            if (tid == 0) issue_blocks(0u, 128u, 0, p.Cout[1], nblk, true);
+            if (warp_u == 0) issue_blocks(0u, 128u, 0, p.Cout[1], nblk, true);
             wait_mma_done();
             if (p.stats_layer == 3) {
               take_stats(t_r1, nblk, s_stat[warp][0] + h * 128, s_stat[warp][1] + h * 128, valid);

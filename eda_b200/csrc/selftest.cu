@@ -146,7 +146,7 @@ umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed_arg, int iters, l
   // precomputed_arg: bits 0-7 the mode below; bits 8-19 a second accumulator's column offset (0 = one accumulator):
   // MMAs then go in pairs sharing A, alternating accumulators and B halves, as the linear kernel does for N > 256;
   // bits 20-30 the row count of the B tile the MMA's N rows are cut from (LBO = rows * 16 bytes; 0 = N)
-  const int precomputed = precomputed_arg & 255;
+  const int precomputed = precomputed_arg & 127;
   const uint32_t acc_off = (uint32_t)(precomputed_arg >> 8) & 4095u;
   const uint32_t b_rows = ((uint32_t)precomputed_arg >> 20) ? ((uint32_t)precomputed_arg >> 20) : (uint32_t)N;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -162,17 +162,57 @@ umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed_arg, int iters, l
     mbar_fence_init_cluster();
   }
   float *f = reinterpret_cast<float *>(base);
-  for (int i = tid; i < 32768; i += blockDim.x) f[i] = 0.f;  // 128 KB of zeros: operands (values do not matter for timing)
+  // 128 KB of operands: zeros, or (mode bit 7) pseudo-random tf32 values in (-1, 1) — real data toggles the datapath
+  for (int i = tid; i < 32768; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + 12345u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    f[i] = (precomputed_arg & 128) ? __uint_as_float(__float_as_uint((float)(int)(h & 0xffffu) * (1.f / 32768.f) - 1.f) & 0xffffe000u) : 0.f;
+  }
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tbase = tmem_base_slot;
+  if (precomputed == 4) {
+    // warp-converged issue loop (umma::mma_tf32_ss_w): all of warp 0 runs it, descriptors by uniform arithmetic, fresh
+    // operand addresses as in mode 2
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // tells the compiler the branch below is warp-uniform
+    if (warp_u == 0) {
+      const uint32_t idesc = umma::idesc_tf32(128, N);
+      const uint32_t a_addr = smem_u32(base), b_addr = smem_u32(base) + 65536u;
+      const uint32_t lbo_w = b_rows * 16u;
+      const uint32_t b_steps = 65536u / (2u * lbo_w);
+      const uint64_t a0 = umma::smem_desc_swizzled(a_addr, 16u, 1024u, 2u);
+      const uint64_t b0 = umma::smem_desc_kmajor_noswizzle(b_addr, lbo_w, 128u);
+      const uint64_t b_step = (uint64_t)((2u * lbo_w) >> 4);
+      const long long t0 = clock64();
+      uint32_t ib = 0;
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t ia = (uint32_t)i & 15u;
+        const uint64_t ad = a0 + (uint64_t)((ia >> 2) * 1024u + (ia & 3u) * 2u);
+        const uint64_t bd = b0 + (uint64_t)ib * b_step;
+        if (a_mode == 1) umma::mma_tf32_ts_w(tbase + (uint32_t)(i & 1) * acc_off, tbase + 288u + (ia & 3u) * 8u, bd, idesc, 1u);
+        else umma::mma_tf32_ss_w(tbase + (uint32_t)(i & 1) * acc_off, ad, bd, idesc, 1u);
+        ib = ib + 1 == b_steps ? 0u : ib + 1;
+      }
+      const long long t1 = clock64();
+      umma::mma_commit_w(&bar);
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      if (tid == 0) {
+        cycles[2 * blockIdx.x] = t1 - t0;
+        cycles[2 * blockIdx.x + 1] = t2 - t0;
+        mbar_arrive_expect_tx(&spin_bar, 0);
+      }
+    } else if (warp_u >= 4) {
+      mbar_wait(&spin_bar, 0);
+    }
+  } else
   if (tid == 0) {
     const uint32_t idesc = umma::idesc_tf32(128, N);
     // precomputed == 2: every MMA reads FRESH shared-memory addresses (16 distinct A K-steps over 64 KB, as many B
     // K-steps as fit into 64 KB) — what a real K loop does; the other modes cycle through 4 K-steps of one tile
-    const bool fresh = precomputed == 2;
+    const bool fresh = precomputed == 2 || precomputed == 3;
     const uint32_t a_addr = smem_u32(base), b_addr = smem_u32(base) + (fresh ? 65536u : 16384u);
     const uint32_t lbo_w = b_rows * 16u;
     const uint32_t b_swz_tile = ((uint32_t)N * 128u + 1023u) & ~1023u;
@@ -192,6 +232,20 @@ umma_rate_kernel(int N, int a_mode, int b_swz, int precomputed_arg, int iters, l
                              : umma::smem_desc_kmajor_noswizzle(b_addr + ib * 2u * lbo_w + half, lbo_w, 128u);
       }
       const long long t0 = clock64();
+      if (precomputed == 3 && a_mode != 1) {
+        // same fresh addresses, but the descriptors of four MMAs are fetched into distinct registers before the four
+        // issues: separates "new operand addresses are slow" from "rewriting the descriptor registers of an MMA that
+        // is still queued stalls the issuing thread"
+        for (int i = 0; i < iters; i += 4) {
+          const int b = i & 12;
+          const uint64_t a0_ = adesc_tab[b], a1_ = adesc_tab[b + 1], a2_ = adesc_tab[b + 2], a3_ = adesc_tab[b + 3];
+          const uint64_t b0_ = bdesc_tab[b], b1_ = bdesc_tab[b + 1], b2_ = bdesc_tab[b + 2], b3_ = bdesc_tab[b + 3];
+          umma::mma_tf32_ss(tbase, a0_, b0_, idesc, 1u);
+          umma::mma_tf32_ss(tbase + acc_off, a1_, b1_, idesc, 1u);
+          umma::mma_tf32_ss(tbase, a2_, b2_, idesc, 1u);
+          umma::mma_tf32_ss(tbase + acc_off, a3_, b3_, idesc, 1u);
+        }
+      } else
 #pragma unroll 4
       for (int i = 0; i < iters; ++i) {
         const uint64_t ad = adesc_tab[i & 15], bd = bdesc_tab[i & 15];

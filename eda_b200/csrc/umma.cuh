@@ -113,6 +113,118 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-converged forms: the WHOLE warp executes the call with warp-uniform arguments and one elected lane issues.  An
+// issue loop written this way keeps its descriptors in uniform registers (computed by the uniform datapath); the same
+// loop inside `if (lane == 0)` makes the compiler move every descriptor from vector to uniform registers through an
+// elect / R2UR / branch "waterfall" per MMA, which costs more than the MMA itself (eda_selftest_umma_rate: 161 -> 72
+// cycles per 128 x 144 x 8 MMA).
+__device__ __forceinline__ void mma_tf32_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Four consecutive K steps (K = 8 each) into one accumulator from ONE statement: step k reads descriptors whose low
+// words are a_lo + k * a_step / b_lo + k * b_step (the 14-bit "address >> 4" field lives in the low word; the high
+// words do not change).  One elect and one branch per group, two adds per MMA: the tensor pipe, not the issue loop,
+// sets the pace (72 cycles per 128 x 144 x 8 MMA instead of 130 - 160 with per-MMA issue code).
+__device__ __forceinline__ void mma4_tf32_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t a_step, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t b_step, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q, t;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@!q bra MMA4_SKIP;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "setp.eq.b32 t, %0, %0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%4, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, p;\n\t"
+      "add.u32 al, %1, %3;\n\t"
+      "add.u32 bl, %4, %6;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, t;\n\t"
+      "add.u32 al, al, %3;\n\t"
+      "add.u32 bl, bl, %6;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, t;\n\t"
+      "add.u32 al, al, %3;\n\t"
+      "add.u32 bl, bl, %6;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %7, t;\n\t"
+      "MMA4_SKIP:\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(a_step), "r"(b_lo), "r"(b_hi), "r"(b_step), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+// Same with the A operand in tensor memory (a_tmem advances by a_step columns per K step).
+__device__ __forceinline__ void mma4_tf32_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t a_step, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t b_step, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q, t;\n\t"
+      ".reg .b64 db;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@!q bra MMA4_SKIP;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.eq.b32 t, %0, %0;\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %6, p;\n\t"
+      "add.u32 al, %1, %2;\n\t"
+      "add.u32 bl, %3, %5;\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], db, %6, t;\n\t"
+      "add.u32 al, al, %2;\n\t"
+      "add.u32 bl, bl, %5;\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], db, %6, t;\n\t"
+      "add.u32 al, al, %2;\n\t"
+      "add.u32 bl, bl, %5;\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], db, %6, t;\n\t"
+      "MMA4_SKIP:\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(a_step), "r"(b_lo), "r"(b_hi), "r"(b_step), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return (uint32_t)d; }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return (uint32_t)(d >> 32); }
+// Warp index as a value the compiler KNOWS is warp-uniform (threadIdx.x >> 5 alone is not): role branches on it keep the
+// code inside on the uniform datapath.
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ void mma_commit_w(uint64_t *bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // All MMAs issued so far by this thread arrive (once) on `bar` when they complete.  Implies
 // tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
