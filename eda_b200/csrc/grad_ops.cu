@@ -15,6 +15,7 @@
 // The activation-gradient GEMMs (dX = dY W) reuse the forward tcgen05 kernel (eda_linear_forward) with the
 // transposed weight packed by eda_linear_pack_strided.
 #include "common.cuh"
+#include "wgrad_tc.h"
 
 namespace eda {
 namespace {
@@ -355,6 +356,11 @@ int eda_wgrad(const eda_wgrad_problem *probs, int nprobs, int N, int K, void *st
     if (q.rows > max_rows) max_rows = q.rows;
   }
   if (max_rows == 0) return EDA_OK;
+  // large row counts without an input prologue: the tcgen05 kernel (wgrad_tc.cu), operands by TMA as they lie in memory
+  if (wgrad_tc_eligible(probs, nprobs, N, K)) {
+    const int rc = wgrad_tc_launch(probs, nprobs, N, K, as_stream(stream));
+    if (rc != kWgradTcDeclined) return rc;
+  }
   p.nprobs = nprobs; p.N = N; p.K = K;
   const int nt = (N + kWgTile - 1) / kWgTile, kt = (K + kWgTile - 1) / kWgTile;
   const int sms = sm_count();

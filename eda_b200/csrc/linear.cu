@@ -28,9 +28,9 @@
 // column quarter): warp w reads TMEM lanes 32 (w % 4).. (its hardware quadrant), four warps per scheduler hide
 // each other's TMEM latency: bias, ReLU, dropout, rounding.  Phase 2, warp = row: residual read with coalesced
 // 16-byte loads, LayerNorm statistics by warp shuffle, coalesced 16-byte stores.
-#include <stdlib.h>
-#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "umma.cuh"
+#include "tensor_map.cuh"
+#include "wgrad_tc.h"
 
 namespace eda {
 namespace {
@@ -109,15 +109,6 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// 2-D tiled TMA load global -> shared (tensor map in kernel-parameter space), completes on `bar` with the box bytes
-__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
 
 // 32 lanes x 32 consecutive columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -711,33 +702,10 @@ __global__ void dropout_apply_kernel(const float *__restrict__ x, uint32_t seed_
 }
 
 inline int kpad_of(int K) { return (K + 7) & ~7; }
-// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-inline EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    if (const char *e = getenv("EDA_LINEAR_TMA")) if (e[0] == '0') return nullptr;
-    void *sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(sym);
-  }();
-  return fn;
-}
 // Tensor map over x (rows, K) fp32 row-major for 32-column x 128-row boxes, SWIZZLE_128B.  false = use cp.async staging.
 inline bool make_a_tensor_map(CUtensorMap *map, const float *x, long long rows, int K) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || (K & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || rows <= 0) return false;
-  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)kRows};
-  const cuuint32_t estride[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), gdim, gstride, box, estride,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (K & 3) return false;
+  return make_tensor_map_rows32(map, x, rows, K, K, kRows);
 }
 
 inline bool lin_supported(int N, int K) { return N >= 16 && N <= kMaxN && (N & 15) == 0 && K >= 1 && K <= 4096; }
@@ -748,7 +716,8 @@ inline bool lin_supported(int N, int K) { return N >= 16 && N <= kMaxN && (N & 1
 extern "C" {
 
 int eda_debug_timestamps(long long *host_out, int n) {
-  if (!host_out || n < 0 || n > 128) return EDA_ERR_INVALID_ARGUMENT;
+  if (n < 0) return eda::wgrad_tc_timestamps(host_out, -n);  // negative count: the weight-gradient kernel's phase stamps
+  if (!host_out || n > 128) return EDA_ERR_INVALID_ARGUMENT;
   EDA_CUDA_TRY(cudaMemcpyFromSymbol(host_out, eda::g_lin_ts, sizeof(long long) * n), "debug timestamps");
   return EDA_OK;
 }

@@ -260,7 +260,8 @@ EDA_API int eda_linear_pack_batch(const void *descs_device, int count, int max_e
 EDA_API int eda_linear_forward(const eda_linear_problem *probs, int nprobs, int K, int N, int relu,
                                const float *ln_gamma, const float *ln_beta, float ln_eps, int layer_norm,
                                float dropout_p, unsigned int dropout_seed, const unsigned int *dropout_epoch, void *stream);
-/* Development aid: clock64() phase stamps of CTA 0 of the most recent eda_linear_forward launch (synchronises). */
+/* Development aid: clock64() phase stamps of CTA 0 of the most recent eda_linear_forward launch (synchronises).  A
+ * negative n returns the first -n (<= 16) stamps of the most recent tcgen05 eda_wgrad launch instead. */
 EDA_API int eda_debug_timestamps(long long *host_out, int n);
 EDA_API int eda_debug_timestamps_attn(long long *host_out, int n); /* same, attention kernel, key block 1 */
 EDA_API int eda_attention_forward(const float *q, const float *k, const float *vt, int ldv,

@@ -31,7 +31,12 @@ def _round_tf32(x):
 
 
 @pytest.mark.parametrize("R,N,K,nprob", [(700, 288, 288, 1), (8192, 288, 256, 1), (100, 64, 8, 1), (5000, 128, 144, 3),
-                                         (31, 256, 288, 5), (200000, 64, 16, 1)])
+                                         (31, 256, 288, 5), (200000, 64, 16, 1),
+                                         # the tcgen05 kernel's shapes (>= 3000 rows in total, N >= 64, K >= 32): two
+                                         # MMA pieces, K chunks (768 = 2 x 384), partial feature boxes, six problems, row
+                                         # tails, the per-piece epilogue (K = 512)
+                                         (8192, 288, 288, 3), (3100, 256, 288, 1), (1600, 288, 768, 2), (3001, 64, 32, 1),
+                                         (4099, 100, 36, 6), (3200, 288, 512, 1)])
 def test_wgrad_kernel(R, N, K, nprob):
     from eda_b200 import attn_ops as ops
 
