@@ -444,6 +444,10 @@ def extra_legs(args, dev, world, rank, inputs, host, step_ms):
         a = kn.attention_point(B_PER_GPU, Nq, Nk, dev)
         a.update({"tf32_peak_TFLOPs": tf32, "frac_of_tf32_peak": a["TFLOPs"] / tf32})
         rl[name] = a
+    wg = kn.wgrad_point(B_PER_GPU * 1024, 288, 288, 3, dev)
+    wg.update({"tf32_peak_TFLOPs": tf32, "frac_of_tf32_peak": wg["TFLOPs"] / tf32,
+               "kernel": "wgrad_tc_kernel (eda_wgrad): the q/k/v in-projection weight gradients of one attention block"})
+    rl["wgrad_qkv"] = wg
     sa = kn.sa_mlp_point(B_PER_GPU, N_POINTS, 2048, 64, 3, [64, 64, 128], 0.2, dev)
     sa.update({"tf32_peak_TFLOPs": tf32, "frac_of_tf32_peak": sa["TFLOPs"] / tf32})
     rl["sa_mlp_sa1"] = sa

@@ -157,6 +157,19 @@ def linear_point(R, K, N, dev, ln=False):
             "min_bytes": 4.0 * (R * K + R * N * (2 if ln else 1) + N * K)}
 
 
+def wgrad_point(R, N, K, nprob, dev):
+    """eda_wgrad (dW += dY^T X, db += column sums) on `nprob` problems of one shape in one launch: ms and TFLOP/s."""
+    from eda_b200 import attn_ops as ops
+
+    g = torch.Generator().manual_seed(0)
+    probs = [dict(dy=torch.randn(R, N, generator=g).to(dev), x=torch.randn(R, K, generator=g).to(dev),
+                  dw=torch.zeros(N, K, device=dev), db=torch.zeros(N, device=dev)) for _ in range(nprob)]
+    ms = time_ms(lambda: ops.wgrad(probs, N, K), 3, 20, graph=True)
+    flops = 2.0 * R * N * K * nprob
+    return {"R": R, "N": N, "K": K, "problems": nprob, "ms": ms, "flops": flops, "TFLOPs": flops / (ms * 1e-3) / 1e12,
+            "min_bytes": 4.0 * nprob * (R * (N + K) + N * K)}
+
+
 def sa_mlp_point(B, N, M, S, C, widths, radius, dev):
     """Fused group + 3-layer MLP + max-pool (eval-mode weights): ms and TFLOP/s over 2*M*S*sum(Cin*Cout) per scene."""
     from eda_b200 import synthetic

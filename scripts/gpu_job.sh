@@ -34,8 +34,8 @@ for step in "$@"; do
       python scripts/ncu_csv_summary.py gpurun_out/${TAG}_sweep_ncu.csv gpurun_out/${TAG}_sweep_ncu.json ;;
     full)
       # one `--set full` capture per roofline kernel (the dominant launch of each), source-correlated
-      for k in linear fps ballq attention sa_mlp; do
-        case $k in linear) re=linear_kernel;; fps) re=fps_cluster_kernel;; ballq) re=ball_query_kernel;; attention) re=attention_kernel;; sa_mlp) re=sa_mlp_kernel;; esac
+      for k in linear wgrad fps ballq attention sa_mlp; do
+        case $k in linear) re=linear_kernel;; wgrad) re=wgrad_tc_kernel;; fps) re=fps_cluster_kernel;; ballq) re=ball_query_kernel;; attention) re=attention_kernel;; sa_mlp) re=sa_mlp_kernel;; esac
         timeout 600 ncu --set full --clock-control none --import-source on -k regex:$re -s 3 -c 1 -f -o gpurun_out/${TAG}_full_$k python scripts/kernels_once.py $k > gpurun_out/${TAG}_full_$k.log 2>&1; echo "full $k rc=$?"
       done ;;
     benchlaunches)

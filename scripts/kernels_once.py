@@ -1,5 +1,5 @@
 """Runs each roofline kernel of bench.py a few times (for ncu captures; numbers printed under a profiler are never
-bench values):  python scripts/kernels_once.py [linear|fps|ballq|attention|sa_mlp|all]"""
+bench values):  python scripts/kernels_once.py [linear|wgrad|fps|ballq|attention|sa_mlp|all]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -11,6 +11,8 @@ _, _, _, sm_mhz, _ = kn.peaks()
 if which in ("linear", "all"):
     print(kn.linear_point(8192, 288, 288, dev))
     print(kn.linear_point(8192, 288, 288, dev, ln=True))
+if which in ("wgrad", "all"):
+    print(kn.wgrad_point(8192, 288, 288, 3, dev))
 if which in ("fps", "all"):
     print(kn.fps_point(8, 50000, 2048, dev, sm_mhz, with_floor=False))
 if which in ("ballq", "all"):
