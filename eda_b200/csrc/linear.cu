@@ -492,7 +492,22 @@ linear_kernel(const __grid_constant__ LinParams p) {
       }
     }
     LIN_TS(9);
-    if (!direct_t) {
+    if (!direct_t && !p.ln) {
+      // no LayerNorm: the tile already holds the final values.  One TMA bulk store per row (its N columns are contiguous
+      // on both sides, 16-byte aligned) instead of 16-byte stores by warp = row, whose second pass over a 144-column row
+      // used 4 of 32 lanes: 4.3k cycles of a 21k-cycle CTA.
+      umma::fence_proxy_async_smem();  // the bulk copy reads the tile through the async proxy
+      named_bar_sync_workers();        // the tile is complete
+      LIN_TS(10);
+      if (tid < nvalid) {
+        const float *src = tile_s + (size_t)tid * pitch;
+        bulk_s2g(pr.y + (row0 + tid) * (long long)pr.ldy + n0, src, (uint32_t)N * 4u);
+        if (pr.pre) bulk_s2g(pr.pre + (row0 + tid) * Nf + n0, src, (uint32_t)N * 4u);
+        bulk_commit();
+        bulk_wait_read_all();  // shared memory may go once the copies have read it; the grid's completion publishes them
+      }
+      LIN_TS(16);
+    } else if (!direct_t) {
       named_bar_sync_workers();  // the tile is complete
       LIN_TS(10);
       const float invN = 1.0f / (float)Nf;

@@ -46,7 +46,7 @@ __device__ __forceinline__ void rg_cp16(void *smem_dst, const void *gsrc, uint32
 }
 
 template <bool kPrologue, bool kStats>
-__global__ void __launch_bounds__(kRgThreads, 1)
+__global__ void __launch_bounds__(kRgThreads, 2)
 rows_gemm_kernel(const RowsGemmParams p) {
   extern __shared__ __align__(16) unsigned char rg_smem[];
   const int K = p.K, PW = K + 4;  // (g * PW + t) % 32 = 4 g + t: conflict-free B fragments (K % 8 == 0)
@@ -222,7 +222,11 @@ extern "C" int eda_rows_gemm_stats(const float *x, int ldx, const float *in_scal
   }
   const int sms = sm_count();
   const int ny = (N + kRgNc - 1) / kRgNc;
-  long long gx = sms / ny;
+  // two resident CTAs per SM when the weight slice leaves room (K <= 64: 92 KB each): the kernel is latency-bound with
+  // one 8-warp CTA (issue slots 40 % active), the second CTA fills its stalls.  EDA_ROWS_GEMM_CTAS=1 keeps one.
+  static const int max_ctas = [] { const char *e = getenv("EDA_ROWS_GEMM_CTAS"); return e ? atoi(e) : 2; }();
+  const int per_sm = (2 * (smem + 1024) <= 227 * 1024 && max_ctas >= 2) ? 2 : 1;
+  long long gx = (long long)per_sm * sms / ny;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   dim3 grid((unsigned)gx, (unsigned)ny);
