@@ -13,6 +13,7 @@
 // Measured (profiles/r1_bwd_kernel_metrics.json): 120-130 us per launch, 1.9-2.4 TB/s, legacy tensor pipe 22-29 %, issue
 // slots 40 % active — latency-bound with one 8-warp CTA per SM, not yet at the HBM roofline it is designed for.
 #include "common.cuh"
+#include "rows_gemm_tc.h"
 
 namespace eda {
 namespace {
@@ -133,17 +134,20 @@ rows_gemm_kernel(const RowsGemmParams p) {
     if (kc == nkc - 1) {
       const long long row0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * kRgRows;
       const long long ra = row0 + r0 + g, rb = ra + 8;
+      const float fa = ra < p.rows ? 1.f : 0.f, fb = rb < p.rows ? 1.f : 0.f;
 #pragma unroll
       for (int j = 0; j < kMaxNT; ++j) {
         if (j < nnt) {
           const int n = n0 + j * 8 + 2 * t;
           if (ra < p.rows) *reinterpret_cast<float2 *>(p.y + ra * p.ldy + n) = make_float2(acc[j][0], acc[j][1]);
           if (rb < p.rows) *reinterpret_cast<float2 *>(p.y + rb * p.ldy + n) = make_float2(acc[j][2], acc[j][3]);
-          if (kStats) {  // rows beyond p.rows were zero-filled on the way in: they add exactly 0
-            csum[j][0] += acc[j][0] + acc[j][2];
-            csum[j][1] += acc[j][1] + acc[j][3];
-            csq[j][0] = fmaf(acc[j][0], acc[j][0], fmaf(acc[j][2], acc[j][2], csq[j][0]));
-            csq[j][1] = fmaf(acc[j][1], acc[j][1], fmaf(acc[j][3], acc[j][3], csq[j][1]));
+          if (kStats) {  // rows beyond p.rows do not count (zero-filled on the way in, but f(0) = relu(shift) != 0)
+            const float v0 = acc[j][0] * fa, v1 = acc[j][1] * fa;
+            const float v2 = acc[j][2] * fb, v3 = acc[j][3] * fb;
+            csum[j][0] += v0 + v2;
+            csum[j][1] += v1 + v3;
+            csq[j][0] = fmaf(v0, v0, fmaf(v2, v2, csq[j][0]));
+            csq[j][1] = fmaf(v1, v1, fmaf(v3, v3, csq[j][1]));
           }
         }
       }
@@ -208,6 +212,12 @@ extern "C" int eda_rows_gemm_stats(const float *x, int ldx, const float *in_scal
     return EDA_ERR_INVALID_ARGUMENT;
   const long long ntiles = (rows + kRgRows - 1) / kRgRows;
   if (ntiles > 0x7fffffffLL) return EDA_ERR_UNSUPPORTED;
+  // the big launches (K <= 160, >= 16k rows): persistent tcgen05 kernel, operands in and out by TMA (rows_gemm_tc.cu)
+  if (rows_gemm_tc_eligible(x, ldx, rows, K, N, y, ldy)) {
+    const int rc = rows_gemm_tc_launch(x, ldx, in_scale, in_shift, w, w_stride_n, w_stride_k, rows, K, N, y, ldy, stats,
+                                       as_stream(stream));
+    if (rc != kRowsGemmTcDeclined) return rc;
+  }
   RowsGemmParams p = {};
   p.x = x; p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.y = y; p.rows = rows; p.w_sn = w_stride_n;
   p.w_sk = w_stride_k; p.ldx = ldx; p.ldy = ldy; p.K = K; p.N = N; p.ntiles = (int)ntiles; p.stats = stats;

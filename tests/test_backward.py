@@ -413,7 +413,13 @@ def test_sa_pool_bn_relu_backward_kernels(training, S, C):
 @pytest.mark.parametrize("R,K,N,prologue,transpose", [(1000, 16, 64, False, False), (70000, 64, 64, True, False),
                                                       (5000, 144, 128, False, False), (3000, 128, 256, True, False),
                                                       (129, 272, 128, False, False), (4000, 256, 128, False, True),
-                                                      (2000, 128, 272, False, True), (1, 64, 8, True, False)])
+                                                      (2000, 128, 272, False, True), (1, 64, 8, True, False),
+                                                      # the persistent tcgen05 kernel's shapes (>= 16384 rows, K <= 160):
+                                                      # a tail box (K = 136, 8), two column slices (N = 256), a row tail,
+                                                      # fewer tiles than SMs, the transposed weight view
+                                                      (20000, 40, 64, False, False), (100000, 136, 128, False, False),
+                                                      (40001, 128, 256, True, False), (16400, 64, 16, True, False),
+                                                      (70000, 128, 64, False, True), (33000, 256, 128, False, True)])
 def test_rows_gemm_kernel(R, K, N, prologue, transpose):
     from eda_b200 import attn_ops as ops
 
@@ -422,13 +428,19 @@ def test_rows_gemm_kernel(R, K, N, prologue, transpose):
     W = (torch.randn(K, N, generator=g) if transpose else torch.randn(N, K, generator=g)).cuda() / math.sqrt(K)
     sc = (1 + 0.3 * torch.randn(K, generator=g)).cuda() if prologue else None
     sh = (0.2 * torch.randn(K, generator=g)).cuda() if prologue else None
-    y = ops.rows_gemm(x, W, transpose=transpose, in_scale=sc, in_shift=sh)
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    y = ops.rows_gemm(x, W, transpose=transpose, in_scale=sc, in_shift=sh, stats=stats)
     xd = x.double()
     if prologue:
         xd = torch.relu(xd * sc.double() + sh.double())
     ref = xd @ (W.double() if transpose else W.double().t())
     assert y.shape == ref.shape and rel(y, ref) <= 2e-3
     torch.testing.assert_close(y.double(), ref, rtol=2e-3, atol=5e-3)
+    # the epilogue's column statistics are those of the tensor it wrote
+    torch.testing.assert_close(stats[:N], y.double().sum(0), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(stats[N:], (y.double() ** 2).sum(0), rtol=1e-5, atol=1e-3)
+    y2 = ops.rows_gemm(x, W, transpose=transpose, in_scale=sc, in_shift=sh)  # the variant without statistics
+    assert torch.equal(y, y2)
 
 
 def test_wgrad_kernel_with_bn_relu_prologue():
