@@ -15,10 +15,9 @@
 //   warp 1      MMA issue, whole warp converged (umma::mma4_tf32_ss_w): per box 4 K steps against the weight slice that
 //               stays in shared memory (packed once per CTA, tf32), accumulators double-buffered in tensor memory
 //   warps 2-9   fix-up of each landed box in place: f(x), cvt.rna.tf32 (the tensor core would truncate)
-//   warps 10-17 epilogue, thread = row (two warps per TMEM lane quadrant, each half of the columns): TMEM -> registers ->
-//               (column statistics by 16-lane butterflies, ~480 cycles per 16 columns and warp: the reason for eight
-//               warps) -> the row's slot of a padded shared-memory tile -> ONE TMA bulk store per row (coalesced,
-//               asynchronous)
+//   warps 10-17 epilogue: TMEM -> registers -> the row's slot of a padded shared-memory tile (thread = row, two warps per
+//               TMEM lane quadrant) -> ONE TMA bulk store per row (coalesced, asynchronous); column statistics read down
+//               the tile's columns (thread = column x row part, running sums in registers over all tiles)
 // Rows past the end of the matrix arrive as zeros, are excluded from the statistics and never stored.
 #include "umma.cuh"
 #include "tensor_map.cuh"
@@ -35,7 +34,6 @@ constexpr int kMaxNc = 128;                      // output columns per CTA (grid
 constexpr int kMaxRing = 8;
 constexpr int kFixWarps = 8, kEpiWarps = 8;
 constexpr int kThreads = (2 + kFixWarps + kEpiWarps) * 32;  // 576
-constexpr unsigned kFull = 0xffffffffu;
 
 struct RgTcParams {
   alignas(64) CUtensorMap map_x;
@@ -63,21 +61,6 @@ __device__ __forceinline__ void bulk_store_row(void *dst_gmem, const void *src_s
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// 16 values per lane -> lane l ends with the sum over the 32 lanes of value (l & 15) (15 + 1 shuffles instead of 80)
-__device__ __forceinline__ float butterfly_sum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int w = 8; w >= 1; w >>= 1) {
-    const bool up = lane & w;
-#pragma unroll
-    for (int i = 0; i < w; ++i) {
-      const float send = up ? v[i] : v[i + w];
-      const float keep = up ? v[i + w] : v[i];
-      v[i] = keep + __shfl_xor_sync(kFull, send, w);
-    }
-  }
-  return v[0] + __shfl_xor_sync(kFull, v[0], 16);
-}
-
 template <bool kPrologue, bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
 rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
@@ -89,7 +72,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
   __shared__ __align__(8) uint64_t full[kMaxRing], ready[kMaxRing], empty[kMaxRing], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_sc[kMaxK], s_sh[kMaxK];
-  __shared__ float s_part[4][2][kMaxNc];  // per TMEM lane quadrant: the two warps of a quadrant own disjoint columns
+  __shared__ float s_part[16][2][16];  // viewed as [nparts][2][Nc] with nparts * Nc = 256 (see the epilogue)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = umma::uniform_warp_index();
@@ -119,7 +102,6 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
     s_sc[k] = (kPrologue && k < K) ? __ldg(p.in_scale + k) : 0.f;
     s_sh[k] = (kPrologue && k < K) ? __ldg(p.in_shift + k) : 0.f;
   }
-  for (int i = tid; i < 4 * 2 * kMaxNc; i += kThreads) (&s_part[0][0][0])[i] = 0.f;
   umma::fence_proxy_async_smem();  // the weights are read by the tensor core (async proxy)
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -208,15 +190,23 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
       }
     }
   } else {
-    // ---------------- epilogue warps: thread = (row, column half) ------------------------------------------------------------------
+    // ---------------- epilogue warps ----------------------------------------------------------------------------------------------------
+    // Phase 1, thread = (row, column half): TMEM -> the row's slot of the padded tile.  Phase 2: one bulk store per row,
+    // and the column statistics with thread = (column, row part): conflict-free reads down the tile's columns, running
+    // sums in two registers over ALL tiles of this CTA (a butterfly reduction over the lanes of the TMEM layout cost
+    // ~480 cycles per 16 columns and warp and bound the kernel at 3.5 TB/s).
+    const int et = tid - (2 + kFixWarps) * 32;        // 0..255
     const int quad = warp & 3;                        // TMEM lanes 32 quad .. (hardware: warp w reads quadrant w % 4)
-    const int half = (warp - (2 + kFixWarps)) >> 2;   // 0 / 1: which half of the 16-column chunks
+    const int half = et >> 7;                         // which half of the 16-column chunks
     const int r = quad * 32 + lane;
     const int pitch = Nc + 4;
     float *trow = tile + (size_t)r * pitch;
     const int nch = Nc >> 4;
     const int ch_lo = half == 0 ? 0 : (nch + 1) / 2, ch_hi = half == 0 ? (nch + 1) / 2 : nch;
-    const uint32_t pair_bar = 1u + (uint32_t)quad;    // named barrier of the two warps that share a row
+    // statistics ownership: column sc, rows [sr0, sr0 + srn) of every tile (Nc is a power of two times 16: 16 ... 128)
+    const int nparts = 256 / Nc, sc = et % Nc, srn = kRows / nparts, sr0 = (et / Nc) * srn;
+    const bool stat_thread = kStats && (256 % Nc == 0);
+    float csum = 0.f, csq = 0.f;
     int it = 0;
     for (int t = (int)blockIdx.x; t < p.ntiles; t += (int)gridDim.x, ++it) {
       const int buf = it & 1;
@@ -226,7 +216,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
       umma::fence_after_thread_sync();
       if (it > 0) {
         if (half == 0) bulk_wait_read0();  // the row's previous store (issued by this thread) has read the tile row
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // ... and everybody is done with the previous tile's columns
       }
       const uint32_t tacc = umma::tmem_addr(tbase, (uint32_t)(quad * 32), (uint32_t)(buf * kMaxNc));
       for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -239,42 +229,46 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
           *reinterpret_cast<float4 *>(trow + c0 + q4 * 4) =
               make_float4(__uint_as_float(u[q4 * 4 + 0]), __uint_as_float(u[q4 * 4 + 1]), __uint_as_float(u[q4 * 4 + 2]),
                           __uint_as_float(u[q4 * 4 + 3]));
-        if (kStats) {
-          float s1[16], s2[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float z = valid ? __uint_as_float(u[e]) : 0.f;
-            s1[e] = z;
-            s2[e] = z * z;
-          }
-          const float a = butterfly_sum16(s1, lane);
-          const float q = butterfly_sum16(s2, lane);
-          if (lane < 16) {  // single writer per slot: fixed order, reproducible
-            s_part[quad][0][c0 + lane] += a;
-            s_part[quad][1][c0 + lane] += q;
-          }
-        }
       }
       // the accumulator has been read: hand it back to the MMA warp
       umma::fence_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_local(&acc_empty[buf]);
-      umma::fence_proxy_async_smem();  // the bulk copy reads the tile row through the async proxy
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // both halves of the row are in the tile
+      umma::fence_proxy_async_smem();  // the bulk copy reads the tile through the async proxy
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the tile is complete
       if (half == 0 && valid) {
         bulk_store_row(p.y + row * p.ldy + n0, trow, (uint32_t)Nc * 4u);
         bulk_commit_group();
       }
+      if (stat_thread) {
+        const long long left = p.rows - ((long long)t * kRows + sr0);  // rows of this part that exist
+        const int nr = left >= srn ? srn : (left > 0 ? (int)left : 0);
+        const float *col = tile + (size_t)sr0 * pitch + sc;
+#pragma unroll 8
+        for (int i = 0; i < nr; ++i) {
+          const float z = col[(size_t)i * pitch];
+          csum += z;
+          csq = fmaf(z, z, csq);
+        }
+      }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this thread's row stores have been performed
     if (kStats) {
-      asm volatile("bar.sync 5, 256;" ::: "memory");  // the eight epilogue warps: partials complete
-      const int c = tid - (2 + kFixWarps) * 32;
-      if (c < Nc) {
-        const double sm = ((double)s_part[0][0][c] + (double)s_part[1][0][c]) + ((double)s_part[2][0][c] + (double)s_part[3][0][c]);
-        const double sq = ((double)s_part[0][1][c] + (double)s_part[1][1][c]) + ((double)s_part[2][1][c] + (double)s_part[3][1][c]);
-        atomicAdd(p.stats + n0 + c, sm);
-        atomicAdd(p.stats + p.N + n0 + c, sq);
+      if (stat_thread) {
+        float *sp = &s_part[0][0][0];  // [part][2][Nc]
+        sp[((et / Nc) * 2 + 0) * Nc + sc] = csum;
+        sp[((et / Nc) * 2 + 1) * Nc + sc] = csq;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et < Nc) {
+        double sm = 0.0, sq = 0.0;
+        const float *sp = &s_part[0][0][0];
+        for (int q = 0; q < nparts; ++q) {
+          sm += (double)sp[(q * 2 + 0) * Nc + et];
+          sq += (double)sp[(q * 2 + 1) * Nc + et];
+        }
+        atomicAdd(p.stats + n0 + et, sm);
+        atomicAdd(p.stats + p.N + n0 + et, sq);
       }
     }
   }
@@ -320,6 +314,7 @@ int rows_gemm_tc_launch(const float *x, int ldx, const float *in_scale, const fl
   }
   if (nring > kMaxRing) nring = kMaxRing;
   if (nring < 3) return kRowsGemmTcDeclined;
+  if (stats && (256 % p.Nc)) return kRowsGemmTcDeclined;  // the statistics pass deals 256 threads as columns x row parts
   p.nring = (int)nring;
   const size_t smem = (size_t)p.ring_off + (size_t)p.nring * kBoxBytes + 1024;
   const int ny = N / p.Nc;
