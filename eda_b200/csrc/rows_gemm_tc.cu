@@ -37,12 +37,15 @@ constexpr int kThreads = (2 + kFixWarps + kEpiWarps) * 32;  // 576
 
 struct RgTcParams {
   alignas(64) CUtensorMap map_x;
+  alignas(64) CUtensorMap map_y;  // (rows, N) output, 128-row x 32-column boxes, SWIZZLE_128B: the epilogue's stores
   const float *in_scale, *in_shift, *w;
   float *y;
   double *stats;
   long long rows, w_sn, w_sk;
   int ldy, K, N, Nc, ntiles, nbox, nring;
-  uint32_t w_bytes, tile_off, ring_off;  // shared-memory carve-up (bytes from the 1024-aligned base)
+  int tile_bufs;                                     // output tiles in shared memory (2 when they fit: the bulk stores of
+                                                     // one tile are still reading it while the next one is written)
+  uint32_t w_bytes, tile_off, tile_bytes, ring_off;  // shared-memory carve-up (bytes from the 1024-aligned base)
 };
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -53,13 +56,16 @@ __device__ __forceinline__ float to_tf32(float x) {
 __device__ __forceinline__ void mbar_arrive_local(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void bulk_store_row(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-               "r"(bytes)
+// 2-D tiled TMA store shared -> global (bulk-group completion); rows / columns outside the tensor are not written
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(smem_u32(src_smem))
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 template <bool kPrologue, bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -68,7 +74,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
   unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char *ring = base + p.ring_off;                        // [nring] boxes of 16 KB (1024-aligned)
   float *sW = reinterpret_cast<float *>(base);                    // [K / 4][Nc] float4: K-major core matrices, chunk-major
-  float *tile = reinterpret_cast<float *>(base + p.tile_off);     // [128][Nc + 4]
+  float *tile = reinterpret_cast<float *>(base + p.tile_off);     // [tile_bufs][Nc / 32][128][32], swizzled (see the epilogue)
   __shared__ __align__(8) uint64_t full[kMaxRing], ready[kMaxRing], empty[kMaxRing], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_sc[kMaxK], s_sh[kMaxK];
@@ -191,32 +197,34 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
     }
   } else {
     // ---------------- epilogue warps ----------------------------------------------------------------------------------------------------
-    // Phase 1, thread = (row, column half): TMEM -> the row's slot of the padded tile.  Phase 2: one bulk store per row,
-    // and the column statistics with thread = (column, row part): conflict-free reads down the tile's columns, running
-    // sums in two registers over ALL tiles of this CTA (a butterfly reduction over the lanes of the TMEM layout cost
-    // ~480 cycles per 16 columns and warp and bound the kernel at 3.5 TB/s).
+    // The output tile lives in shared memory as Nc / 32 boxes of [128 rows][32 columns], 128-byte rows with the 16-byte
+    // chunks XOR-swizzled by (row & 7) — the image a SWIZZLE_128B tensor map stores from.  Phase 1, thread = (row, column
+    // half): TMEM -> the row's chunks (conflict-free: 8 consecutive rows hit 8 different chunk positions).  Phase 2: ONE
+    // elected thread issues one 2-D TMA store per box (rows past the end of the matrix are clipped by the tensor map; 128
+    // per-row bulk stores per tile kept the TMA unit busy for ~4k cycles per tile whatever the shape), and everybody
+    // takes the column statistics with thread = (column, row part): conflict-free reads down the tile's columns, running
+    // sums in two registers over ALL tiles of this CTA.
     const int et = tid - (2 + kFixWarps) * 32;        // 0..255
     const int quad = warp & 3;                        // TMEM lanes 32 quad .. (hardware: warp w reads quadrant w % 4)
     const int half = et >> 7;                         // which half of the 16-column chunks
     const int r = quad * 32 + lane;
-    const int pitch = Nc + 4;
-    float *trow = tile + (size_t)r * pitch;
     const int nch = Nc >> 4;
     const int ch_lo = half == 0 ? 0 : (nch + 1) / 2, ch_hi = half == 0 ? (nch + 1) / 2 : nch;
-    // statistics ownership: column sc, rows [sr0, sr0 + srn) of every tile (Nc is a power of two times 16: 16 ... 128)
+    // statistics ownership: column sc, rows [sr0, sr0 + srn) of every tile (Nc in {32, 64, 128})
     const int nparts = 256 / Nc, sc = et % Nc, srn = kRows / nparts, sr0 = (et / Nc) * srn;
     const bool stat_thread = kStats && (256 % Nc == 0);
+    const uint32_t s_box = (uint32_t)(sc >> 5) * (uint32_t)kBoxBytes, s_c16 = (uint32_t)((sc & 31) >> 2), s_e = (uint32_t)(sc & 3) * 4u;
     float csum = 0.f, csq = 0.f;
     int it = 0;
     for (int t = (int)blockIdx.x; t < p.ntiles; t += (int)gridDim.x, ++it) {
       const int buf = it & 1;
-      const long long row = (long long)t * kRows + r;
-      const bool valid = row < p.rows;
+      unsigned char *tl = reinterpret_cast<unsigned char *>(tile) + (size_t)(p.tile_bufs == 2 ? buf : 0) * p.tile_bytes;
       mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
       umma::fence_after_thread_sync();
       if (it > 0) {
-        if (half == 0) bulk_wait_read0();  // the row's previous store (issued by this thread) has read the tile row
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // ... and everybody is done with the previous tile's columns
+        // the stores that last read this tile buffer (issued by thread 0 of the group) have read it ...
+        if (et == 0) { if (p.tile_bufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // ... and everybody is done with that tile's columns
       }
       const uint32_t tacc = umma::tmem_addr(tbase, (uint32_t)(quad * 32), (uint32_t)(buf * kMaxNc));
       for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -224,9 +232,11 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
         uint32_t u[16];
         umma::tmem_ld16(tacc + (uint32_t)c0, u);
         umma::tmem_ld_wait();
+        unsigned char *rowp = tl + (size_t)(c0 >> 5) * kBoxBytes + (size_t)r * 128;
+        const int c16 = (c0 & 31) >> 2;  // 0 or 4: first 16-byte chunk of these 16 columns inside the box row
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<float4 *>(trow + c0 + q4 * 4) =
+          *reinterpret_cast<float4 *>(rowp + (((c16 + q4) ^ (r & 7)) << 4)) =
               make_float4(__uint_as_float(u[q4 * 4 + 0]), __uint_as_float(u[q4 * 4 + 1]), __uint_as_float(u[q4 * 4 + 2]),
                           __uint_as_float(u[q4 * 4 + 3]));
       }
@@ -234,25 +244,26 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
       umma::fence_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_local(&acc_empty[buf]);
-      umma::fence_proxy_async_smem();  // the bulk copy reads the tile through the async proxy
+      umma::fence_proxy_async_smem();  // the TMA store reads the tile through the async proxy
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the tile is complete
-      if (half == 0 && valid) {
-        bulk_store_row(p.y + row * p.ldy + n0, trow, (uint32_t)Nc * 4u);
+      if (et == 0) {
+        for (int b = 0; b < (Nc >> 5); ++b) tma_store_2d(&p.map_y, n0 + 32 * b, t * kRows, tl + (size_t)b * kBoxBytes);
         bulk_commit_group();
       }
       if (stat_thread) {
         const long long left = p.rows - ((long long)t * kRows + sr0);  // rows of this part that exist
         const int nr = left >= srn ? srn : (left > 0 ? (int)left : 0);
-        const float *col = tile + (size_t)sr0 * pitch + sc;
+        const unsigned char *col = tl + s_box + s_e;
 #pragma unroll 8
         for (int i = 0; i < nr; ++i) {
-          const float z = col[(size_t)i * pitch];
+          const uint32_t row_i = (uint32_t)(sr0 + i);
+          const float z = *reinterpret_cast<const float *>(col + row_i * 128u + ((s_c16 ^ (row_i & 7u)) << 4));
           csum += z;
           csq = fmaf(z, z, csq);
         }
       }
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this thread's row stores have been performed
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stores have been performed
     if (kStats) {
       if (stat_thread) {
         float *sp = &s_part[0][0][0];  // [part][2][Nc]
@@ -282,7 +293,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
 bool rows_gemm_tc_eligible(const float *x, int ldx, long long rows, int K, int N, const float *y, int ldy) {
   static const bool off = [] { const char *e = getenv("EDA_ROWS_GEMM_TC"); return e && e[0] == '0'; }();
   if (off || !encode_tiled_fn()) return false;
-  if ((K & 7) || K > kMaxK || K < 32 || (N & 15)) return false;  // (K < 32: a 32-column box would be mostly padding)
+  if ((K & 7) || K > kMaxK || (N & 31)) return false;
   if (N > kMaxNc && (N % kMaxNc)) return false;
   if ((ldx & 3) || (ldy & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
   if (rows > 0x7fffffffLL - kRows) return false;
@@ -293,7 +304,9 @@ int rows_gemm_tc_launch(const float *x, int ldx, const float *in_scale, const fl
                         long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y, int ldy,
                         double *stats, cudaStream_t stream) {
   RgTcParams p = {};
-  if (!make_tensor_map_rows32(&p.map_x, x, rows, K, ldx, kRows, false)) return kRowsGemmTcDeclined;
+  if (!make_tensor_map_rows32(&p.map_x, x, rows, K, ldx, kRows, false) ||
+      !make_tensor_map_rows32(&p.map_y, y, rows, N, ldy, kRows, false))
+    return kRowsGemmTcDeclined;
   p.in_scale = in_scale; p.in_shift = in_shift; p.w = w; p.y = y; p.stats = stats; p.rows = rows;
   p.w_sn = w_stride_n; p.w_sk = w_stride_k; p.ldy = ldy; p.K = K; p.N = N;
   p.ntiles = (int)((rows + kRows - 1) / kRows);
@@ -302,19 +315,27 @@ int rows_gemm_tc_launch(const float *x, int ldx, const float *in_scale, const fl
   // narrower slice re-reads X once per slice: K = 256, N = 128 runs as two slices of 64)
   const size_t budget = 220 * 1024;  // next to ~8 KB of static shared memory and the alignment slack
   long long nring = 0;
-  for (int nc = N < kMaxNc ? N : kMaxNc; nc >= 16; nc >>= 1) {
-    if (N % nc || (nc & 15)) continue;
+  for (int nc = N < kMaxNc ? N : kMaxNc; nc >= 32; nc >>= 1) {
+    if (N % nc || (nc & 31)) continue;  // whole 32-column boxes
     p.Nc = nc;
     p.w_bytes = (uint32_t)(((size_t)K * nc * 4 + 1023) & ~(size_t)1023);
-    const uint32_t tile_bytes = (uint32_t)(((size_t)kRows * (nc + 4) * 4 + 1023) & ~(size_t)1023);
+    p.tile_bytes = (uint32_t)((nc / 32) * kBoxBytes);
     p.tile_off = p.w_bytes;
-    p.ring_off = p.w_bytes + tile_bytes;
+    p.tile_bufs = 1;
+    p.ring_off = p.w_bytes + p.tile_bytes;
     nring = ((long long)budget - 1024 - (long long)p.ring_off) / kBoxBytes;
+    // a second output tile when it leaves a ring of one tile's boxes + 2 (at least 4)
+    const long long want = p.nbox + 2 > 4 ? p.nbox + 2 : 4;
+    if (((long long)budget - 1024 - (long long)p.ring_off - (long long)p.tile_bytes) / kBoxBytes >= want) {
+      p.tile_bufs = 2;
+      p.ring_off += p.tile_bytes;
+      nring = ((long long)budget - 1024 - (long long)p.ring_off) / kBoxBytes;
+    }
     if (nring >= 3) break;
   }
   if (nring > kMaxRing) nring = kMaxRing;
   if (nring < 3) return kRowsGemmTcDeclined;
-  if (stats && (256 % p.Nc)) return kRowsGemmTcDeclined;  // the statistics pass deals 256 threads as columns x row parts
+  if (256 % p.Nc) return kRowsGemmTcDeclined;  // the statistics pass deals 256 threads as columns x row parts
   p.nring = (int)nring;
   const size_t smem = (size_t)p.ring_off + (size_t)p.nring * kBoxBytes + 1024;
   const int ny = N / p.Nc;

@@ -417,7 +417,7 @@ def test_sa_pool_bn_relu_backward_kernels(training, S, C):
                                                       # the persistent tcgen05 kernel's shapes (>= 16384 rows, K <= 160):
                                                       # a tail box (K = 136, 8), two column slices (N = 256), a row tail,
                                                       # fewer tiles than SMs, the transposed weight view
-                                                      (20000, 40, 64, False, False), (100000, 136, 128, False, False),
+                                                      (20000, 40, 64, False, False), (30000, 8, 64, False, False), (100000, 136, 128, False, False),
                                                       (40001, 128, 256, True, False), (16400, 64, 16, True, False),
                                                       (70000, 128, 64, False, True), (33000, 256, 128, False, True)])
 def test_rows_gemm_kernel(R, K, N, prologue, transpose):
