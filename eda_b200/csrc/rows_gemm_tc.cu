@@ -29,8 +29,9 @@ namespace {
 constexpr int kRows = 128;
 constexpr int kBoxCols = 32;
 constexpr int kBoxBytes = kRows * kBoxCols * 4;  // 16 KB
-constexpr int kMaxK = 256;                       // 8 boxes
-constexpr int kMaxNc = 128;                      // output columns per CTA (grid.y slices wider layers)
+constexpr int kMaxK = 288;                       // 9 boxes
+constexpr int kMaxNc = 160;                      // output columns per CTA (grid.y slices wider layers): a multiple of 32;
+                                                 // columns >= N of the last slice are zero weights, clipped by the store
 constexpr int kMaxRing = 8;
 constexpr int kFixWarps = 8, kEpiWarps = 8;
 constexpr int kThreads = (2 + kFixWarps + kEpiWarps) * 32;  // 576
@@ -79,13 +80,15 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_sc[kMaxK], s_sh[kMaxK];
   __shared__ float s_part[16][2][16];  // viewed as [nparts][2][Nc] with nparts * Nc = 256 (see the epilogue)
+  static_assert(kMaxNc % 32 == 0 && kMaxNc <= 256, "one MMA per accumulator");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = umma::uniform_warp_index();
   const int K = p.K, Nc = p.Nc, nbox = p.nbox, nring = p.nring;
   const int n0 = (int)blockIdx.y * Nc;
 
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
+  const uint32_t acc_stride = Nc > 128 ? 256u : 128u;  // columns between the two accumulators
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 2u * acc_stride);
   if (tid == 32) {
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&full[s], 1);
@@ -102,7 +105,8 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
   // element (n, k) at float ((k / 4) * Nc + n) * 4 + k % 4
   for (int e = tid; e < K * Nc; e += kThreads) {
     const int k = e / Nc, n = e - k * Nc;  // consecutive threads: consecutive n (coalesced for a (K, N)-strided view)
-    sW[((k >> 2) * Nc + n) * 4 + (k & 3)] = to_tf32(__ldg(p.w + (long long)(n0 + n) * p.w_sn + (long long)k * p.w_sk));
+    sW[((k >> 2) * Nc + n) * 4 + (k & 3)] =
+        n0 + n < p.N ? to_tf32(__ldg(p.w + (long long)(n0 + n) * p.w_sn + (long long)k * p.w_sk)) : 0.f;
   }
   for (int k = tid; k < kMaxK; k += kThreads) {
     s_sc[k] = (kPrologue && k < K) ? __ldg(p.in_scale + k) : 0.f;
@@ -141,7 +145,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
       const int buf = it & 1;
       mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));  // the epilogue has drained this accumulator
       umma::fence_after_thread_sync();
-      const uint32_t d = tbase + (uint32_t)(buf * kMaxNc);
+      const uint32_t d = tbase + (uint32_t)buf * acc_stride;
       for (int j = 0; j < nbox; ++j, slot = (slot + 1 == nring) ? 0 : slot + 1, par ^= (slot == 0) ? 1u : 0u) {
         mbar_wait(&ready[slot], par);
         umma::fence_after_thread_sync();
@@ -226,7 +230,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
         if (et == 0) { if (p.tile_bufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // ... and everybody is done with that tile's columns
       }
-      const uint32_t tacc = umma::tmem_addr(tbase, (uint32_t)(quad * 32), (uint32_t)(buf * kMaxNc));
+      const uint32_t tacc = umma::tmem_addr(tbase, (uint32_t)(quad * 32), (uint32_t)buf * acc_stride);
       for (int ch = ch_lo; ch < ch_hi; ++ch) {
         const int c0 = ch << 4;
         uint32_t u[16];
@@ -271,7 +275,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
         sp[((et / Nc) * 2 + 1) * Nc + sc] = csq;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et < Nc) {
+      if (et < Nc && n0 + et < p.N) {
         double sm = 0.0, sq = 0.0;
         const float *sp = &s_part[0][0][0];
         for (int q = 0; q < nparts; ++q) {
@@ -285,7 +289,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
   }
   umma::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tbase, 256);
+  if (warp == 0) umma::tmem_dealloc(tbase, 2u * acc_stride);
 }
 
 }  // namespace
@@ -293,8 +297,7 @@ rows_gemm_tc_kernel(const __grid_constant__ RgTcParams p) {
 bool rows_gemm_tc_eligible(const float *x, int ldx, long long rows, int K, int N, const float *y, int ldy) {
   static const bool off = [] { const char *e = getenv("EDA_ROWS_GEMM_TC"); return e && e[0] == '0'; }();
   if (off || !encode_tiled_fn()) return false;
-  if ((K & 7) || K > kMaxK || (N & 31)) return false;
-  if (N > kMaxNc && (N % kMaxNc)) return false;
+  if ((K & 7) || K > kMaxK || (N & 3)) return false;
   if ((ldx & 3) || (ldy & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
   if (rows > 0x7fffffffLL - kRows) return false;
   return rows >= 16384;  // below that the warp-level kernel's shorter set-up wins
@@ -311,12 +314,16 @@ int rows_gemm_tc_launch(const float *x, int ldx, const float *in_scale, const fl
   p.w_sn = w_stride_n; p.w_sk = w_stride_k; p.ldy = ldy; p.K = K; p.N = N;
   p.ntiles = (int)((rows + kRows - 1) / kRows);
   p.nbox = (K + kBoxCols - 1) / kBoxCols;
-  // output columns per CTA: as many as leave a ring of >= 3 boxes next to the weight slice and the output tile (a
-  // narrower slice re-reads X once per slice: K = 256, N = 128 runs as two slices of 64)
-  const size_t budget = 220 * 1024;  // next to ~8 KB of static shared memory and the alignment slack
+  // output columns per CTA (whole 32-column boxes): the fewest slices, then the narrowest slice that covers N with them,
+  // as long as a ring of >= 3 boxes fits next to the weight slice and the output tile (every slice re-reads X: K = 256,
+  // N = 128 runs as two slices of 64).  With batch statistics the slice must divide 256 (thread = column x row part).
+  const size_t budget = 218 * 1024;  // next to ~9 KB of static shared memory and the alignment slack
   long long nring = 0;
-  for (int nc = N < kMaxNc ? N : kMaxNc; nc >= 32; nc >>= 1) {
-    if (N % nc || (nc & 31)) continue;  // whole 32-column boxes
+  const int n32 = (N + 31) & ~31;
+  for (int slices = (n32 + kMaxNc - 1) / kMaxNc; slices <= 8; ++slices) {
+    int nc = (((n32 / 32) + slices - 1) / slices) * 32;  // boxes per slice, rounded up
+    if (stats) { int pw = 32; while (pw < nc) pw <<= 1; nc = pw; }
+    if (nc > kMaxNc || (stats && nc > 128)) continue;
     p.Nc = nc;
     p.w_bytes = (uint32_t)(((size_t)K * nc * 4 + 1023) & ~(size_t)1023);
     p.tile_bytes = (uint32_t)((nc / 32) * kBoxBytes);
@@ -335,10 +342,10 @@ int rows_gemm_tc_launch(const float *x, int ldx, const float *in_scale, const fl
   }
   if (nring > kMaxRing) nring = kMaxRing;
   if (nring < 3) return kRowsGemmTcDeclined;
-  if (256 % p.Nc) return kRowsGemmTcDeclined;  // the statistics pass deals 256 threads as columns x row parts
+  if (stats && (256 % p.Nc)) return kRowsGemmTcDeclined;  // the statistics pass deals 256 threads as columns x row parts
   p.nring = (int)nring;
   const size_t smem = (size_t)p.ring_off + (size_t)p.nring * kBoxBytes + 1024;
-  const int ny = N / p.Nc;
+  const int ny = (N + p.Nc - 1) / p.Nc;
   long long gx = sm_count() / ny;
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;

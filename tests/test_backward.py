@@ -419,7 +419,10 @@ def test_sa_pool_bn_relu_backward_kernels(training, S, C):
                                                       # fewer tiles than SMs, the transposed weight view
                                                       (20000, 40, 64, False, False), (30000, 8, 64, False, False), (100000, 136, 128, False, False),
                                                       (40001, 128, 256, True, False), (16400, 64, 16, True, False),
-                                                      (70000, 128, 64, False, True), (33000, 256, 128, False, True)])
+                                                      (70000, 128, 64, False, True), (33000, 256, 128, False, True),
+                                                      # padded column slices (N = 136 -> one slice of 160, N = 264 -> two), K = 264
+                                                      (40000, 128, 136, False, True), (20000, 264, 128, True, False),
+                                                      (17000, 128, 264, False, True)])
 def test_rows_gemm_kernel(R, K, N, prologue, transpose):
     from eda_b200 import attn_ops as ops
 
