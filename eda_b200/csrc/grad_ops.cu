@@ -388,8 +388,10 @@ int eda_layernorm_backward(const float *dy, const float *u, const float *gamma, 
   if (!aligned16(dy) || !aligned16(u) || !aligned16(du) || (dproj && !aligned16(dproj)) || (gamma && !aligned16(gamma)))
     return EDA_ERR_INVALID_ARGUMENT;
   if (rows * 3 > 0xffffffffLL) return EDA_ERR_UNSUPPORTED;
-  // every block ends with 2 N global atomics onto the same 2 N addresses: few, fat blocks (each warp keeps >= 8 rows)
-  long long blocks = (rows + kLnWarps * 8 - 1) / (kLnWarps * 8);
+  // one row per warp until the chip is full (one block per SM), more rows per warp beyond that: the per-row chain (two
+  // loads, two warp reductions, a store) is pure latency, and the 2 N atomics per block at the end are cheap next to it
+  // (scripts/ln_bwd_time.py: 640 / 2048 / 8192 rows 11.4 / 11.6 / 15.4 us with >= 8 rows per warp, 5.1 / 5.6 / 10.9 us so)
+  long long blocks = (rows + kLnWarps - 1) / kLnWarps;
   const int sms = sm_count();
   if (blocks > sms) blocks = sms;
   if (blocks < 1) blocks = 1;
