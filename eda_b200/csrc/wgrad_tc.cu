@@ -17,7 +17,8 @@
 //   warp 0     one lane: TMA producer, ring of 32-row stages: 4 boxes of dY + ceil(kw / 32) boxes of X per stage
 //   warp 1     MMA issue, whole warp converged (umma::mma4_tf32_ss_w): per stage 4 K steps of 8 rows, each one or two
 //              MMAs of 128 x (<= 256) columns; fp32 accumulators in tensor memory
-//   warps 2-9  round the landed operands to tf32 in place (cvt.rna; the tensor core would truncate), then the epilogue:
+//   warps 2-9  round the landed operands to tf32 in place (cvt.rna; the tensor core would truncate; X optionally through
+//              relu(x * scale[k] + shift[k]) first — the folded BatchNorm + ReLU of the SA layers), then the epilogue:
 //              TMEM -> registers -> red.global.add (v4) into dW; thread = output row
 // The bias gradient (exact fp32 column sums of dY, before rounding) is taken by the rounding warps on the way: a thread
 // meets the same four features of every dY box in every stage, keeps their running sums in registers and adds them into
@@ -44,6 +45,7 @@ constexpr int kTcMaxChunk = 32 * kTcMaxBoxes;
 constexpr int kScratchBytes = kRoundWarps * 32 * kYBoxes * 16;  // bias partials: [warp][lane][box] float4 = 16 KB
 
 struct TcProblem {
+  const float *x_scale, *x_shift;  // optional (K): x is consumed as relu(x * x_scale[k] + x_shift[k])
   float *dw, *db;
   long long rows;
   int ldw;
@@ -89,6 +91,7 @@ wgrad_tc_kernel(const __grid_constant__ TcParams p) {
   unsigned char *ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // swizzle atoms: 1024-byte aligned
   __shared__ __align__(8) uint64_t full[kTcMaxStages], ready[kTcMaxStages], empty[kTcMaxStages], done;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_sc[kTcMaxChunk], s_sh[kTcMaxChunk];  // the prologue's scale / shift of this K chunk
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = umma::uniform_warp_index();
@@ -126,7 +129,14 @@ wgrad_tc_kernel(const __grid_constant__ TcParams p) {
     mbar_fence_init_cluster();
   }
   pdl_launch_dependents();
-  pdl_wait();  // dY / X come from the kernels before this one
+  pdl_wait();  // dY / X (and the folded BatchNorm terms) come from the kernels before this one
+  const bool prologue = pr.x_scale != nullptr;
+  if (prologue)
+    for (int i = tid; i < kTcMaxChunk; i += kTcThreads) {
+      const bool in = i < kw;  // features past the chunk: scale = shift = 0, so the zero-filled columns stay zero
+      s_sc[i] = in ? __ldg(pr.x_scale + k0 + i) : 0.f;
+      s_sh[i] = in ? __ldg(pr.x_shift + k0 + i) : 0.f;
+    }
   umma::fence_before_thread_sync();
   __syncthreads();
   umma::fence_after_thread_sync();
@@ -199,11 +209,26 @@ wgrad_tc_kernel(const __grid_constant__ TcParams p) {
         v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
         st[j * (kBoxBytes / 16)] = v;
       }
+      if (prologue) {
+        // x -> relu(x * scale + shift) on the way (the folded BatchNorm + ReLU of the layer that produced x).  Rows past
+        // the end arrive as zeros and become relu(shift): they meet zero rows of dY, so they add nothing
+        const int feat = ((((rt & 7) >> 1) ^ ((rt >> 3) & 3)) << 3) | ((rt & 1) << 2);  // this thread's 4 features in a box
 #pragma unroll 4
-      for (int j = kYBoxes; j < kYBoxes + nb; ++j) {
-        float4 v = st[j * (kBoxBytes / 16)];
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-        st[j * (kBoxBytes / 16)] = v;
+        for (int j = 0; j < nb; ++j) {
+          const float4 sc = *reinterpret_cast<const float4 *>(s_sc + 32 * j + feat);
+          const float4 sh = *reinterpret_cast<const float4 *>(s_sh + 32 * j + feat);
+          float4 v = st[(kYBoxes + j) * (kBoxBytes / 16)];
+          v.x = to_tf32(fmaxf(fmaf(v.x, sc.x, sh.x), 0.f)); v.y = to_tf32(fmaxf(fmaf(v.y, sc.y, sh.y), 0.f));
+          v.z = to_tf32(fmaxf(fmaf(v.z, sc.z, sh.z), 0.f)); v.w = to_tf32(fmaxf(fmaf(v.w, sc.w, sh.w), 0.f));
+          st[(kYBoxes + j) * (kBoxBytes / 16)] = v;
+        }
+      } else {
+#pragma unroll 4
+        for (int j = kYBoxes; j < kYBoxes + nb; ++j) {
+          float4 v = st[j * (kBoxBytes / 16)];
+          v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+          st[j * (kBoxBytes / 16)] = v;
+        }
       }
       umma::fence_proxy_async_smem();
       __syncwarp();
@@ -306,7 +331,7 @@ bool wgrad_tc_eligible(const eda_wgrad_problem *probs, int nprobs, int N, int K)
   long long max_rows = 0;
   for (int i = 0; i < nprobs; ++i) {
     const eda_wgrad_problem &q = probs[i];
-    if (q.x_scale || q.x_shift) return false;   // BatchNorm + ReLU prologue on X: the warp-level kernel
+    if ((q.x_scale == nullptr) != (q.x_shift == nullptr)) return false;
     if (q.rows <= 0 || q.rows > 0x7fffffffLL - kTcRows) return false;
     if ((q.ldy & 3) || (q.ldx & 3) || (reinterpret_cast<uintptr_t>(q.dy) & 15) || (reinterpret_cast<uintptr_t>(q.x) & 15))
       return false;
@@ -330,6 +355,7 @@ int wgrad_tc_launch(const eda_wgrad_problem *probs, int nprobs, int N, int K, cu
         !make_tensor_map_rows32(&p.map_x[i], q.x, q.rows, K, q.ldx, kTcRows, true))
       return kWgradTcDeclined;
     p.pr[i].dw = q.dw; p.pr[i].db = q.db; p.pr[i].rows = q.rows; p.pr[i].ldw = q.ldw;
+    p.pr[i].x_scale = q.x_scale; p.pr[i].x_shift = q.x_shift;
     p.pr[i].vec = ((q.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(q.dw) & 15) == 0) ? 1 : 0;
     if (q.rows > max_rows) max_rows = q.rows;
   }

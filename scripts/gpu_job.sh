@@ -34,9 +34,10 @@ for step in "$@"; do
       python scripts/ncu_csv_summary.py gpurun_out/${TAG}_sweep_ncu.csv gpurun_out/${TAG}_sweep_ncu.json ;;
     full)
       # one `--set full` capture per roofline kernel (the dominant launch of each), source-correlated
-      for k in linear wgrad fps ballq attention sa_mlp; do
-        case $k in linear) re=linear_kernel;; wgrad) re=wgrad_tc_kernel;; fps) re=fps_cluster_kernel;; ballq) re=ball_query_kernel;; attention) re=attention_kernel;; sa_mlp) re=sa_mlp_kernel;; esac
-        timeout 600 ncu --set full --clock-control none --import-source on -k regex:$re -s 3 -c 1 -f -o gpurun_out/${TAG}_full_$k python scripts/kernels_once.py $k > gpurun_out/${TAG}_full_$k.log 2>&1; echo "full $k rc=$?"
+      for k in linear wgrad rows_gemm fps ballq attention sa_mlp; do
+        cmd="python scripts/kernels_once.py $k"
+        case $k in linear) re=linear_kernel;; wgrad) re=wgrad_tc_kernel;; rows_gemm) re=rows_gemm_tc_kernel; cmd="python scripts/rows_gemm_compare.py";; fps) re=fps_cluster_kernel;; ballq) re=ball_query_kernel;; attention) re=attention_kernel;; sa_mlp) re=sa_mlp_kernel;; esac
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:$re -s 3 -c 1 -f -o gpurun_out/${TAG}_full_$k $cmd > gpurun_out/${TAG}_full_$k.log 2>&1; echo "full $k rc=$?"
       done ;;
     benchlaunches)
       # launch list of the bench command itself (graph replays show up as their kernels)
