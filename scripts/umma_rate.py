@@ -1,6 +1,8 @@
 """Tensor-pipe rate probe: cycles per kind::tf32 MMA (128 x N x 8) for operand sources / layouts; `fresh` = every MMA
 reads new shared-memory addresses (a real K loop), `fixed` = the same descriptors every time, `cycled` = 4 K-steps of one
-tile.  Second table: pairs of MMAs sharing A into two accumulators (the linear kernel's N = 288 = 2 x 144 case)."""
+tile, `4 descriptors ahead` = fresh addresses with the descriptors of four MMAs in distinct registers before the four
+issues (the form umma::mma4_tf32_ss_w gives the production kernels), `warp-converged` = whole warp, uniform datapath, one
+MMA per statement.  Second table: pairs of MMAs sharing A into two accumulators (the linear kernel's N = 288 = 2 x 144 case)."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -19,7 +21,7 @@ iters = 2000
 for N in (144, 256):
     for a_mode, an in ((1, "A tmem"), (2, "A smem swz128")):
         for b_swz in (0, 1):
-            for pre, pn in ((1, "fixed"), (0, "cycled"), (2, "fresh")):
+            for pre, pn in ((1, "fixed"), (0, "cycled"), (2, "fresh"), (3, "fresh, 4 descriptors ahead"), (4, "fresh, warp-converged")):
                 r = run(N, a_mode, b_swz, pre, iters)
                 if r:
                     print(f"N {N:3d} {an:14s} B {'swz128' if b_swz else 'noswz '} {pn:6s}: issue {r[0]:7.1f}  complete {r[1]:7.1f} cycles/MMA")
