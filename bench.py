@@ -550,7 +550,8 @@ def sa_forward_leg(dev, pc_host):
         ms = kn.time_ms(step, 3, 20)
     return {"ms": ms, "value": B_PER_GPU / (ms * 1e-3), "unit": "scenes/s",
             "workload": "configs[1]: SA1(2048,r.2,ns64,[6,64,64,128]) -> SA2(1024,r.4,ns32,[131,128,128,256]) forward, "
-                        "B=8, N=50000, eval-mode BN, device-resident"}
+                        "B=8, N=50000, eval-mode BN, device-resident; launched eagerly from Python (chunk-pipelined sampler, "
+                        "not a graph): host-launch-bound, varies with the host's load"}
 
 
 def main():
