@@ -286,8 +286,9 @@ EDA_API int eda_attention_forward_lse(const float *q, const float *k, const floa
  *   vt (B, H*D, ldv) with v = NULL — no transposed copy is needed then.  delta (B,H,Nq) is scratch (rowsum(dctx * ctx)).  The dropout mask of the forward call
  *   (dropout_p, dropout_seed) is regenerated from the same hash.  Head dims compiled: D in {32, 36}.
  * eda_wgrad: for every problem i, dw_i (N, K; row stride ldw) += dy_i (rows, N; ldy)^T x_i (rows, K; ldx) and, when db_i
- *   is not NULL, db_i (N) += column sums of dy_i.  ACCUMULATES (atomics): zero the outputs first.  N, K, ldy, ldx
- *   multiples of 4, dy / x 16-byte aligned.  Up to 6 problems of one (N, K) per launch.
+ *   is not NULL, db_i (N) += column sums of dy_i.  ACCUMULATES (atomics / TMA bulk reductions): zero the outputs first.
+ *   N, K, ldy, ldx multiples of 4, dy / x 16-byte aligned.  Up to 6 problems of one (N, K) per launch.  From 3000 rows in
+ *   total (N >= 64, K >= 32) the tcgen05 kernel runs (operands by TMA as they lie in memory), else warp-level mma.sync.
  * eda_layernorm_backward: y = LayerNorm(u) * gamma + beta over the last dim N (<= 384, multiple of 4).  Writes
  *   du (rows, N); dgamma / dbeta (N) are ACCUMULATED (may be NULL).  With dropout_p > 0 also writes
  *   dproj = du * keep / (1 - p), the gradient of the GEMM output that eda_linear_forward(dropout_p, dropout_seed)
@@ -371,7 +372,9 @@ EDA_API int eda_dropout_apply(const float *x, unsigned int seed, const unsigned 
 /* eda_rows_gemm: y (rows, N; row stride ldy) = f(x) (rows, K; ldx) W'^T with W'[n][k] = w[n * w_stride_n + k * w_stride_k]
  * (so a row-major (N, K) weight is (K, 1), and its use as dX = dY W is (1, ld)) and f(x) = x, or
  * relu(x * in_scale[k] + in_shift[k]) when in_scale / in_shift are given.  K, N multiples of 8, K <= 288; tf32 operands,
- * fp32 accumulation.  Persistent row-streaming kernel for the 10^5 - 10^6-row GEMMs of the SA backward pass. */
+ * fp32 accumulation.  Persistent row-streaming kernels for the 10^5 - 10^6-row GEMMs of the SA stage: tcgen05 with
+ * TMA-fed operands and TMA tile stores from 16 384 rows (x, y 16-byte aligned, ldx, ldy multiples of 4), warp-level
+ * mma.sync below that. */
 EDA_API int eda_rows_gemm(const float *x, int ldx, const float *in_scale, const float *in_shift, const float *w,
                           long long w_stride_n, long long w_stride_k, long long rows, int K, int N, float *y, int ldy,
                           void *stream);
