@@ -48,9 +48,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);// m_dim
 }
 
-// Same, B operand MN-major ("transposed": shared memory holds, per 16-byte unit, 4 consecutive N
-// elements of one k; 8 consecutive k are contiguous (128 B); descriptor SBO = byte distance between
-// 4-element N groups, LBO = byte distance between 8-k groups).
+// Same, B operand MN-major ("transposed").  Measured on B200 (scripts/probe_umma_mn.py): kind::tf32 reads MN-major
+// operands only in the 128-byte swizzle with 32-byte atoms (descriptor layout type 1: 128-byte rows of 32 consecutive
+// MN elements per k, 32-byte units XOR (k & 3), 4 k rows per 512-byte group = SBO, next 32 MN elements = LBO) —
+// the no-swizzle and 16-byte-atom layouts return zeros.  See csrc/wgrad_tc.cu for the user.
 __host__ __device__ constexpr uint32_t idesc_tf32_bmn(int M, int N) { return idesc_tf32(M, N) | (1u << 16); }
 
 // ---- Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS): many in flight, no registers.

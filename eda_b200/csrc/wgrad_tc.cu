@@ -6,8 +6,8 @@
 // column reduction per weight.
 //
 // The contraction index is the ROW of both row-major operands, so both are "MN-major" for the tensor core.  For 32-bit
-// operands the tensor core reads MN-major tiles only in the no-swizzle layout or in "128-byte swizzle with 32-byte atoms"
-// (UMMA layout type 1; types 2 / 4 / 6 return zeros — scripts/probe_umma_mn.py): one 128-byte row per contraction index
+// operands the tensor core reads MN-major tiles only in the "128-byte swizzle with 32-byte atoms" layout (UMMA layout
+// type 1; types 0 / 2 / 4 / 6 return zeros — scripts/probe_umma_mn.py): one 128-byte row per contraction index
 // holding 32 consecutive features, its four 32-byte units XOR-swizzled by (row & 3), four rows = one 512-byte group, the
 // next 32 features one box further.  That is exactly what a 2-D TMA box of 32 rows x 32 columns with
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B puts into shared memory.  No transposition, no per-thread staging: dY and X tiles

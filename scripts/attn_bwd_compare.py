@@ -1,5 +1,5 @@
 """Attention backward: warp-level mma.sync kernel vs the tcgen05 kernel on the step's four attention shapes (device time,
-back-to-back launches; the tc path's transposes / channel-major copies are inside its time)."""
+CUDA-graph replay of back-to-back calls; the tc path's transposes / channel-major copies are inside its time)."""
 import os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from eda_b200 import attn_ops as ops
@@ -14,10 +14,10 @@ for name, Nq, Nk in (("vis_self", 1024, 1024), ("cross_v", 256, 1024), ("cross_v
     vt = r(B, E, ld); dctx = r(B * Nq, E)
     lse = torch.empty(B, H, Nq, device=dev)
     c = ops.attention_raw(q, k, vt, None, B, Nq, Nk, H, lse=lse)
-    fwd = time_ms(lambda: ops.attention_raw(q, k, vt, None, B, Nq, Nk, H, lse=lse))
+    fwd = time_ms(lambda: ops.attention_raw(q, k, vt, None, B, Nq, Nk, H, lse=lse), 3, 10, graph=True)
     out = {}
     for impl in ("mma", "tc"):
-        out[impl] = time_ms(lambda: ops.attention_backward_raw(q, k, vt, dctx, c, lse, None, B, Nq, Nk, H, impl=impl))
+        out[impl] = time_ms(lambda: ops.attention_backward_raw(q, k, vt, dctx, c, lse, None, B, Nq, Nk, H, impl=impl), 3, 10, graph=True)
     a = ops.attention_backward_raw(q, k, vt, dctx, c, lse, None, B, Nq, Nk, H, impl="mma")
     b = ops.attention_backward_raw(q, k, vt, dctx, c, lse, None, B, Nq, Nk, H, impl="tc")
     err = max(float((x - y).abs().max() / x.abs().max()) for x, y in zip(a, b))
