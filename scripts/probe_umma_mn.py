@@ -9,7 +9,7 @@ def probe(N, lbo, sbo, mn, layout, off):
     rc = lib.eda_selftest_umma_probe(N, lbo, sbo, mn, layout, off, ctypes.c_void_p(D.data_ptr()), None)
     _lib.check(rc, "probe"); torch.cuda.synchronize()
     return D.cpu().int()
-for layout, lbo, sbo in ((1, 4096, 1024), (1, 1024, 4096), (0, 128, 2048), (2, 4096, 1024), (4, 4096, 1024), (6, 4096, 1024)):
+for layout, lbo, sbo in ((1, 4096, 1024), (1, 1024, 4096), (0, 128, 1024), (2, 4096, 1024), (4, 4096, 1024), (6, 4096, 1024)):
     N = 64
     D = probe(N, lbo, sbo, 1, layout, 0)
     print(f"MN-major layout={layout} lbo={lbo} sbo={sbo}: rows k=0..7, cols n=0..{N-1}")
