@@ -16,5 +16,7 @@ for layout, lbo, sbo in ((1, 4096, 1024), (1, 1024, 4096), (0, 128, 1024), (2, 4
     for k in range(8):
         print("  k=%d:" % k, " ".join("%4d" % v for v in D[k].tolist()))
     if layout == 1:
-        exp = [[(n // 32) * (lbo // 4) + k * 32 + ((((n % 32) >> 3) ^ (k & 3)) * 8) + n % 8 for n in range(N)] for k in range(8)]
-        print("  matches box model with 32-byte atoms (unit (n%32)/8 ^ (k&3)):", D.tolist() == exp)
+        exp = [[(n // 32) * (lbo // 4) + (k // 4) * (sbo // 4) + (k % 4) * 32 + ((((n % 32) >> 3) ^ (k & 3)) * 8) + n % 8
+                for n in range(N)] for k in range(8)]
+        print("  matches: 32 MN elements per 128-byte row, 32-byte units XOR (k & 3), 4 k rows per group (SBO), next 32 MN at LBO:",
+              D.tolist() == exp)
