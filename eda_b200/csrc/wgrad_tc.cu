@@ -240,7 +240,9 @@ wgrad_tc_kernel(const __grid_constant__ TcParams p) {
     __syncwarp();
     WG_TS(4, 64);
     if (want_db) {
-      // all MMAs have completed: the ring is free.  Partials -> ring[warp][lane][box], then thread f < 128 adds up the
+      // all MMAs have completed: the ring is free (every rounding warp's last write precedes its last `ready` arrival,
+      // which precedes the final commit onto `done` — an mbarrier chain; compute-sanitizer's racecheck, which only
+      // follows bar.sync, reports these writes against the loop's as hazards).  Partials -> ring[warp][lane][box], then thread f < 128 adds up the
       // 8 warps x 4 lanes that met feature f (lane = (row & 3) * 8 + chunk position; shared-memory float atomics would
       // be 32-way contended compare-and-swap loops)
       float4 *scratch = reinterpret_cast<float4 *>(ring);
