@@ -374,7 +374,11 @@ int wgrad_tc_launch(const eda_wgrad_problem *probs, int nprobs, int N, int K, cu
   // 32-row stages each
   const long long units = (long long)p.ntiles * p.kchunks * nprobs;
   const long long chunks = (max_rows + kTcRows - 1) / kTcRows;
-  long long splits = sm_count() / units;
+  // EDA_WGRAD_TC_SMS caps the CTAs of one launch (measurements: the kernel runs on a side stream next to the step's
+  // critical path, whose kernels cannot share an SM with a 200 KB CTA)
+  static const int sm_cap = [] { const char *e = getenv("EDA_WGRAD_TC_SMS"); return e ? atoi(e) : 0; }();
+  const int sm_budget = (sm_cap > 0 && sm_cap < sm_count()) ? sm_cap : sm_count();
+  long long splits = sm_budget / units;
   if (splits > chunks / 2) splits = chunks / 2;
   if (splits < 1) splits = 1;
   p.splits = (int)splits;
