@@ -2,7 +2,6 @@
 (tests/golden/umma_probe_b200.txt = profiles/r2_probe_umma.txt, produced on a B200 by scripts/probe_umma_mn.py: a one-MMA probe whose result is the
 shared-memory float index read as B(n, k)).  CPU only: the probe output is a committed fixture."""
 import os
-import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PROBE = os.path.join(HERE, "golden", "umma_probe_b200.txt")  # a copy of profiles/r2_probe_umma.txt
